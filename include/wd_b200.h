@@ -1,0 +1,209 @@
+/*
+ * wd_b200.h — C-ABI of libwd_b200.so: the B200-native Wide&Deep CTR train/eval step.
+ *
+ * The reference (Lapis-Hong/wide_deep) has no native plugin/FFI boundary: its seam is the Python-level
+ * estimator object built by build_custom_estimator (reference python/lib/build_estimator.py:264-294) whose
+ * .train/.evaluate/.predict run TensorFlow's model_fn (reference python/lib/joint.py:81-269).  This header
+ * is the boundary a maintainer binds instead of TensorFlow; each entry point cites what it replaces.
+ *
+ * Conventions: plain C, plain pointers and sizes; every function returns 0 on success or a negative
+ * WD_E* code (never throws; wd_last_error() holds the message); the caller owns host buffers, the
+ * library owns all device memory; one host thread drives one WdModel; handles are not thread-safe.
+ * All device work is enqueued on the model's stream; functions that return host data synchronise it.
+ * There is NO CPU fallback: every compute entry point fails with WD_ENODEVICE without a CUDA device.
+ */
+#ifndef WD_B200_H_
+#define WD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WD_API_VERSION 1
+
+enum { WD_OK = 0, WD_EINVAL = -1, WD_ENODEVICE = -2, WD_ECUDA = -3, WD_ENOMEM = -4, WD_EUNSUPPORTED = -5, WD_ESTATE = -6 };
+
+/* categorical column kinds (reference python/lib/build_estimator.py:83-158) */
+enum { WD_COL_HASH = 0, WD_COL_VOCAB = 1, WD_COL_IDENTITY = 2, WD_COL_BUCKET = 3, WD_COL_CROSS = 4 };
+/* continuous normalisers (reference python/lib/build_estimator.py:61-68) */
+enum { WD_NORM_NONE = 0, WD_NORM_MINMAX = 1, WD_NORM_STANDARD = 2, WD_NORM_LOG = 3 };
+/* cross key sources: raw string field (dense input incl. padding) or a categorical column (sparse input) */
+enum { WD_KEY_FIELD = 0, WD_KEY_COLUMN = 1 };
+/* optimizers (reference python/lib/utils/model_util.py:62-105) */
+enum { WD_OPT_SGD = 0, WD_OPT_ADAGRAD = 1, WD_OPT_FTRL = 2 };
+/* activations (reference python/lib/utils/model_util.py:28-59) */
+enum { WD_ACT_RELU = 0, WD_ACT_RELU6, WD_ACT_SIGMOID, WD_ACT_TANH, WD_ACT_LEAKY_RELU, WD_ACT_ELU, WD_ACT_SELU,
+       WD_ACT_SOFTPLUS, WD_ACT_SOFTSIGN };
+/* dnn_connected_mode (reference python/lib/dnn.py:92-193) */
+enum { WD_MODE_SIMPLE = 0, WD_MODE_FIRST_DENSE, WD_MODE_LAST_DENSE, WD_MODE_DENSE, WD_MODE_RESNET };
+/* GEMM engine for the MLP */
+enum { WD_GEMM_AUTO = 0, WD_GEMM_FFMA = 1, WD_GEMM_TC3X = 2 /* tcgen05 kind::tf32, 3-pass split */,
+       WD_GEMM_TC1X = 3 /* tcgen05 kind::tf32 single pass: fast, NOT within the 1e-4 parity bar */ };
+
+typedef struct WdOptimizer {
+    int32_t kind;        /* WD_OPT_* */
+    float lr, l1, l2, lr_power, init_acc;
+} WdOptimizer;
+
+/* Immutable description of the model, produced by wide_deep_b200.plan.compile_plan() from conf/*.yaml.
+ * Replaces the feature-column lists of _build_model_columns (reference build_estimator.py:49-169). */
+typedef struct WdPlanDesc {
+    int32_t api_version;
+    int32_t model_type;             /* bit0: wide part, bit1: deep part */
+    int32_t n_cat_fields;           /* key fields of a batch (string features as uint64 fingerprints, identity as ints) */
+    int32_t n_dense_fields;         /* continuous fields */
+    const uint8_t *cat_field_is_string; /* [n_cat_fields] 1: fingerprints (Fingerprint64("") marks ''), 0: int ids */
+
+    int32_t n_columns;              /* categorical columns, in evaluation order */
+    const int32_t *col_kind;        /* WD_COL_* */
+    const int32_t *col_field;       /* cat field (HASH/VOCAB/IDENTITY) | dense field (BUCKET) | -1 */
+    const int64_t *col_buckets;     /* id range of the column */
+    const int32_t *col_aux_off;     /* VOCAB: into vocab_fp; BUCKET: into boundaries; CROSS: into cross_key_* */
+    const int32_t *col_aux_n;
+    const int32_t *col_norm_kind;   /* BUCKET: normaliser applied before bucketising (quirk Q3) */
+    const float *col_norm_a, *col_norm_b;
+    const int64_t *col_wide_base;   /* first row in the wide table, -1: not a wide column */
+    const int32_t *col_emb_table;   /* embedding table fed by this column, -1: none */
+    const int32_t *col_ind_off;     /* indicator (multi-hot count) offset in the deep input, -1: none */
+    const uint64_t *vocab_fp;       int32_t n_vocab_fp;
+    const float *boundaries;        int32_t n_boundaries;
+    const int32_t *cross_key_type;  /* WD_KEY_*; keys of each cross are stored in OP order */
+    const int32_t *cross_key_idx;   int32_t n_cross_keys;
+
+    int32_t n_tables;               /* embedding tables (combiner = mean) */
+    const int64_t *table_rows;
+    const int32_t *table_dim;       /* physical width: logical width padded to a multiple of 4 (pad columns stay 0) */
+    const int32_t *table_dim_logical; /* embedding_column dimension (reference build_estimator.py:57-59) */
+    const int32_t *table_x0_off;    /* physical column offset in the deep input, multiple of 4 */
+    int32_t n_numeric;              /* numeric deep columns */
+    const int32_t *num_field, *num_norm_kind, *num_x0_off;
+    const float *num_norm_a, *num_norm_b;
+    int32_t d0_phys;                /* physical width of the deep input (multiple of 32; padding columns stay 0) */
+    int64_t wide_rows;              /* total rows of the wide weight table */
+
+    int32_t n_towers;
+    const int32_t *tower_nlayers;   /* hidden layers per tower */
+    const int32_t *tower_mode;      /* WD_MODE_* */
+    const int32_t *hidden_units;    /* concatenated over towers */
+    int32_t activation;             /* WD_ACT_* */
+    int32_t batch_norm;             /* inference-mode affine gamma/sqrt(1+1e-3), beta (quirk Q4) */
+    WdOptimizer lin_opt, dnn_opt;
+    int32_t max_batch;              /* rows per step this handle must accept */
+    int64_t max_nnz;                /* upper bound on categorical-column ids per step (0: derive) */
+    int64_t max_keys;               /* upper bound on batch keys per step (0: derive) */
+    int32_t gemm_engine;            /* WD_GEMM_* */
+} WdPlanDesc;
+
+/* One batch in HOST memory (pinned for async copies).  Replaces the feature dict produced by input_fn
+ * (reference python/lib/dataset.py:293-310): CSR over (row, cat field), row-major. */
+typedef struct WdBatch {
+    int32_t batch_size;
+    const int32_t *cat_offsets;     /* [batch_size*n_cat_fields+1], NULL: exactly one key per (row, field) */
+    const uint64_t *cat_keys;       /* [nnz] fingerprints / ints */
+    int64_t nnz;
+    const float *dense;             /* [batch_size*n_dense_fields] */
+    const float *label;             /* [batch_size] 0/1, NULL for predict */
+    const float *weight;            /* [batch_size] example weights, NULL = 1 (weight_column, dataset.py:159-163) */
+} WdBatch;
+
+typedef struct WdModel WdModel;
+
+/* tensor selectors for wd_tensor_io */
+enum { WD_T_WIDE_COL = 0, WD_T_EMB_TABLE = 1, WD_T_DENSE = 2, WD_T_WIDE_BIAS = 3 };
+/* dense tensor ids: tower t, layer l (l == nlayers: logits): see wd_dense_tensor_id */
+enum { WD_D_KERNEL = 0, WD_D_BIAS = 1, WD_D_GAMMA = 2, WD_D_BETA = 3 };
+
+const char *wd_last_error(void);
+int wd_version(void);
+int wd_device_count(void);
+
+/* Model lifetime.  Replaces WideAndDeepClassifier.__init__ (reference python/lib/joint.py:326-432). */
+int wd_model_create(const WdPlanDesc *plan, int device, WdModel **out);
+int wd_model_destroy(WdModel *m);
+/* Device-side initialisation with the TF initialisers (truncated normal / glorot uniform / zeros). */
+int wd_model_init(WdModel *m, uint64_t seed);
+/* Copy a parameter or optimizer slot to/from host.  slot 0 = value, 1.. = optimizer accumulators
+ * (Adagrad: acc; FTRL: n, z).  Logical (unpadded) shapes; kernels are [in, out] like tf.layers.dense. */
+int wd_tensor_io(WdModel *m, int kind, int index, int sub, int slot, void *host, int64_t count, int to_device);
+int64_t wd_tensor_size(WdModel *m, int kind, int index, int sub);
+
+/* One training step: H2D copy, ids, forward, loss, backward, optimizers.  Replaces one
+ * sess.run(train_op) of Estimator.train (reference python/train.py:128-133; joint.py:224-262).
+ * loss_out (nullable): sum-reduced sigmoid cross entropy of this batch (joint.py:404-406). */
+int wd_train_step(WdModel *m, const WdBatch *batch, float *loss_out);
+/* Forward only: logits[batch_size].  Replaces Estimator.predict / the forward half of evaluate. */
+int wd_forward(WdModel *m, const WdBatch *batch, float *logits_out, float *loss_out);
+
+/* Device-resident variants used by bench.py's `value` and by multi-GPU: upload once, then step on the
+ * resident batch (the e2e number uses wd_train_step with host buffers). */
+int wd_batch_upload(WdModel *m, const WdBatch *batch);
+int wd_train_step_resident(WdModel *m, float *loss_out);
+int wd_forward_resident(WdModel *m, float *logits_out, float *loss_out);
+
+/* Split step for data-parallel training (multi-GPU): phase 1 computes gradients and leaves
+ *   dense grads  : device float[wd_dense_grad_count]  (to be sum-allreduced, joint.py loss is a SUM)
+ *   sparse grads : unique rows + summed grads for the embedding and the wide tables
+ * phase 2 applies the optimizers.  wd_sparse_* expose the device buffers for the exchange. */
+int wd_step_backward(WdModel *m, const WdBatch *batch_or_null, float *loss_out);
+int wd_step_apply(WdModel *m);
+int64_t wd_dense_grad_count(WdModel *m);
+void *wd_dense_grad_ptr(WdModel *m);          /* device pointer */
+/* Sparse gradient lists after wd_step_backward.  which: 0 = embedding rows, 1 = wide rows.
+ * rows: device uint32[n] global row ids (sorted unique), grads: device float[n*width] (width 1 for wide,
+ * max table dim for embeddings, rows of narrower tables are zero padded). */
+int wd_sparse_grads(WdModel *m, int which, void **rows, void **grads, int64_t *n, int32_t *width, int64_t *capacity);
+/* Replace the sparse gradient list by a merged one (rows need not be unique or sorted). */
+int wd_sparse_set(WdModel *m, int which, const void *rows_dev, const void *grads_dev, int64_t n);
+
+/* Streaming eval metrics (binary head, reference joint.py:402-406): accumulate per batch, then finish.
+ * out[0..9] = accuracy, accuracy_baseline, auc, auc_precision_recall, average_loss, label/mean, loss,
+ *             precision, prediction/mean, recall. */
+int wd_eval_reset(WdModel *m);
+int wd_eval_accumulate(WdModel *m, const WdBatch *batch);
+int wd_eval_finish(WdModel *m, double *out10);
+
+/* Stand-alone integer kernels (device), exposed so parity tests can check them bit-exactly:
+ * Fingerprint64 over byte strings; hash-bucket; SparseCross chain. */
+int wd_fingerprint64_device(const uint8_t *bytes, const int64_t *offsets, int64_t n, uint64_t *out);
+/* Host implementations used by the TSV loader (same source, compiled for the host). */
+uint64_t wd_fingerprint64(const uint8_t *bytes, size_t n);
+uint64_t wd_fingerprint_cat64(uint64_t a, uint64_t b);
+
+/* Column ids of the last uploaded/stepped batch, for parity tests: CSR over (row, column). */
+int wd_debug_column_ids(WdModel *m, int32_t *offsets_out, int64_t offsets_cap, int64_t *ids_out, int64_t ids_cap, int64_t *nnz_out);
+/* Deep input matrix of the last forward: [batch, d0_phys]. */
+int wd_debug_deep_input(WdModel *m, float *out, int64_t cap);
+/* Kernel launch counter (launches of this library's kernels since creation). */
+int64_t wd_launch_count(WdModel *m);
+/* Per-phase device timings of the last step in milliseconds (CUDA events on the model stream):
+ * [0] h2d [1] ids [2] gather+wide fwd [3] mlp fwd+loss [4] mlp bwd [5] sparse bwd [6] dense opt [7] total */
+int wd_last_timings(WdModel *m, float *out8);
+int wd_set_profile(WdModel *m, int enable);
+void *wd_stream(WdModel *m);
+int wd_sync(WdModel *m);
+
+/* TSV loader (host, multi-threaded).  Replaces _CsvDataset._parse_csv (reference python/lib/dataset.py:107-165):
+ * parses `n_lines` tab-separated records into the WdBatch CSR arrays. */
+typedef struct WdTsvSpec {
+    int32_t n_columns;              /* columns per record incl. label when has_label */
+    const int32_t *col_role;        /* per file column: -1 skip, 0 label, 1 string cat field, 2 int cat field, 3 dense */
+    const int32_t *col_target;      /* field index for roles 1,2,3 */
+    int32_t n_cat_fields, n_dense_fields;
+    int32_t multivalue;             /* split string fields on ',' and drop empty tokens */
+    int32_t tf_compat_pad;          /* quirk Q2: pad string fields to the batch max length with Fingerprint64("") */
+    float pos_weight, neg_weight;   /* used when use_weight */
+    int32_t use_weight;
+    int32_t has_label;
+} WdTsvSpec;
+/* Returns nnz, or negative error.  Two-call protocol: keys_cap==0 -> only counts (offsets filled). */
+int64_t wd_tsv_parse(const WdTsvSpec *spec, const char *text, int64_t text_len, int32_t n_lines,
+                     int32_t *offsets_out, uint64_t *keys_out, int64_t keys_cap,
+                     float *dense_out, float *label_out, float *weight_out, int32_t n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WD_B200_H_ */

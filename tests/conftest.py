@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """libwd_b200.so, built in-tree if missing (nvcc cross-compiles without a GPU)."""
+    import build_native
+    build_native.build(verbose=False)
+    from wide_deep_b200 import _native
+    return _native.lib()

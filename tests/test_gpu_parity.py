@@ -1,0 +1,204 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): hashed-cross ids and bucketised ids BIT-EXACT; fp32 logits within 1e-4
+relative.  "Relative" is implemented as |gpu - oracle| <= 1e-4 * max(|oracle|, 1) for logits (the head adds
+O(1) terms, logits near zero have no meaningful relative error), and the same bound scaled by the tensor's
+max magnitude for parameters after training steps.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from oracle import model as OM
+from tests.helpers import copy_params_to_product, random_raw_batch, to_product_batch
+from wide_deep_b200.model import WideDeepModel
+from wide_deep_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def small_conf(hidden=(64, 32), mode="simple", act="relu", bn=1, dnn_opt="Adagrad",
+               lin_opt="tf.train.FtrlOptimizer(learning_rate=0.1,l1_regularization_strength=0.5,l2_regularization_strength=1)"):
+    fc = OrderedDict()
+    fc["h1"] = dict(type="category", transform="hash_bucket", parameter=1000)
+    fc["h2"] = dict(type="category", transform="hash_bucket", parameter=37)
+    fc["h3"] = dict(type="category", transform="hash_bucket", parameter=200000)
+    fc["v1"] = dict(type="category", transform="vocab", parameter=[0, 1, 2, 3, 4])
+    fc["v2"] = dict(type="category", transform="vocab", parameter=["male", "female"])
+    fc["id1"] = dict(type="category", transform="identity", parameter=15)
+    fc["x1"] = dict(type="continuous", transform="min_max", parameter=dict(normalization=[10, 90], boundaries=[15, 20, 25, 30, 35, 40, 45, 50]))
+    fc["x2"] = dict(type="continuous", transform="standard", parameter=dict(normalization=[40.0, 30.0], boundaries=[-1, 0, 1]))
+    fc["x3"] = dict(type="continuous", transform=None, parameter=dict(normalization=None, boundaries=None))
+    cross = [(["h1", "h2"], 1000, 1), (["h1", "x1"], 500, 1), (["id1", "x1", "v2"], 100, 1), (["v1", "h3"], 2000, 0),
+             (["h2", "id1"], 300, 1)]
+    model = dict(linear_optimizer=lin_opt, linear_initial_learning_rate=0.05, dnn_hidden_units=list(hidden),
+                 dnn_connected_mode=mode, dnn_optimizer=dnn_opt, dnn_initial_learning_rate=0.05,
+                 dnn_activation_function=act, dnn_dropout=None, dnn_batch_normalization=bn)
+    return fc, cross, model
+
+
+def build_pair(fc, cross, model, model_type="wide_deep", B=96, seed=0, tf_compat_pad=False, emb_dim=None, max_batch=None):
+    om = OM.OracleModel(fc, cross, model, model_type, embedding_dim_override=emb_dim, tf_compat_pad=tf_compat_pad).init(seed)
+    plan = Plan(fc, cross, model, model_type, max_batch=max_batch or B, embedding_dim_override=emb_dim,
+                tf_compat_pad=tf_compat_pad, max_nnz=(max_batch or B) * 64, max_keys=(max_batch or B) * 64, gemm_engine="ffma")
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    return om, plan, pm
+
+
+def check_ids(om, plan, pm, raw, B):
+    offs, ids = pm.column_ids()
+    ref = om.transform(raw)
+    C = len(plan.columns)
+    checked = 0
+    for ci, col in enumerate(plan.columns):
+        if col.name not in ref:
+            continue
+        ro, ri = ref[col.name]
+        for b in range(B):
+            s, e = offs[b * C + ci], offs[b * C + ci + 1]
+            got = ids[s:e]
+            exp = ri[ro[b]:ro[b + 1]]
+            assert np.array_equal(got, exp), "column %s row %d: gpu %s oracle %s" % (col.name, b, got, exp)
+        checked += 1
+    assert checked >= len(om.wide_cols) if om.use_wide else checked > 0
+
+
+@pytest.mark.parametrize("tf_compat_pad", [False, True])
+def test_column_ids_bit_exact(tf_compat_pad):
+    fc, cross, model = small_conf()
+    rng = np.random.default_rng(1)
+    B = 96
+    om, plan, pm = build_pair(fc, cross, model, B=B, tf_compat_pad=tf_compat_pad)
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    pm.forward(to_product_batch(plan, raw, label, tf_compat_pad=tf_compat_pad))
+    check_ids(om, plan, pm, raw, B)
+
+
+@pytest.mark.parametrize("mode", ["simple", "first_dense", "last_dense", "dense", "resnet"])
+@pytest.mark.parametrize("model_type", ["wide_deep", "deep", "wide"])
+def test_forward_logits(mode, model_type):
+    if model_type == "wide" and mode != "simple":
+        pytest.skip("wide has no towers")
+    fc, cross, model = small_conf(hidden=(64, 48, 32), mode=mode)
+    rng = np.random.default_rng(2)
+    B = 200
+    om, plan, pm = build_pair(fc, cross, model, model_type, B=B, seed=3)
+    # give the zero-initialised wide weights some signal
+    if om.use_wide:
+        for c in om.wide_cols:
+            om.params[om.wname(c)][:] = rng.standard_normal(c.num_buckets).astype(np.float32) * 0.1
+        copy_params_to_product(om, pm)
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    logits, loss = pm.forward(to_product_batch(plan, raw, label))
+    ref, cache = om.forward(raw)
+    np.testing.assert_array_less(np.abs(logits - cache["logits"]), RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+    ref_loss = om.loss(cache["logits"], label)
+    assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0)
+    if om.use_deep:
+        X = pm.deep_input(B)
+        for name, (lo, po, w) in plan.deep_layout.items():
+            np.testing.assert_allclose(X[:, po:po + w], cache["X"][:, lo:lo + w], rtol=1e-5, atol=1e-6, err_msg=name)
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", "elu", "selu", "softplus", "softsign", "leaky_relu", "relu6"])
+def test_activations_train(act):
+    fc, cross, model = small_conf(hidden=(32, 32), act=act)
+    _train_compare(fc, cross, model, "wide_deep", steps=2, seed=5)
+
+
+@pytest.mark.parametrize("mode", ["simple", "first_dense", "last_dense", "dense", "resnet"])
+def test_train_steps_modes(mode):
+    fc, cross, model = small_conf(hidden=(64, 48, 32), mode=mode)
+    _train_compare(fc, cross, model, "wide_deep", steps=3, seed=7)
+
+
+@pytest.mark.parametrize("model_type,dnn_opt,lin_opt,bn", [
+    ("deep", "Adagrad", "Ftrl", 0),
+    ("wide", "Adagrad", "Ftrl", 1),
+    ("wide_deep", "tf.train.GradientDescentOptimizer(learning_rate=0.00002)", "Adagrad", 1),
+    ("wide_deep", "tf.train.FtrlOptimizer(learning_rate=0.05,l1_regularization_strength=0.001,l2_regularization_strength=0.01)", "SGD", 1),
+    ("wide_deep", "Adagrad", "tf.train.FtrlOptimizer(learning_rate=0.1,l1_regularization_strength=0.5,l2_regularization_strength=1)", 1),
+])
+def test_train_steps_optimizers(model_type, dnn_opt, lin_opt, bn):
+    fc, cross, model = small_conf(hidden=(64, 32), dnn_opt=dnn_opt, lin_opt=lin_opt, bn=bn)
+    _train_compare(fc, cross, model, model_type, steps=3, seed=11)
+
+
+def test_multi_tower():
+    fc, cross, model = small_conf()
+    model["dnn_hidden_units"] = [[64, 32], [48, 16, 8]]
+    model["dnn_connected_mode"] = ["simple", "dense"]
+    _train_compare(fc, cross, model, "wide_deep", steps=2, seed=13)
+
+
+def test_weighted_examples_and_ragged_batch():
+    fc, cross, model = small_conf()
+    _train_compare(fc, cross, model, "wide_deep", steps=2, seed=17, weighted=True, B=77, max_batch=128)
+
+
+def _train_compare(fc, cross, model, model_type, steps, seed, weighted=False, B=160, max_batch=None):
+    rng = np.random.default_rng(seed)
+    om, plan, pm = build_pair(fc, cross, model, model_type, B=B, seed=seed, max_batch=max_batch)
+    for step in range(steps):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        weight = (rng.random(B).astype(np.float32) + 0.5) if weighted else None
+        loss = pm.train_step(to_product_batch(plan, raw, label, weight))
+        ref_loss, _ = om.train_step(raw, label, weight)
+        assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    # parameters and optimizer state after the steps
+    for name in pm.tensor_names():
+        got, exp = pm.get_tensor(name), om.params[name]
+        scale = max(float(np.abs(exp).max()), 1e-3)
+        assert np.max(np.abs(got - exp)) <= 2e-4 * scale, "%s: max abs diff %g (scale %g)" % (name, np.max(np.abs(got - exp)), scale)
+        for si, key in enumerate([k for k in ("acc", "n", "z") if k in om.slots[name]]):
+            g2, e2 = pm.get_tensor(name, slot=si + 1), om.slots[name][key]
+            sc = max(float(np.abs(e2).max()), 1e-3)
+            assert np.max(np.abs(g2 - e2)) <= 5e-4 * sc, "%s slot %s" % (name, key)
+    # and a fresh forward agrees
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    logits, _ = pm.forward(to_product_batch(plan, raw, label))
+    _, cache = om.forward(raw)
+    np.testing.assert_array_less(np.abs(logits - cache["logits"]), 5 * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+
+
+def test_run_to_run_bit_reproducible():
+    fc, cross, model = small_conf()
+    rng = np.random.default_rng(23)
+    B = 128
+    raws = [(random_raw_batch(fc, B, rng), (rng.random(B) < 0.3).astype(np.float32)) for _ in range(3)]
+    outs = []
+    for _ in range(2):
+        om, plan, pm = build_pair(fc, cross, model, B=B, seed=29)
+        for raw, label in raws:
+            pm.train_step(to_product_batch(plan, raw, label))
+        outs.append({n: pm.get_tensor(n) for n in pm.tensor_names()})
+        pm.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n]), n
+
+
+def test_eval_metrics():
+    from oracle.metrics import EvalAccumulator
+    fc, cross, model = small_conf()
+    rng = np.random.default_rng(31)
+    B = 150
+    om, plan, pm = build_pair(fc, cross, model, B=B, seed=37)
+    acc = EvalAccumulator()
+    pm.eval_reset()
+    for _ in range(3):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.4).astype(np.float32)
+        pm.eval_accumulate(to_product_batch(plan, raw, label))
+        _, cache = om.forward(raw)
+        acc.update(cache["logits"].astype(np.float32), label)
+    got, exp = pm.eval_finish(), acc.result()
+    for k in exp:
+        assert abs(got[k] - exp[k]) <= 2e-4 * max(abs(exp[k]), 1.0), "%s: %g vs %g" % (k, got[k], exp[k])

@@ -1,0 +1,775 @@
+// C-ABI of libwd_b200 (include/wd_b200.h): model construction from the compiled plan, parameter IO,
+// and the orchestration of one train / forward / eval step on the model's stream.
+//
+// A step replaces one sess.run(train_op) of the reference's Estimator.train loop (reference
+// python/train.py:128-133 -> joint.py:81-269): ids -> sparse forward -> towers -> head -> backward ->
+// optimizers.  Nothing here falls back to the CPU: without a CUDA device every entry point returns
+// WD_ENODEVICE.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <random>
+
+#include "common.cuh"
+#include "farmhash.cuh"
+
+namespace wd {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int init_sparse_tables(WdModel* m, uint64_t seed, int random_w);
+int dense_refresh_transposes(WdModel* m);
+int wide_bias_grad(WdModel* m);
+int metrics_setup();
+int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int64_t n);
+
+static int pad_to(int n, int k) { return (n + k - 1) / k * k; }
+static int bits_for(int64_t n) {
+    int b = 1;
+    while ((1ll << b) < n) ++b;
+    return b;
+}
+
+template <typename T>
+static int upload_vec(WdModel* m, const T* src, int64_t n, const T** dst) {
+    T* p = nullptr;
+    int rc = dev_alloc(m, &p, n, true);
+    if (rc) return rc;
+    if (n > 0) WD_CUDA(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, m->stream));
+    *dst = p;
+    return WD_OK;
+}
+
+// sources of each layer input, in concat order (reference dnn.py:92-193); -1 = deep input x
+static std::vector<std::vector<int>> layer_sources(int mode, int L) {
+    std::vector<std::vector<int>> out;
+    for (int l = 0; l < L; ++l) {
+        std::vector<int> s;
+        if (l == 0) s = {-1};
+        else if (mode == WD_MODE_SIMPLE || mode == WD_MODE_LAST_DENSE) s = {l - 1};
+        else if (mode == WD_MODE_FIRST_DENSE) s = {l - 1, -1};
+        else if (mode == WD_MODE_DENSE) { s.push_back(-1); for (int j = 0; j < l; ++j) s.push_back(j); }
+        else { for (int j = l - 1; j >= 0; --j) s.push_back(j); s.push_back(-1); }
+        out.push_back(s);
+    }
+    std::vector<int> last;
+    if (L == 0) last = {-1};
+    else if (mode == WD_MODE_SIMPLE) last = {L - 1};
+    else if (mode == WD_MODE_FIRST_DENSE) last = {L - 1, -1};
+    else if (mode == WD_MODE_LAST_DENSE || mode == WD_MODE_DENSE) { last.push_back(-1); for (int j = 0; j < L; ++j) last.push_back(j); }
+    else { for (int j = L - 1; j >= 0; --j) last.push_back(j); last.push_back(-1); }
+    out.push_back(last);
+    return out;
+}
+}  // namespace wd
+
+using namespace wd;
+
+struct WdModelExtra {   // host-only bookkeeping kept beside WdModel
+    std::vector<uint8_t> x0_real;            // [d0_phys] 1 where a physical deep-input column is a real feature
+    int d0_logical = 0;
+    std::vector<std::vector<int>> dense_index;   // [tower-layer id][sub] -> index into WdModel::dense, -1
+    std::vector<int> did_tower, did_layer;
+};
+static std::vector<std::pair<WdModel*, WdModelExtra*>> g_extra;
+static WdModelExtra* extra_of(WdModel* m) {
+    for (auto& p : g_extra) if (p.first == m) return p.second;
+    return nullptr;
+}
+
+extern "C" const char* wd_last_error(void) { return wd::g_err; }
+extern "C" int wd_version(void) { return WD_API_VERSION; }
+extern "C" int wd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" uint64_t wd_fingerprint64(const uint8_t* bytes, size_t n) { return wd::fingerprint64(bytes, n); }
+extern "C" uint64_t wd_fingerprint_cat64(uint64_t a, uint64_t b) { return wd::fingerprint_cat64(a, b); }
+
+extern "C" int wd_model_destroy(WdModel* m) {
+    if (!m) return WD_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
+    if (m->timer.enabled || m->timer.ev[0]) for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    for (size_t i = 0; i < g_extra.size(); ++i)
+        if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
+    delete m;
+    return WD_OK;
+}
+
+// optimizer slots of the dense arena start at the initial accumulator value everywhere (padding included)
+static int init_dense_slots(WdModel* m) {
+    if (m->dense_count == 0) return WD_OK;
+    std::vector<float> S1(m->dense_count, 0.f);
+    for (size_t i = 0; i < m->dense.size(); ++i) {
+        const WdOptimizer& o = (m->use_wide && i == 0) ? m->lin_opt : m->dnn_opt;
+        float s1 = o.kind == WD_OPT_SGD ? 0.f : o.init_acc;
+        int64_t end = i + 1 < m->dense.size() ? m->dense[i + 1].off : m->dense_count;
+        for (int64_t j = m->dense[i].off; j < end; ++j) S1[j] = s1;
+    }
+    WD_CUDA(cudaMemcpyAsync(m->d_S1, S1.data(), S1.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    return WD_OK;
+}
+
+static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
+    int rc;
+    m->use_wide = d->model_type & 1;
+    m->use_deep = (d->model_type & 2) != 0;
+    m->n_cat_fields = d->n_cat_fields; m->n_dense_fields = d->n_dense_fields; m->n_columns = d->n_columns;
+    const int C = d->n_columns;
+    m->col_kind.assign(d->col_kind, d->col_kind + C);
+    m->col_field.assign(d->col_field, d->col_field + C);
+    m->col_buckets.assign(d->col_buckets, d->col_buckets + C);
+    m->col_wide_base.assign(d->col_wide_base, d->col_wide_base + C);
+    m->col_emb_table.assign(d->col_emb_table, d->col_emb_table + C);
+    m->col_ind_off.assign(d->col_ind_off, d->col_ind_off + C);
+    m->n_numeric = d->n_numeric;
+    m->d0_phys = d->d0_phys; m->wide_rows = d->wide_rows;
+    m->activation = d->activation; m->batch_norm = d->batch_norm;
+    m->lin_opt = d->lin_opt; m->dnn_opt = d->dnn_opt;
+    m->max_batch = d->max_batch; m->max_batch_pad = pad_to(d->max_batch, 128);
+    m->ldt = m->max_batch_pad;
+    m->row_tiles = m->max_batch_pad / 128;
+    m->gemm_engine = d->gemm_engine == WD_GEMM_AUTO ? WD_GEMM_FFMA : d->gemm_engine;
+    m->max_nnz = d->max_nnz > 0 ? d->max_nnz : (int64_t)d->max_batch * std::max(C, 1) * 2;
+    m->keys_cap = d->max_keys > 0 ? d->max_keys : (int64_t)d->max_batch * std::max(d->n_cat_fields, 1) * 4;
+    if (m->lin_opt.kind == WD_OPT_FTRL && m->lin_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
+    if (m->dnn_opt.kind == WD_OPT_FTRL && m->dnn_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
+    for (int c = 0; c < C; ++c)
+        if (d->col_kind[c] == WD_COL_CROSS && d->col_aux_n[c] > 8) { set_error("cross with more than 8 keys"); return WD_EUNSUPPORTED; }
+
+    // ---- plan tables on the device
+    DevPlan& p = m->dplan;
+    p.n_cat_fields = d->n_cat_fields; p.n_dense_fields = d->n_dense_fields; p.n_columns = C; p.d0_phys = d->d0_phys;
+    if ((rc = upload_vec(m, d->cat_field_is_string, d->n_cat_fields, &p.field_is_string))) return rc;
+    if ((rc = upload_vec(m, d->col_kind, C, &p.col_kind))) return rc;
+    if ((rc = upload_vec(m, d->col_field, C, &p.col_field))) return rc;
+    if ((rc = upload_vec(m, d->col_buckets, C, &p.col_buckets))) return rc;
+    if ((rc = upload_vec(m, d->col_aux_off, C, &p.col_aux_off))) return rc;
+    if ((rc = upload_vec(m, d->col_aux_n, C, &p.col_aux_n))) return rc;
+    if ((rc = upload_vec(m, d->col_norm_kind, C, &p.col_norm_kind))) return rc;
+    if ((rc = upload_vec(m, d->col_norm_a, C, &p.col_norm_a))) return rc;
+    if ((rc = upload_vec(m, d->col_norm_b, C, &p.col_norm_b))) return rc;
+    if ((rc = upload_vec(m, d->col_wide_base, C, &p.col_wide_base))) return rc;
+    if ((rc = upload_vec(m, d->col_emb_table, C, &p.col_emb_table))) return rc;
+    if ((rc = upload_vec(m, d->col_ind_off, C, &p.col_ind_off))) return rc;
+    if ((rc = upload_vec(m, d->vocab_fp, d->n_vocab_fp, &p.vocab_fp))) return rc;
+    if ((rc = upload_vec(m, d->boundaries, d->n_boundaries, &p.boundaries))) return rc;
+    if ((rc = upload_vec(m, d->cross_key_type, d->n_cross_keys, &p.cross_key_type))) return rc;
+    if ((rc = upload_vec(m, d->cross_key_idx, d->n_cross_keys, &p.cross_key_idx))) return rc;
+    {
+        const int32_t* t;
+        const float* f;
+        if ((rc = upload_vec(m, d->num_field, d->n_numeric, &t))) return rc; m->d_num_field = (int32_t*)t;
+        if ((rc = upload_vec(m, d->num_norm_kind, d->n_numeric, &t))) return rc; m->d_num_norm_kind = (int32_t*)t;
+        if ((rc = upload_vec(m, d->num_x0_off, d->n_numeric, &t))) return rc; m->d_num_x0_off = (int32_t*)t;
+        if ((rc = upload_vec(m, d->num_norm_a, d->n_numeric, &f))) return rc; m->d_num_a = (float*)f;
+        if ((rc = upload_vec(m, d->num_norm_b, d->n_numeric, &f))) return rc; m->d_num_b = (float*)f;
+    }
+
+    // ---- batch buffers
+    const int64_t Bm = m->max_batch;
+    if ((rc = dev_alloc(m, &m->d_cat_offsets, Bm * std::max(d->n_cat_fields, 1) + 1))) return rc;
+    if ((rc = dev_alloc(m, &m->d_cat_keys, m->keys_cap))) return rc;
+    if ((rc = dev_alloc(m, &m->d_dense, Bm * std::max(d->n_dense_fields, 1)))) return rc;
+    if ((rc = dev_alloc(m, &m->d_label, Bm))) return rc;
+    if ((rc = dev_alloc(m, &m->d_weight, Bm))) return rc;
+    if ((rc = dev_alloc(m, &m->d_col_offs, Bm * std::max(C, 1) + 2))) return rc;
+    if ((rc = dev_alloc(m, &m->d_e_wide, m->max_nnz))) return rc;
+    if ((rc = dev_alloc(m, &m->d_e_emb, m->max_nnz))) return rc;
+    if ((rc = dev_alloc(m, &m->d_e_bc, m->max_nnz))) return rc;
+    if ((rc = dev_alloc(m, &m->d_e_id, m->max_nnz))) return rc;
+    if ((rc = dev_alloc(m, &m->d_nnz, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_flags, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_sort_counter, 4))) return rc;
+    {
+        int64_t n = std::max<int64_t>(Bm * std::max(C, 1) + 2, m->max_nnz + 2);
+        int32_t* t;
+        if ((rc = dev_alloc(m, &t, n / 4096 + 8))) return rc;
+        m->d_scan_tmp = t;
+    }
+    if ((rc = dev_alloc(m, &m->d_logits, Bm))) return rc;
+    if ((rc = dev_alloc(m, &m->d_dlogit, Bm))) return rc;
+    if ((rc = dev_alloc(m, &m->d_loss_part, 512))) return rc;
+    if ((rc = dev_alloc(m, &m->d_loss, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_metrics, 512))) return rc;
+    WD_CUDA(cudaMallocHost(&m->h_loss_pinned, 64));
+
+    // ---- dense tensors
+    auto add_dense = [&](int rows, int cols, int gparts, int g_rowtiles, int64_t gstride, bool transpose) {
+        DenseTensor t{};
+        t.off = m->dense_count; t.count = (int64_t)rows * cols; t.rows = rows; t.cols = cols;
+        t.gpart_off = m->gpart_count; t.gparts = gparts; t.g_rowtiles = g_rowtiles; t.gstride = gstride;
+        t.wt_off = transpose ? m->wt_count : -1;
+        m->dense_count += (t.count + 3) / 4 * 4;
+        m->gpart_count += (int64_t)gparts * gstride;
+        if (transpose) m->wt_count += t.count;
+        m->dense.push_back(t);
+        return (int)m->dense.size() - 1;
+    };
+    if (m->use_wide) {
+        add_dense(1, 1, m->row_tiles, 1, 4, false);            // [0] wide bias
+        if ((rc = dev_alloc(m, &m->d_wide, m->wide_rows))) return rc;
+        if ((rc = dev_alloc(m, &m->d_wide_logit, Bm))) return rc;
+    }
+
+    // ---- deep part
+    x->x0_real.assign(std::max(d->d0_phys, 1), 0);
+    if (m->use_deep) {
+        int64_t row_base = 0;
+        std::vector<int64_t> h_row_base;
+        const int nslots = m->dnn_opt.kind == WD_OPT_FTRL ? 2 : (m->dnn_opt.kind == WD_OPT_ADAGRAD ? 1 : 0);
+        for (int t = 0; t < d->n_tables; ++t) {
+            EmbTable tb{};
+            tb.rows = d->table_rows[t]; tb.dim = d->table_dim[t]; tb.x0_off = d->table_x0_off[t];
+            tb.dim_logical = d->table_dim_logical[t];
+            if (tb.dim_logical < 1 || tb.dim_logical > tb.dim) { set_error("table %d: bad logical width", t); return WD_EINVAL; }
+            tb.row_base = row_base; tb.stride = tb.dim * (1 + nslots); tb.col = -1;
+            if (tb.dim % 4 || tb.x0_off % 4) { set_error("table %d: dim and deep-input offset must be multiples of 4", t); return WD_EINVAL; }
+            for (int c = 0; c < C; ++c) if (d->col_emb_table[c] == t) tb.col = c;
+            if (tb.col < 0) { set_error("table %d has no producing column", t); return WD_EINVAL; }
+            if ((rc = dev_alloc(m, &tb.data, tb.rows * tb.stride, true))) return rc;
+            for (int i = 0; i < tb.dim_logical; ++i) x->x0_real[tb.x0_off + i] = 1;
+            h_row_base.push_back(row_base);
+            row_base += tb.rows;
+            m->emb_max_dim = std::max(m->emb_max_dim, tb.dim);
+            m->tables.push_back(tb);
+        }
+        m->emb_total_rows = row_base;
+        if (row_base >= (1ll << 31)) { set_error("more than 2^31 embedding rows on one device"); return WD_EUNSUPPORTED; }
+        for (int i = 0; i < d->n_numeric; ++i) x->x0_real[d->num_x0_off[i]] = 1;
+        for (int c = 0; c < C; ++c)
+            if (d->col_ind_off[c] >= 0) for (int64_t i = 0; i < d->col_buckets[c]; ++i) x->x0_real[d->col_ind_off[c] + i] = 1;
+        for (auto v : x->x0_real) x->d0_logical += v;
+        // device table descriptors
+        const int nt = (int)m->tables.size();
+        std::vector<float*> h_data; std::vector<int32_t> h_dim, h_stride, h_x0, h_col;
+        for (auto& tb : m->tables) { h_data.push_back(tb.data); h_dim.push_back(tb.dim); h_stride.push_back(tb.stride); h_x0.push_back(tb.x0_off); h_col.push_back(tb.col); }
+        { float* const* t; if ((rc = upload_vec<float*>(m, h_data.data(), nt, (float* const**)&t))) return rc; m->d_tab_data = (float**)t; }
+        { const int32_t* t;
+          if ((rc = upload_vec(m, h_dim.data(), nt, &t))) return rc; m->d_tab_dim = (int32_t*)t;
+          if ((rc = upload_vec(m, h_stride.data(), nt, &t))) return rc; m->d_tab_stride = (int32_t*)t;
+          if ((rc = upload_vec(m, h_x0.data(), nt, &t))) return rc; m->d_tab_x0 = (int32_t*)t;
+          if ((rc = upload_vec(m, h_col.data(), nt, &t))) return rc; m->d_tab_col = (int32_t*)t; }
+        { const int64_t* t; if ((rc = upload_vec(m, h_row_base.data(), nt, &t))) return rc; m->d_tab_row_base = (int64_t*)t; p.table_row_base = t; }
+        // group tables by width
+        for (int t = 0; t < nt; ++t) {
+            int di = -1;
+            for (int i = 0; i < m->n_dims; ++i) if (m->dims[i] == m->tables[t].dim) di = i;
+            if (di < 0) {
+                if (m->n_dims == kMaxDims) { set_error("more than %d distinct embedding widths", kMaxDims); return WD_EUNSUPPORTED; }
+                di = m->n_dims++; m->dims[di] = m->tables[t].dim; m->dim_ntables[di] = 0;
+            }
+            m->dim_ntables[di]++;
+        }
+        for (int i = 0; i < m->n_dims; ++i) {
+            std::vector<int32_t> ids;
+            for (int t = 0; t < nt; ++t) if (m->tables[t].dim == m->dims[i]) ids.push_back(t);
+            const int32_t* dp;
+            if ((rc = upload_vec(m, ids.data(), (int64_t)ids.size(), &dp))) return rc;
+            m->d_dim_tables[i] = (int32_t*)dp;
+        }
+        const int64_t actn = (int64_t)m->max_batch_pad * d->d0_phys;
+        if ((rc = dev_alloc(m, &m->d_X0, actn))) return rc;
+        if ((rc = dev_alloc(m, &m->d_X0T, actn))) return rc;
+        if ((rc = dev_alloc(m, &m->d_dX0, actn))) return rc;
+
+        // towers
+        int hu_off = 0, did = 0;
+        for (int t = 0; t < d->n_towers; ++t) {
+            Tower tw{};
+            tw.n_hidden = d->tower_nlayers[t]; tw.mode = d->tower_mode[t];
+            std::vector<int> hu(d->hidden_units + hu_off, d->hidden_units + hu_off + tw.n_hidden);
+            hu_off += tw.n_hidden;
+            auto srcs = layer_sources(tw.mode, tw.n_hidden);
+            for (int l = 0; l <= tw.n_hidden; ++l) {
+                Layer L{};
+                if ((int)srcs[l].size() > kMaxSegs) { set_error("layer with more than %d concatenated inputs", kMaxSegs); return WD_EUNSUPPORTED; }
+                L.n_in_segs = (int)srcs[l].size();
+                int koff = 0, klog = 0;
+                for (int s = 0; s < L.n_in_segs; ++s) {
+                    int src = srcs[l][s];
+                    Seg sg{};
+                    sg.src = src;
+                    sg.width = src < 0 ? x->d0_logical : hu[src];
+                    sg.width_phys = src < 0 ? d->d0_phys : pad_to(hu[src], 32);
+                    sg.k_off = koff;
+                    koff += sg.width_phys; klog += sg.width;
+                    L.segs[s] = sg;
+                }
+                L.K = klog; L.K_phys = koff;
+                const bool hidden = l < tw.n_hidden;
+                L.N = hidden ? hu[l] : 1;
+                L.N_phys = hidden ? pad_to(hu[l], 32) : 1;
+                L.t_gamma = L.t_beta = -1;
+                std::vector<int> idx(4, -1);
+                if (hidden) {
+                    L.t_kernel = add_dense(L.K_phys, L.N_phys, m->wgrad_splits, 0, (int64_t)L.K_phys * L.N_phys, true);
+                    L.t_bias = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
+                    if (m->batch_norm) {
+                        L.t_gamma = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
+                        L.t_beta = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
+                    }
+                    const int64_t n = (int64_t)m->max_batch_pad * L.N_phys;
+                    if ((rc = dev_alloc(m, &L.H, n))) return rc;
+                    if (m->batch_norm) { if ((rc = dev_alloc(m, &L.A, n))) return rc; } else L.A = L.H;
+                    if ((rc = dev_alloc(m, &L.HT, n))) return rc;
+                    if ((rc = dev_alloc(m, &L.dH, n))) return rc;
+                    if ((rc = dev_alloc(m, &L.dZ, n))) return rc;
+                    if ((rc = dev_alloc(m, &L.dZT, n))) return rc;
+                } else {
+                    L.t_kernel = add_dense(L.K_phys, 1, m->row_tiles, 1, L.K_phys, false);
+                    L.t_bias = add_dense(1, 1, m->row_tiles, 1, 4, false);
+                }
+                idx[WD_D_KERNEL] = L.t_kernel; idx[WD_D_BIAS] = L.t_bias; idx[WD_D_GAMMA] = L.t_gamma; idx[WD_D_BETA] = L.t_beta;
+                x->dense_index.push_back(idx);
+                x->did_tower.push_back(t); x->did_layer.push_back(l);
+                ++did;
+                tw.layers.push_back(L);
+            }
+            if ((rc = dev_alloc(m, &tw.logit, Bm))) return rc;
+            m->towers.push_back(tw);
+        }
+    }
+    if (m->dense_count > 0) {
+        if ((rc = dev_alloc(m, &m->d_P, m->dense_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_S1, m->dense_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_S2, m->dense_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_G, m->dense_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_gpart, m->gpart_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_Wt, std::max<int64_t>(m->wt_count, 1)))) return rc;
+        const DenseTensor* dp;
+        if ((rc = upload_vec(m, m->dense.data(), (int64_t)m->dense.size(), &dp))) return rc;
+        m->d_dense_desc = (DenseTensor*)dp;
+    }
+
+    // ---- sparse backward scratch
+    m->sort_bits[0] = bits_for(std::max<int64_t>(m->emb_total_rows, 2));
+    m->sort_bits[1] = bits_for(std::max<int64_t>(m->wide_rows, 2));
+    if (m->sort_bits[0] > 30 || m->sort_bits[1] > 30) { set_error("more than 2^30 rows in one table space on one device"); return WD_EUNSUPPORTED; }
+    const int which_lo = (m->use_deep && !m->tables.empty()) ? 0 : 1, which_hi = m->use_wide ? 1 : 0;
+    for (int w = which_lo; w <= which_hi; ++w) {
+        if ((rc = dev_alloc(m, &m->d_sk[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_sv[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_sk2[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_sv2[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_urow[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_ustart[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_ugrad[w], (m->max_nnz + 8) * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
+        if ((rc = dev_alloc(m, &m->d_nuniq[w], 4))) return rc;
+        if ((rc = dev_alloc(m, &m->d_nvalid[w], 4))) return rc;
+        m->sparse_cap[w] = m->max_nnz;
+    }
+    m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1);
+    if ((rc = dev_alloc(m, &m->d_sort_hist, m->sort_hist_cap))) return rc;
+    if ((rc = metrics_setup())) return rc;
+    if ((rc = init_sparse_tables(m, 0, 0))) return rc;           // slots = initial accumulator, weights 0
+    if ((rc = init_dense_slots(m))) return rc;
+    for (auto& e : m->timer.ev) WD_CUDA(cudaEventCreate(&e));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    return WD_OK;
+}
+
+extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
+    if (!d || !out) { set_error("null argument"); return WD_EINVAL; }
+    if (d->api_version != WD_API_VERSION) { set_error("plan api_version %d != library %d", d->api_version, WD_API_VERSION); return WD_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libwd_b200 has no CPU fallback");
+        return WD_ENODEVICE;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return WD_EINVAL; }
+    WD_CUDA(cudaSetDevice(device));
+    WdModel* m = new WdModel();
+    WdModelExtra* x = new WdModelExtra();
+    g_extra.push_back({m, x});
+    m->device = device;
+    memset(m->timer.ev, 0, sizeof(m->timer.ev));
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
+    int rc = build_model(d, m, x);
+    if (rc) { wd_model_destroy(m); return rc; }
+    *out = m;
+    return WD_OK;
+}
+
+// glorot-uniform kernels / zero biases / gamma 1 / beta 0 built on the host (dense part is ~1.5M floats)
+static int init_dense(WdModel* m, WdModelExtra* x, uint64_t seed) {
+    if (m->dense_count == 0) return WD_OK;
+    std::vector<float> P(m->dense_count, 0.f), S1(m->dense_count, 0.f), S2(m->dense_count, 0.f);
+    std::mt19937_64 rng(seed * 7919 + 17);
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    for (size_t ti = 0; ti < m->towers.size(); ++ti) {
+        Tower& tw = m->towers[ti];
+        for (int l = 0; l <= tw.n_hidden; ++l) {
+            Layer& L = tw.layers[l];
+            const DenseTensor& tk = m->dense[L.t_kernel];
+            const float lim = std::sqrt(6.f / (float)(L.K + L.N));
+            for (int s = 0; s < L.n_in_segs; ++s) {
+                const Seg& sg = L.segs[s];
+                for (int j = 0; j < sg.width_phys; ++j) {
+                    bool real = sg.src < 0 ? (x->x0_real[j] != 0) : (j < sg.width);
+                    if (!real) continue;
+                    for (int n = 0; n < L.N; ++n) P[tk.off + (int64_t)(sg.k_off + j) * L.N_phys + n] = lim * U(rng);
+                }
+            }
+            if (L.t_gamma >= 0) for (int n = 0; n < L.N; ++n) P[m->dense[L.t_gamma].off + n] = 1.f;
+        }
+    }
+    for (size_t i = 0; i < m->dense.size(); ++i) {
+        const WdOptimizer& o = (m->use_wide && i == 0) ? m->lin_opt : m->dnn_opt;
+        float s1 = o.kind == WD_OPT_SGD ? 0.f : o.init_acc;
+        for (int64_t j = 0; j < m->dense[i].count; ++j) S1[m->dense[i].off + j] = s1;
+    }
+    WD_CUDA(cudaMemcpyAsync(m->d_P, P.data(), P.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    WD_CUDA(cudaMemcpyAsync(m->d_S1, S1.data(), S1.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    WD_CUDA(cudaMemcpyAsync(m->d_S2, S2.data(), S2.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    return dense_refresh_transposes(m);
+}
+
+extern "C" int wd_model_init(WdModel* m, uint64_t seed) {
+    if (!m) { set_error("null model"); return WD_EINVAL; }
+    WD_CUDA(cudaSetDevice(m->device));
+    int rc = init_sparse_tables(m, seed, 1);
+    if (rc) return rc;
+    rc = init_dense(m, extra_of(m), seed);
+    if (rc) return rc;
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    m->initialized = true;
+    return WD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tensor IO
+static int resolve_dense(WdModel* m, WdModelExtra* x, int did, int sub, int* out) {
+    if (did < 0 || did >= (int)x->dense_index.size() || sub < 0 || sub > 3 || x->dense_index[did][sub] < 0) {
+        set_error("no dense tensor (%d, %d)", did, sub);
+        return WD_EINVAL;
+    }
+    *out = x->dense_index[did][sub];
+    return WD_OK;
+}
+
+extern "C" int64_t wd_tensor_size(WdModel* m, int kind, int index, int sub) {
+    if (!m) return WD_EINVAL;
+    WdModelExtra* x = extra_of(m);
+    if (kind == WD_T_WIDE_COL) return (index >= 0 && index < m->n_columns && m->col_wide_base[index] >= 0) ? m->col_buckets[index] : WD_EINVAL;
+    if (kind == WD_T_WIDE_BIAS) return m->use_wide ? 1 : WD_EINVAL;
+    if (kind == WD_T_EMB_TABLE) return (index >= 0 && index < (int)m->tables.size()) ? m->tables[index].rows * m->tables[index].dim_logical : WD_EINVAL;
+    if (kind == WD_T_DENSE) {
+        int di;
+        if (resolve_dense(m, x, index, sub, &di)) return WD_EINVAL;
+        Layer& L = m->towers[x->did_tower[index]].layers[x->did_layer[index]];
+        return sub == WD_D_KERNEL ? (int64_t)L.K * L.N : L.N;
+    }
+    return WD_EINVAL;
+}
+
+extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, void* host, int64_t count, int to_device) {
+    if (!m || !host) { set_error("null argument"); return WD_EINVAL; }
+    WD_CUDA(cudaSetDevice(m->device));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    WdModelExtra* x = extra_of(m);
+    int64_t want = wd_tensor_size(m, kind, index, sub);
+    if (want < 0 || want != count) { set_error("tensor (%d,%d,%d): size %lld, caller passed %lld", kind, index, sub, (long long)want, (long long)count); return WD_EINVAL; }
+    if (slot < 0 || slot > 2) { set_error("slot out of range"); return WD_EINVAL; }
+    const cudaMemcpyKind dir = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (kind == WD_T_WIDE_COL) {
+        float* dev = reinterpret_cast<float*>(m->d_wide + m->col_wide_base[index]) + slot;
+        if (to_device) WD_CUDA(cudaMemcpy2D(dev, 16, host, 4, 4, count, dir));
+        else WD_CUDA(cudaMemcpy2D(host, 4, dev, 16, 4, count, dir));
+        return WD_OK;
+    }
+    if (kind == WD_T_EMB_TABLE) {
+        EmbTable& tb = m->tables[index];
+        if (slot * tb.dim >= tb.stride) { set_error("table has no optimizer slot %d", slot); return WD_EINVAL; }
+        float* dev = tb.data + slot * tb.dim;
+        const size_t lw = (size_t)tb.dim_logical * 4;
+        if (to_device) WD_CUDA(cudaMemcpy2D(dev, (size_t)tb.stride * 4, host, lw, lw, tb.rows, dir));
+        else WD_CUDA(cudaMemcpy2D(host, lw, dev, (size_t)tb.stride * 4, lw, tb.rows, dir));
+        return WD_OK;
+    }
+    float* arena = slot == 0 ? m->d_P : (slot == 1 ? m->d_S1 : m->d_S2);
+    if (kind == WD_T_WIDE_BIAS) {
+        WD_CUDA(cudaMemcpy(to_device ? (void*)(arena + m->dense[0].off) : host, to_device ? host : (void*)(arena + m->dense[0].off), 4, dir));
+        return WD_OK;
+    }
+    int di;
+    int rc = resolve_dense(m, x, index, sub, &di);
+    if (rc) return rc;
+    const DenseTensor& t = m->dense[di];
+    Layer& L = m->towers[x->did_tower[index]].layers[x->did_layer[index]];
+    std::vector<float> phys(t.count, 0.f);
+    float* h = (float*)host;
+    if (!to_device || slot > 0) WD_CUDA(cudaMemcpy(phys.data(), arena + t.off, t.count * 4, cudaMemcpyDeviceToHost));
+    if (sub == WD_D_KERNEL) {
+        int64_t lk = 0;
+        for (int s = 0; s < L.n_in_segs; ++s) {
+            const Seg& sg = L.segs[s];
+            for (int j = 0; j < sg.width_phys; ++j) {
+                bool real = sg.src < 0 ? (x->x0_real[j] != 0) : (j < sg.width);
+                if (!real) continue;
+                for (int n = 0; n < L.N; ++n) {
+                    float& pv = phys[(int64_t)(sg.k_off + j) * L.N_phys + n];
+                    if (to_device) pv = h[lk * L.N + n]; else h[lk * L.N + n] = pv;
+                }
+                ++lk;
+            }
+        }
+        if (lk != L.K) { set_error("internal: logical K mismatch %lld vs %d", (long long)lk, L.K); return WD_ESTATE; }
+    } else {
+        for (int n = 0; n < L.N; ++n) { if (to_device) phys[n] = h[n]; else h[n] = phys[n]; }
+    }
+    if (to_device) {
+        WD_CUDA(cudaMemcpy(arena + t.off, phys.data(), t.count * 4, cudaMemcpyHostToDevice));
+        if (slot == 0 && t.wt_off >= 0) return dense_refresh_transposes(m);
+    }
+    return WD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------- steps
+static int check_ready(WdModel* m) {
+    if (!m) { set_error("null model"); return WD_EINVAL; }
+    WD_CUDA(cudaSetDevice(m->device));
+    return WD_OK;
+}
+static void tick(WdModel* m, int i) { if (m->timer.enabled) cudaEventRecord(m->timer.ev[i], m->stream); }
+
+extern "C" int wd_batch_upload(WdModel* m, const WdBatch* b) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!b || b->batch_size <= 0 || b->batch_size > m->max_batch) { set_error("batch_size %d outside (0, %d]", b ? b->batch_size : -1, m->max_batch); return WD_EINVAL; }
+    const int B = b->batch_size, F = m->n_cat_fields, Nd = m->n_dense_fields;
+    int64_t nnz = b->cat_offsets ? b->nnz : (int64_t)B * F;
+    if (nnz > m->keys_cap) { set_error("batch has %lld keys, capacity %lld (raise max_keys)", (long long)nnz, (long long)m->keys_cap); return WD_EINVAL; }
+    tick(m, 0);
+    if (F > 0) {
+        if (b->cat_offsets) WD_CUDA(cudaMemcpyAsync(m->d_cat_offsets, b->cat_offsets, ((int64_t)B * F + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+        if (nnz > 0) WD_CUDA(cudaMemcpyAsync(m->d_cat_keys, b->cat_keys, nnz * 8, cudaMemcpyHostToDevice, m->stream));
+    }
+    if (Nd > 0) WD_CUDA(cudaMemcpyAsync(m->d_dense, b->dense, (int64_t)B * Nd * 4, cudaMemcpyHostToDevice, m->stream));
+    if (b->label) WD_CUDA(cudaMemcpyAsync(m->d_label, b->label, (int64_t)B * 4, cudaMemcpyHostToDevice, m->stream));
+    if (b->weight) WD_CUDA(cudaMemcpyAsync(m->d_weight, b->weight, (int64_t)B * 4, cudaMemcpyHostToDevice, m->stream));
+    m->dbatch.B = B;
+    m->dbatch.cat_offsets = (F > 0 && b->cat_offsets) ? m->d_cat_offsets : nullptr;
+    m->dbatch.cat_keys = m->d_cat_keys;
+    m->dbatch.dense = m->d_dense;
+    m->dbatch.label = b->label ? m->d_label : nullptr;
+    m->dbatch.weight = b->weight ? m->d_weight : nullptr;
+    m->batch_has_label = b->label != nullptr;
+    tick(m, 1);
+    return WD_OK;
+}
+
+static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
+    int32_t* flags_host = reinterpret_cast<int32_t*>(m->h_loss_pinned + 4);
+    WD_CUDA(cudaMemcpyAsync(m->h_loss_pinned, m->d_loss, 4, cudaMemcpyDeviceToHost, m->stream));
+    WD_CUDA(cudaMemcpyAsync(flags_host, m->d_flags, 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_out) WD_CUDA(cudaMemcpyAsync(logits_out, m->d_logits, (int64_t)m->dbatch.B * 4, cudaMemcpyDeviceToHost, m->stream));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    if (flags_host[0] & 1) {
+        cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
+        set_error("categorical-column id capacity exceeded (max_nnz=%lld): recreate the model with a larger max_nnz", (long long)m->max_nnz);
+        return WD_EINVAL;
+    }
+    if (loss_out) *loss_out = m->batch_has_label ? m->h_loss_pinned[0] : 0.f;
+    if (m->timer.enabled) {
+        for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&m->last_ms[i], m->timer.ev[i], m->timer.ev[i + 1]);
+        cudaEventElapsedTime(&m->last_ms[7], m->timer.ev[0], m->timer.ev[7]);
+    }
+    return WD_OK;
+}
+
+static int forward_core(WdModel* m, bool train) {
+    int rc;
+    if ((rc = ids_prepare(m))) return rc;
+    tick(m, 2);
+    if ((rc = sparse_forward(m))) return rc;
+    tick(m, 3);
+    if ((rc = mlp_forward(m, train))) return rc;
+    if ((rc = loss_forward(m, train))) return rc;
+    tick(m, 4);
+    return WD_OK;
+}
+
+static int backward_core(WdModel* m) {
+    int rc;
+    if ((rc = mlp_backward(m))) return rc;
+    if ((rc = wide_bias_grad(m))) return rc;
+    if ((rc = dense_reduce_grads(m))) return rc;
+    tick(m, 5);
+    if ((rc = sparse_backward_reduce(m))) return rc;
+    tick(m, 6);
+    m->grads_pending = true;
+    return WD_OK;
+}
+
+static int apply_core(WdModel* m) {
+    int rc;
+    if ((rc = sparse_apply(m))) return rc;
+    if ((rc = dense_apply(m))) return rc;
+    tick(m, 7);
+    m->grads_pending = false;
+    return WD_OK;
+}
+
+extern "C" int wd_train_step_resident(WdModel* m, float* loss_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    if (!m->timer.enabled) {} else { /* events 0,1 recorded by upload; keep ordering when resident */ cudaEventRecord(m->timer.ev[0], m->stream); cudaEventRecord(m->timer.ev[1], m->stream); }
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    if ((rc = apply_core(m))) return rc;
+    if (loss_out) return finish_step(m, loss_out, nullptr);
+    return WD_OK;
+}
+
+extern "C" int wd_train_step(WdModel* m, const WdBatch* b, float* loss_out) {
+    int rc = wd_batch_upload(m, b);
+    if (rc) return rc;
+    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    if ((rc = apply_core(m))) return rc;
+    return finish_step(m, loss_out, nullptr);
+}
+
+extern "C" int wd_forward_resident(WdModel* m, float* logits_out, float* loss_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if ((rc = forward_core(m, false))) return rc;
+    return finish_step(m, loss_out, logits_out);
+}
+
+extern "C" int wd_forward(WdModel* m, const WdBatch* b, float* logits_out, float* loss_out) {
+    int rc = wd_batch_upload(m, b);
+    if (rc) return rc;
+    if ((rc = forward_core(m, false))) return rc;
+    return finish_step(m, loss_out, logits_out);
+}
+
+extern "C" int wd_step_backward(WdModel* m, const WdBatch* b, float* loss_out) {
+    int rc = b ? wd_batch_upload(m, b) : check_ready(m);
+    if (rc) return rc;
+    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    if (loss_out) return finish_step(m, loss_out, nullptr);
+    return WD_OK;
+}
+
+extern "C" int wd_step_apply(WdModel* m) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!m->grads_pending) { set_error("wd_step_apply without wd_step_backward"); return WD_ESTATE; }
+    return apply_core(m);
+}
+
+extern "C" int64_t wd_dense_grad_count(WdModel* m) { return m ? m->dense_count : 0; }
+extern "C" void* wd_dense_grad_ptr(WdModel* m) { return m ? m->d_G : nullptr; }
+
+extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads, int64_t* n, int32_t* width, int64_t* capacity) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
+    int32_t nu = 0;
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    WD_CUDA(cudaMemcpy(&nu, m->d_nuniq[which], 4, cudaMemcpyDeviceToHost));
+    if (rows) *rows = m->d_urow[which];
+    if (grads) *grads = m->d_ugrad[which];
+    if (n) *n = nu;
+    if (width) *width = which == 0 ? m->emb_max_dim : 1;
+    if (capacity) *capacity = m->sparse_cap[which];
+    return WD_OK;
+}
+
+extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int64_t n) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
+    return merge_sparse(m, which, rows_dev, grads_dev, n);
+}
+
+// ------------------------------------------------------------------------------------------------- eval
+extern "C" int wd_eval_reset(WdModel* m) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    WD_CUDA(cudaMemsetAsync(m->d_metrics, 0, 512 * sizeof(double), m->stream));
+    m->eval_batches = 0;
+    return WD_OK;
+}
+extern "C" int wd_eval_accumulate(WdModel* m, const WdBatch* b) {
+    int rc = wd_batch_upload(m, b);
+    if (rc) return rc;
+    if (!m->batch_has_label) { set_error("evaluation needs labels"); return WD_EINVAL; }
+    if ((rc = forward_core(m, false))) return rc;
+    if ((rc = metrics_accumulate(m))) return rc;
+    return finish_step(m, nullptr, nullptr);
+}
+extern "C" int wd_eval_finish(WdModel* m, double* out10) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    return metrics_finish(m, out10);
+}
+
+// ------------------------------------------------------------------------------------------ debug / misc
+extern "C" int wd_debug_column_ids(WdModel* m, int32_t* offsets_out, int64_t offsets_cap, int64_t* ids_out, int64_t ids_cap, int64_t* nnz_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    int64_t no = (int64_t)m->dbatch.B * m->n_columns + 1;
+    int32_t nnz = 0;
+    WD_CUDA(cudaMemcpy(&nnz, m->d_nnz, 4, cudaMemcpyDeviceToHost));
+    if (nnz_out) *nnz_out = nnz;
+    if (offsets_out) {
+        if (offsets_cap < no) { set_error("offsets buffer too small"); return WD_EINVAL; }
+        WD_CUDA(cudaMemcpy(offsets_out, m->d_col_offs, no * 4, cudaMemcpyDeviceToHost));
+    }
+    if (ids_out) {
+        if (ids_cap < nnz) { set_error("ids buffer too small"); return WD_EINVAL; }
+        std::vector<int32_t> tmp(nnz);
+        WD_CUDA(cudaMemcpy(tmp.data(), m->d_e_id, (int64_t)nnz * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nnz; ++i) ids_out[i] = tmp[i];
+    }
+    return WD_OK;
+}
+extern "C" int wd_debug_deep_input(WdModel* m, float* out, int64_t cap) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!m->use_deep) { set_error("model has no deep part"); return WD_EINVAL; }
+    int64_t n = (int64_t)m->dbatch.B * m->d0_phys;
+    if (cap < n) { set_error("buffer too small"); return WD_EINVAL; }
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    WD_CUDA(cudaMemcpy(out, m->d_X0, n * 4, cudaMemcpyDeviceToHost));
+    return WD_OK;
+}
+extern "C" int64_t wd_launch_count(WdModel* m) { return m ? m->launches : 0; }
+extern "C" int wd_last_timings(WdModel* m, float* out8) {
+    if (!m || !out8) return WD_EINVAL;
+    memcpy(out8, m->last_ms, sizeof(m->last_ms));
+    return WD_OK;
+}
+extern "C" int wd_set_profile(WdModel* m, int enable) {
+    if (!m) return WD_EINVAL;
+    m->timer.enabled = enable != 0;
+    return WD_OK;
+}
+extern "C" void* wd_stream(WdModel* m) { return m ? (void*)m->stream : nullptr; }
+extern "C" int wd_sync(WdModel* m) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    return WD_OK;
+}

@@ -1,0 +1,270 @@
+// Shared declarations of libwd_b200: host-side model object, device plan tables, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wd_b200.h"
+
+namespace wd {
+
+void set_error(const char* fmt, ...);
+
+#define WD_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            wd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return WD_ECUDA;                                                                  \
+        }                                                                                     \
+    } while (0)
+
+constexpr uint32_t kInvalidRow = 0xFFFFFFFFu;
+constexpr int kMaxSegs = 8;      // sources concatenated into one MLP layer input
+constexpr int kMaxDims = 8;      // distinct embedding widths per model
+
+// ---- device image of the categorical-column plan (all pointers are device pointers)
+struct DevPlan {
+    int n_cat_fields, n_dense_fields, n_columns;
+    const uint8_t* field_is_string;
+    const int32_t* col_kind;
+    const int32_t* col_field;
+    const int64_t* col_buckets;
+    const int32_t* col_aux_off;
+    const int32_t* col_aux_n;
+    const int32_t* col_norm_kind;
+    const float* col_norm_a;
+    const float* col_norm_b;
+    const int64_t* col_wide_base;
+    const int32_t* col_emb_table;
+    const int32_t* col_ind_off;
+    const uint64_t* vocab_fp;
+    const float* boundaries;
+    const int32_t* cross_key_type;
+    const int32_t* cross_key_idx;
+    const int64_t* table_row_base;   // global embedding row id of row 0 of each table
+    int d0_phys;
+};
+
+// ---- device view of one batch
+struct DevBatch {
+    int B;
+    const int32_t* cat_offsets;      // may be null: one key per (row, field)
+    const uint64_t* cat_keys;
+    const float* dense;
+    const float* label;              // may be null
+    const float* weight;             // may be null
+};
+
+struct EmbTable {
+    int64_t rows;
+    int dim;                 // physical width (multiple of 4)
+    int dim_logical;         // embedding_column dimension; columns [dim_logical, dim) are zero padding
+    int x0_off;
+    int col;                 // producing column
+    int64_t row_base;        // global row id base
+    float* data;             // rows * stride floats; record = [w[dim] | slot1[dim] | slot2[dim]]
+    int stride;              // dim * (1 + nslots)
+};
+
+struct DenseTensor {         // one trainable dense tensor inside the dense arena
+    int64_t off;             // offset in arena (floats)
+    int64_t count;           // physical element count
+    int rows, cols;          // physical shape (rows = K_phys for kernels, 1 for vectors)
+    // gradient partials: grad[i] = sum_p gpart[p * gstride + i]
+    int64_t gpart_off;       // offset in the partial buffer
+    int gparts;
+    int g_rowtiles;          // 1: partials are per 128-row batch tile (only the tiles of the current batch are live)
+    int64_t gstride;
+    int64_t wt_off;          // offset of the transposed copy in the wt buffer, -1 if none
+};
+
+struct Seg {                 // one source of a layer input
+    int src;                 // -1: deep input x, >=0: hidden layer index of the same tower
+    int width;               // logical width
+    int width_phys;          // padded to 32
+    int k_off;               // physical row offset inside the layer's kernel
+};
+
+struct Layer {
+    int n_in_segs;
+    Seg segs[kMaxSegs];
+    int K, K_phys;           // logical / physical input width
+    int N, N_phys;           // logical / physical output width (1 for logits)
+    int t_kernel, t_bias, t_gamma, t_beta;   // indices into Model::dense (-1 if absent)
+    // activations (hidden layers only), all [max_batch_pad, N_phys] unless noted
+    float* A;                // post-activation (pre-BN); == H when no batch norm
+    float* H;                // layer output
+    float* HT;               // transposed output [N_phys, ldt]
+    float* dH;               // gradient w.r.t. H (accumulated over consumers)
+    float* dZ;               // gradient w.r.t. pre-activation
+    float* dZT;              // transposed [N_phys, ldt]
+    float* colpart;          // [3][row_tiles][N_phys] partial column sums: dbias, dgamma, dbeta
+};
+
+struct Tower {
+    int n_hidden;
+    int mode;
+    std::vector<Layer> layers;   // n_hidden hidden layers + 1 logits layer
+    float* logit;                // [max_batch]
+};
+
+struct PhaseTimer {
+    cudaEvent_t ev[9];
+    bool enabled = false;
+};
+
+}  // namespace wd
+
+struct WdModel {
+    // ---- host copy of the plan
+    int device = 0;
+    bool use_wide = false, use_deep = false;
+    int n_cat_fields = 0, n_dense_fields = 0, n_columns = 0;
+    std::vector<int32_t> col_kind, col_field, col_aux_off, col_aux_n, col_norm_kind, col_emb_table, col_ind_off;
+    std::vector<int64_t> col_buckets, col_wide_base;
+    std::vector<float> col_norm_a, col_norm_b;
+    int n_numeric = 0;
+    int d0_phys = 0;
+    int64_t wide_rows = 0;
+    int activation = 0, batch_norm = 0;
+    WdOptimizer lin_opt{}, dnn_opt{};
+    int max_batch = 0, max_batch_pad = 0;   // pad: multiple of 128 (leading dim of transposed buffers)
+    int64_t max_nnz = 0;
+    int gemm_engine = 0;
+
+    cudaStream_t stream = nullptr;
+    wd::DevPlan dplan{};
+    std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
+    int64_t bytes_allocated = 0;
+
+    // numeric deep columns (device arrays)
+    int32_t *d_num_field = nullptr, *d_num_norm_kind = nullptr, *d_num_x0_off = nullptr;
+    float *d_num_a = nullptr, *d_num_b = nullptr;
+
+    // ---- batch buffers
+    int32_t* d_cat_offsets = nullptr;
+    uint64_t* d_cat_keys = nullptr;
+    int64_t keys_cap = 0;
+    float *d_dense = nullptr, *d_label = nullptr, *d_weight = nullptr;
+    wd::DevBatch dbatch{};
+    bool batch_has_label = false;
+
+    // ---- column ids (CSR over (row, column)) and per-entry arrays
+    int32_t* d_col_offs = nullptr;           // [max_batch * n_columns + 1]
+    uint32_t* d_e_wide = nullptr;            // [max_nnz] global wide row or kInvalidRow
+    uint32_t* d_e_emb = nullptr;             // [max_nnz] global embedding row or kInvalidRow
+    int32_t* d_e_bc = nullptr;               // [max_nnz] row * n_columns + column
+    int32_t* d_e_id = nullptr;               // [max_nnz] column-local id (debug / parity)
+    int32_t* d_nnz = nullptr;                // device scalar: entries this step
+    int32_t* d_flags = nullptr;              // device error flags [4]
+    void* d_scan_tmp = nullptr;
+
+    // ---- wide part: record {w, n, z, 0} per row
+    float4* d_wide = nullptr;
+    float* d_wide_logit = nullptr;           // [max_batch]
+
+    // ---- deep part
+    std::vector<wd::EmbTable> tables;
+    int64_t emb_total_rows = 0;
+    int emb_max_dim = 0;
+    int n_dims = 0;
+    int dims[wd::kMaxDims];                  // distinct widths
+    int32_t* d_dim_tables[wd::kMaxDims];     // table ids per width (device)
+    int dim_ntables[wd::kMaxDims];
+    // device table descriptors
+    float** d_tab_data = nullptr;
+    int32_t *d_tab_dim = nullptr, *d_tab_stride = nullptr, *d_tab_x0 = nullptr, *d_tab_col = nullptr;
+    int64_t* d_tab_row_base = nullptr;
+    float *d_X0 = nullptr, *d_X0T = nullptr, *d_dX0 = nullptr;
+    int ldt = 0;                             // leading dim of transposed activations (= max_batch_pad)
+    std::vector<wd::Tower> towers;
+
+    // ---- dense parameter arena
+    std::vector<wd::DenseTensor> dense;
+    int64_t dense_count = 0, gpart_count = 0, wt_count = 0;
+    float *d_P = nullptr, *d_S1 = nullptr, *d_S2 = nullptr, *d_G = nullptr, *d_gpart = nullptr, *d_Wt = nullptr;
+    wd::DenseTensor* d_dense_desc = nullptr;
+    int row_tiles = 0;                       // max_batch_pad / 128
+    int wgrad_splits = 4;
+
+    // ---- loss / logits
+    float* d_logits = nullptr;               // [max_batch]
+    float* d_dlogit = nullptr;               // [max_batch]
+    float* d_loss_part = nullptr;            // per-block partials
+    float* d_loss = nullptr;                 // scalar
+    float* h_loss_pinned = nullptr;
+
+    // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
+    uint32_t *d_sk[2] = {nullptr, nullptr}, *d_sv[2] = {nullptr, nullptr};     // ping-pong keys / values
+    uint32_t *d_sk2[2] = {nullptr, nullptr}, *d_sv2[2] = {nullptr, nullptr};
+    int32_t* d_sort_hist = nullptr;
+    int64_t sort_hist_cap = 0;
+    int32_t* d_sort_counter = nullptr;
+    uint32_t* d_urow[2] = {nullptr, nullptr};   // unique rows
+    int32_t* d_ustart[2] = {nullptr, nullptr};  // segment starts in the sorted list (+1 sentinel)
+    float* d_ugrad[2] = {nullptr, nullptr};     // [cap, width]
+    int32_t* d_nuniq[2] = {nullptr, nullptr};   // device scalars
+    int32_t* d_nvalid[2] = {nullptr, nullptr};
+    int64_t sparse_cap[2] = {0, 0};
+    bool sparse_overridden[2] = {false, false};
+    int64_t sparse_override_n[2] = {0, 0};
+    int sort_bits[2] = {0, 0};
+
+    // ---- eval metrics
+    double* d_metrics = nullptr;             // accumulators
+    int64_t eval_batches = 0;
+
+    int64_t launches = 0;
+    wd::PhaseTimer timer;
+    float last_ms[8] = {0};
+    bool initialized = false;
+    bool grads_pending = false;
+};
+
+namespace wd {
+// ---- kernels / stages implemented in the .cu files (all enqueue on m->stream)
+int ids_prepare(WdModel* m);                                     // ids.cu
+int sparse_forward(WdModel* m);                                  // sparse.cu: wide logit + embedding pooling + numerics
+int sparse_backward_reduce(WdModel* m);                          // sparse.cu: sort + per-row gradient sums
+int sparse_apply(WdModel* m);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
+int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
+int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0
+int dense_reduce_grads(WdModel* m);                              // mlp.cu
+int dense_apply(WdModel* m);                                     // mlp.cu
+int loss_forward(WdModel* m, bool need_grad);                    // mlp.cu: logits = wide + deep, loss, dlogit
+int model_init_params(WdModel* m, uint64_t seed);                // init.cu
+int metrics_accumulate(WdModel* m);                              // metrics.cu
+int metrics_finish(WdModel* m, double* out10);
+
+int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n);   // sort.cu
+int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out);   // sort.cu (in place, n known on host)
+
+template <typename T>
+int dev_alloc(WdModel* m, T** p, int64_t count, bool zero = true) {
+    if (count <= 0) count = 1;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+        return WD_ENOMEM;
+    }
+    if (zero) {
+        e = cudaMemsetAsync(q, 0, (size_t)count * sizeof(T), m->stream);
+        if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return WD_ECUDA; }
+    }
+    m->allocs.push_back(q);
+    m->bytes_allocated += count * (int64_t)sizeof(T);
+    *p = (T*)q;
+    return WD_OK;
+}
+
+inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+}  // namespace wd

@@ -1,0 +1,643 @@
+// Dense half of the step: the Dnn / ResDnn / DenseDnn towers, the binary head, their backward and the
+// dense optimizers.
+//
+//   layer forward    act(x W + b) -> [BN inference affine] -> concat          (reference dnn.py:92-233)
+//   head             logits = sum of tower logits + wide logit; sigmoid CE, SUM (reference joint.py:216-222, 402-406)
+//   backward         MatMul grads, activation / affine grads                  (reference joint.py:234-239 minimize())
+//   dense optimizer  ApplyAdagrad / ApplyFtrl / SGD with constant LR (Q1)     (reference model_util.py:62-105)
+//
+// Every matrix product is a "TN" GEMM  C[M,N] = sum_k A[M,k] * B[N,k]  (both operands K-contiguous):
+//   forward   A = layer input segments [batch, K],  B = Wt [N, K]
+//   dgrad     A = dZ [batch, N],                    B = W  [K, N] rows of one input segment
+//   wgrad     A = inputT [K, batch],                B = dZT [N, batch]     (split over the batch)
+// which is why activations and gradients are also kept transposed.  This file holds the fp32 CUDA-core
+// (FFMA) engine — exact fp32 products, used as the parity engine and as the reference the tcgen05 engine
+// (gemm_tc.cu) is validated against.
+#include "common.cuh"
+
+namespace wd {
+
+// --------------------------------------------------------------------------------------------- activations
+__device__ __forceinline__ float act_fwd(int kind, float z) {
+    switch (kind) {
+        case WD_ACT_RELU: return fmaxf(z, 0.f);
+        case WD_ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
+        case WD_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+        case WD_ACT_TANH: return tanhf(z);
+        case WD_ACT_LEAKY_RELU: return z > 0.f ? z : 0.2f * z;
+        case WD_ACT_ELU: return z > 0.f ? z : expm1f(z);
+        case WD_ACT_SELU: return 1.0507009873554805f * (z > 0.f ? z : 1.6732632423543772f * expm1f(z));
+        case WD_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+        case WD_ACT_SOFTSIGN: return z / (1.f + fabsf(z));
+    }
+    return z;
+}
+// derivative expressed through the stored post-activation value a
+__device__ __forceinline__ float act_bwd(int kind, float a) {
+    switch (kind) {
+        case WD_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+        case WD_ACT_RELU6: return (a > 0.f && a < 6.f) ? 1.f : 0.f;
+        case WD_ACT_SIGMOID: return a * (1.f - a);
+        case WD_ACT_TANH: return 1.f - a * a;
+        case WD_ACT_LEAKY_RELU: return a > 0.f ? 1.f : 0.2f;
+        case WD_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+        case WD_ACT_SELU: return a > 0.f ? 1.0507009873554805f : a + 1.0507009873554805f * 1.6732632423543772f;
+        case WD_ACT_SOFTPLUS: return 1.f - expf(-a);
+        case WD_ACT_SOFTSIGN: { float t = 1.f - fabsf(a); return t * t; }
+    }
+    return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------- FFMA GEMM
+struct GemmA {                         // A operand: up to kMaxSegs K-contiguous segments
+    int n;
+    const float* ptr[kMaxSegs];
+    int ld[kMaxSegs];
+    int k[kMaxSegs];                   // multiple of 16
+};
+enum { EPI_FWD = 0, EPI_STORE = 1, EPI_WGRAD = 2 };
+struct Epi {
+    float* C; int ldc;                 // STORE / WGRAD target
+    int accumulate;                    // STORE: C += acc
+    float* A_out; float* H_out; int ldh;   // FWD outputs
+    float* HT; int ldt;                // FWD transposed output (nullable)
+    const float *bias, *gamma, *beta;
+    int n_logical, act, bn;
+    int m_valid;                       // rows >= m_valid are written as zero (transposed padding)
+    int64_t split_stride;              // WGRAD: floats between split partials
+};
+
+constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(GT) gemm_tn_ffma(GemmA A, const float* __restrict__ Bm, int ldb, int M, int N, int ksplit_len, Epi ep) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // K range of this CTA (split over blockIdx.z in WGRAD); segments are walked in order
+    int ktot = 0;
+    for (int s = 0; s < A.n; ++s) ktot += A.k[s];
+    int kbeg = 0, kend = ktot;
+    if (MODE == EPI_WGRAD) {
+        kbeg = blockIdx.z * ksplit_len;
+        kend = min(ktot, kbeg + ksplit_len);
+    }
+    const int lrow = tid >> 2, lkc = tid & 3;          // load mapping: 64 rows x 4 k-chunks per pass, 2 passes
+    float4 ra[2], rb[2];
+
+    auto gload = [&](int kg) {                         // kg: global k (multiple of 16) in concatenated space
+        int s = 0, kk = kg;
+        while (s < A.n - 1 && kk >= A.k[s]) { kk -= A.k[s]; ++s; }
+        const float* ap = A.ptr[s];
+        const int lda = A.ld[s];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            int r = lrow + p * 64;
+            int gm = m0 + r, gn = n0 + r;
+            ra[p] = (gm < M) ? *reinterpret_cast<const float4*>(ap + (int64_t)gm * lda + kk + lkc * 4) : make_float4(0, 0, 0, 0);
+            rb[p] = (gn < N) ? *reinterpret_cast<const float4*>(Bm + (int64_t)gn * ldb + kg + lkc * 4) : make_float4(0, 0, 0, 0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            int r = lrow + p * 64;
+            As[buf][lkc * 4 + 0][r] = ra[p].x; As[buf][lkc * 4 + 1][r] = ra[p].y;
+            As[buf][lkc * 4 + 2][r] = ra[p].z; As[buf][lkc * 4 + 3][r] = ra[p].w;
+            Bs[buf][lkc * 4 + 0][r] = rb[p].x; Bs[buf][lkc * 4 + 1][r] = rb[p].y;
+            Bs[buf][lkc * 4 + 2][r] = rb[p].z; Bs[buf][lkc * 4 + 3][r] = rb[p].w;
+        }
+    };
+
+    int buf = 0;
+    if (kbeg < kend) {
+        gload(kbeg);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int kg = kbeg; kg < kend; kg += BK) {
+        bool more = kg + BK < kend;
+        if (more) gload(kg + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) sstore(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // ---- epilogue: thread owns rows {ty*4+i, 64+ty*4+i}, cols {tx*4+j, 64+tx*4+j}
+#pragma unroll
+    for (int ih = 0; ih < 2; ++ih) {
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int mb = m0 + ih * 64 + ty * 4, nb = n0 + jh * 64 + tx * 4;
+            if (nb >= N) continue;
+            if (MODE == EPI_FWD) {
+                float hv[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int gm = mb + i;
+                    float a4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int gn = nb + j;
+                        float a = 0.f, h = 0.f;
+                        if (gn < ep.n_logical && gm < ep.m_valid) {
+                            a = act_fwd(ep.act, acc[ih * 4 + i][jh * 4 + j] + ep.bias[gn]);
+                            h = ep.bn ? a * (ep.gamma[gn] * 0.99950037468777f) + ep.beta[gn] : a;   // 1/sqrt(1+1e-3)
+                        }
+                        a4[j] = a;
+                        hv[i][j] = h;
+                    }
+                    if (gm < M) {
+                        if (ep.A_out != ep.H_out)
+                            *reinterpret_cast<float4*>(ep.A_out + (int64_t)gm * ep.ldh + nb) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                        *reinterpret_cast<float4*>(ep.H_out + (int64_t)gm * ep.ldh + nb) = make_float4(hv[i][0], hv[i][1], hv[i][2], hv[i][3]);
+                    }
+                }
+                if (ep.HT) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(ep.HT + (int64_t)(nb + j) * ep.ldt + mb) = make_float4(hv[0][j], hv[1][j], hv[2][j], hv[3][j]);
+                }
+            } else {
+                float* Cb = ep.C + (MODE == EPI_WGRAD ? (int64_t)blockIdx.z * ep.split_stride : 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int gm = mb + i;
+                    if (gm >= M) continue;
+                    float4 v = make_float4(acc[ih * 4 + i][jh * 4 + 0], acc[ih * 4 + i][jh * 4 + 1], acc[ih * 4 + i][jh * 4 + 2], acc[ih * 4 + i][jh * 4 + 3]);
+                    float4* dst = reinterpret_cast<float4*>(Cb + (int64_t)gm * ep.ldc + nb);
+                    if (MODE == EPI_STORE && ep.accumulate) {
+                        float4 o = *dst;
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    *dst = v;
+                }
+            }
+        }
+    }
+}
+
+static void launch_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len) {
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, mode == EPI_WGRAD ? splits : 1);
+    if (mode == EPI_FWD) gemm_tn_ffma<EPI_FWD><<<grid, GT, 0, m->stream>>>(A, B, ldb, M, N, 0, ep);
+    else if (mode == EPI_STORE) gemm_tn_ffma<EPI_STORE><<<grid, GT, 0, m->stream>>>(A, B, ldb, M, N, 0, ep);
+    else gemm_tn_ffma<EPI_WGRAD><<<grid, GT, 0, m->stream>>>(A, B, ldb, M, N, ksplit_len, ep);
+    m->launches++;
+}
+
+// tcgen05 engine (gemm_tc.cu); returns WD_EUNSUPPORTED when the shape is not covered
+int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len);
+
+static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits = 1, int ksplit_len = 0) {
+    if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
+        int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
+        if (rc != WD_EUNSUPPORTED) return rc;
+    }
+    launch_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
+    return WD_OK;
+}
+
+// --------------------------------------------------------------------------------------- small kernels
+// out[n][m] = in[m][n] for m < M (zeros for M <= m < Mpad), 32x32 tiles through shared memory
+__global__ void transpose_kernel(const float* __restrict__ in, int ld_in, int M, int Mpad, int N, float* __restrict__ out, int ld_out) {
+    __shared__ float t[32][33];
+    int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int mm = m0 + i, nn = n0 + threadIdx.x;
+        t[i][threadIdx.x] = (mm < M && nn < N) ? in[(int64_t)mm * ld_in + nn] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int nn = n0 + i, mm = m0 + threadIdx.x;
+        if (nn < N && mm < Mpad) out[(int64_t)nn * ld_out + mm] = t[threadIdx.x][i];
+    }
+}
+
+// logits layer forward: one warp per example, dot over the concatenated sources
+struct GemvSegs { int n; const float* ptr[kMaxSegs]; int ld[kMaxSegs]; int k[kMaxSegs]; int koff[kMaxSegs]; };
+__global__ void __launch_bounds__(256) logits_fwd_kernel(GemvSegs S, const float* __restrict__ kernel, const float* __restrict__ bias,
+                                                        int B, float* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int b = warp; b < B; b += nw) {
+        float acc = 0.f;
+        for (int s = 0; s < S.n; ++s) {
+            const float* row = S.ptr[s] + (int64_t)b * S.ld[s];
+            const float* kw = kernel + S.koff[s];
+            for (int k = lane * 4; k < S.k[s]; k += 128) {
+                float4 x = *reinterpret_cast<const float4*>(row + k);
+                float4 w = *reinterpret_cast<const float4*>(kw + k);
+                acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) out[b] = acc + bias[0];
+    }
+}
+
+// head: logits = wide + sum of towers; per-example loss; dlogit = (sigmoid(x) - y) * w; block partial sums
+struct TowerLogits { int n; const float* p[8]; };
+__global__ void __launch_bounds__(256) head_kernel(int B, const float* __restrict__ wide_logit, TowerLogits T,
+                                                  const float* __restrict__ label, const float* __restrict__ weight,
+                                                  float* __restrict__ logits, float* __restrict__ dlogit, float* __restrict__ loss_part) {
+    __shared__ float red[8];
+    float lsum = 0.f;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x = wide_logit ? wide_logit[b] : 0.f;
+        for (int t = 0; t < T.n; ++t) x += T.p[t][b];
+        logits[b] = x;
+        if (label) {
+            float y = label[b], w = weight ? weight[b] : 1.f;
+            // sigmoid cross entropy with logits: max(x,0) - x*y + log1p(exp(-|x|))   
+            float l = fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+            lsum += w * l;
+            if (dlogit) dlogit[b] = (1.f / (1.f + expf(-x)) - y) * w;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        loss_part[blockIdx.x] = s;
+    }
+}
+__global__ void loss_final_kernel(const float* __restrict__ part, int n, float* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += (double)part[i];
+        *out = (float)s;
+    }
+}
+
+// logits layer backward, data part: dsrc[b, k] (+)= dlogit[b] * kernel[koff + k]
+__global__ void logits_dgrad_kernel(int B, int K, const float* __restrict__ dlogit, const float* __restrict__ kw,
+                                    float* __restrict__ dst, int ld, int accumulate) {
+    int64_t total = (int64_t)B * (K / 4);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int b = (int)(t / (K / 4)), k = (int)(t % (K / 4)) * 4;
+        float g = dlogit[b];
+        float4 w = *reinterpret_cast<const float4*>(kw + k);
+        float4* d = reinterpret_cast<float4*>(dst + (int64_t)b * ld + k);
+        float4 v = make_float4(g * w.x, g * w.y, g * w.z, g * w.w);
+        if (accumulate) { float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *d = v;
+    }
+}
+// logits layer backward, weight part: gpart[rt][koff + k] = sum_{b in row tile} src[b,k] * dlogit[b]; bias likewise
+__global__ void __launch_bounds__(256) logits_wgrad_kernel(int B, int K, const float* __restrict__ src, int ld,
+                                                          const float* __restrict__ dlogit, float* __restrict__ gpart,
+                                                          int64_t gstride, float* __restrict__ bias_part, int64_t bias_stride) {
+    int rt = blockIdx.y;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int b0 = rt * 128, b1 = min(B, b0 + 128);
+    if (k < K) {
+        float acc = 0.f;
+        for (int b = b0; b < b1; ++b) acc = fmaf(src[(int64_t)b * ld + k], dlogit[b], acc);
+        gpart[(int64_t)rt * gstride + k] = acc;
+    }
+    if (bias_part && blockIdx.x == 0 && threadIdx.x == 0) {
+        float s = 0.f;
+        for (int b = b0; b < b1; ++b) s += dlogit[b];
+        bias_part[(int64_t)rt * bias_stride] = s;
+    }
+}
+
+// hidden layer backward through [BN affine] and activation:
+//   da = dH * gamma/sqrt(1+eps); dZ = da * act'(a); column partial sums of dZ (bias), dH*a/sqrt(1+eps) (gamma), dH (beta)
+// block = 32 columns x 128 rows (one row tile); writes dZ and dZT (zero padded to the tile)
+__global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_logical, const float* __restrict__ dH, const float* __restrict__ Aact,
+                                                        int ld, const float* __restrict__ gamma, int act, int bn,
+                                                        float* __restrict__ dZ, float* __restrict__ dZT, int ldt,
+                                                        float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
+                                                        int64_t pstride) {
+    __shared__ float tile[32][33];
+    __shared__ float red[3][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int n = blockIdx.x * 32 + tx, rt = blockIdx.y;
+    const float inv = 0.99950037468777f;
+    float sb = 0.f, sg = 0.f, sbe = 0.f;
+    const float gsc = (bn && n < n_logical) ? gamma[n] * inv : 1.f;
+    for (int sub = 0; sub < 4; ++sub) {                           // 4 sub-tiles of 32 rows
+        const int mbase = rt * 128 + sub * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int mm = mbase + ty * 4 + i;
+            float dz = 0.f;
+            if (mm < B && n < n_logical) {
+                float dh = dH[(int64_t)mm * ld + n], a = Aact[(int64_t)mm * ld + n];
+                dz = dh * gsc * act_bwd(act, a);
+                sb += dz; sg += dh * a * inv; sbe += dh;
+            }
+            if (mm < B && n < N) dZ[(int64_t)mm * ld + n] = dz;
+            tile[ty * 4 + i][tx] = dz;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int nn = blockIdx.x * 32 + ty * 4 + i;
+            if (nn < N) dZT[(int64_t)nn * ldt + mbase + tx] = tile[tx][ty * 4 + i];
+        }
+        __syncthreads();
+    }
+    red[0][ty][tx] = sb; red[1][ty][tx] = sg; red[2][ty][tx] = sbe;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[0][i][tx]; b += red[1][i][tx]; c += red[2][i][tx]; }
+        p_bias[(int64_t)rt * pstride + n] = a;
+        if (bn) { p_gamma[(int64_t)rt * pstride + n] = b; p_beta[(int64_t)rt * pstride + n] = c; }
+    }
+}
+
+// wide bias gradient partials: per 128-row tile sum of dlogit
+__global__ void rowtile_sum_kernel(int B, const float* __restrict__ v, float* __restrict__ part, int64_t stride) {
+    int rt = blockIdx.x;
+    int b0 = rt * 128, b1 = min(B, b0 + 128);
+    float s = 0.f;
+    for (int b = b0 + threadIdx.x; b < b1; b += 32) s += v[b];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (threadIdx.x == 0) part[(int64_t)rt * stride] = s;
+}
+int wide_bias_grad(WdModel* m) {
+    if (!m->use_wide) return WD_OK;
+    const int rts = (m->dbatch.B + 127) / 128;
+    rowtile_sum_kernel<<<rts, 32, 0, m->stream>>>(m->dbatch.B, m->d_dlogit, m->d_gpart + m->dense[0].gpart_off, m->dense[0].gstride);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// ---------------------------------------------------------------------------------- dense optimizer side
+// G[i] = sum_p gpart[t.gpart_off + p * t.gstride + (i - t.off)] over the live partials of tensor t
+__global__ void dense_reduce_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ gpart,
+                                    float* __restrict__ G, int live_row_tiles) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = nt - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (T[mid].off <= i) lo = mid; else hi = mid - 1;
+        }
+        const DenseTensor t = T[lo];
+        if (i - t.off >= t.count) { G[i] = 0.f; continue; }          // alignment gap between tensors
+        int parts = t.g_rowtiles ? live_row_tiles : t.gparts;              // row-tile partials: only tiles of this batch
+        float s = 0.f;
+        const float* p = gpart + t.gpart_off + (i - t.off);
+        for (int q = 0; q < parts; ++q) s += p[(int64_t)q * t.gstride];
+        G[i] = s;
+    }
+}
+
+struct OptParamsD { int kind; float lr, l1, l2; };
+__device__ __forceinline__ void opt_update_d(const OptParamsD& o, float g, float& w, float& s1, float& s2) {
+    if (o.kind == WD_OPT_ADAGRAD) {
+        s1 += g * g;
+        w -= o.lr * g / sqrtf(s1);
+    } else if (o.kind == WD_OPT_FTRL) {
+        float n1 = s1 + g * g;
+        float z1 = s2 + g - (sqrtf(n1) - sqrtf(s1)) / o.lr * w;
+        float wn = 0.f;
+        if (fabsf(z1) > o.l1) wn = (copysignf(o.l1, z1) - z1) / (sqrtf(n1) / o.lr + 2.f * o.l2);
+        w = wn; s1 = n1; s2 = z1;
+    } else {
+        w -= o.lr * g;
+    }
+}
+// applies the optimizer over the dense arena; kernels also refresh their transposed copy Wt[n][k]
+__global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ G,
+                                   float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ Wt,
+                                   OptParamsD dnn, OptParamsD lin, int lin_tensor) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = nt - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (T[mid].off <= i) lo = mid; else hi = mid - 1;
+        }
+        const DenseTensor t = T[lo];
+        if (i - t.off >= t.count) continue;
+        float w = P[i], s1 = S1[i], s2 = S2[i];
+        opt_update_d(lo == lin_tensor ? lin : dnn, G[i], w, s1, s2);
+        P[i] = w; S1[i] = s1; S2[i] = s2;
+        if (t.wt_off >= 0) {
+            int64_t e = i - t.off;
+            int k = (int)(e / t.cols), n = (int)(e % t.cols);
+            Wt[t.wt_off + (int64_t)n * t.rows + k] = w;
+        }
+    }
+}
+// Wt refresh only (after init / tensor upload)
+__global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ P, float* __restrict__ Wt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = nt - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (T[mid].off <= i) lo = mid; else hi = mid - 1;
+        }
+        const DenseTensor t = T[lo];
+        if (t.wt_off >= 0 && i - t.off < t.count) {
+            int64_t e = i - t.off;
+            int k = (int)(e / t.cols), n = (int)(e % t.cols);
+            Wt[t.wt_off + (int64_t)n * t.rows + k] = P[i];
+        }
+    }
+}
+int dense_refresh_transposes(WdModel* m) {
+    if (m->dense_count == 0) return WD_OK;
+    dense_transpose_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_P, m->d_Wt);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host drivers
+static const float* src_ptr(WdModel* m, Tower& tw, int src, bool transposed) {
+    if (src < 0) return transposed ? m->d_X0T : m->d_X0;
+    return transposed ? tw.layers[src].HT : tw.layers[src].H;
+}
+static int src_ld(WdModel* m, Tower& tw, int src, bool transposed) {
+    if (transposed) return m->ldt;
+    return src < 0 ? m->d0_phys : tw.layers[src].N_phys;
+}
+
+int mlp_forward(WdModel* m, bool train) {
+    const int B = m->dbatch.B;
+    if (!m->use_deep) return WD_OK;
+    if (train) {                                       // X0T for the first layer's weight gradient
+        int Bp = (B + 127) / 128 * 128;
+        dim3 g((m->d0_phys + 31) / 32, (Bp + 31) / 32);
+        transpose_kernel<<<g, dim3(32, 8), 0, m->stream>>>(m->d_X0, m->d0_phys, B, Bp, m->d0_phys, m->d_X0T, m->ldt);
+        m->launches++;
+    }
+    for (auto& tw : m->towers) {
+        for (int l = 0; l < tw.n_hidden; ++l) {
+            Layer& L = tw.layers[l];
+            GemmA A{};
+            A.n = L.n_in_segs;
+            for (int s = 0; s < L.n_in_segs; ++s) {
+                A.ptr[s] = src_ptr(m, tw, L.segs[s].src, false);
+                A.ld[s] = src_ld(m, tw, L.segs[s].src, false);
+                A.k[s] = L.segs[s].width_phys;
+            }
+            Epi ep{};
+            ep.A_out = L.A; ep.H_out = L.H; ep.ldh = L.N_phys;
+            ep.HT = train ? L.HT : nullptr; ep.ldt = m->ldt;
+            ep.bias = m->d_P + m->dense[L.t_bias].off;
+            ep.gamma = L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr;
+            ep.beta = L.t_beta >= 0 ? m->d_P + m->dense[L.t_beta].off : nullptr;
+            ep.n_logical = L.N; ep.act = m->activation; ep.bn = m->batch_norm; ep.m_valid = B;
+            const float* Wt = m->d_Wt + m->dense[L.t_kernel].wt_off;
+            int rc = run_gemm(m, EPI_FWD, A, Wt, L.K_phys, B, L.N_phys, ep);
+            if (rc) return rc;
+        }
+        Layer& LL = tw.layers[tw.n_hidden];
+        GemvSegs S{};
+        S.n = LL.n_in_segs;
+        for (int s = 0; s < LL.n_in_segs; ++s) {
+            S.ptr[s] = src_ptr(m, tw, LL.segs[s].src, false);
+            S.ld[s] = src_ld(m, tw, LL.segs[s].src, false);
+            S.k[s] = LL.segs[s].width_phys;
+            S.koff[s] = LL.segs[s].k_off;
+        }
+        logits_fwd_kernel<<<grid_for((int64_t)B * 32, 256), 256, 0, m->stream>>>(S, m->d_P + m->dense[LL.t_kernel].off,
+                                                                                m->d_P + m->dense[LL.t_bias].off, B, tw.logit);
+        m->launches++;
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int loss_forward(WdModel* m, bool need_grad) {
+    const int B = m->dbatch.B;
+    TowerLogits T{};
+    T.n = m->use_deep ? (int)m->towers.size() : 0;
+    for (int t = 0; t < T.n; ++t) T.p[t] = m->towers[t].logit;
+    int blocks = grid_for(B, 256, 256);
+    head_kernel<<<blocks, 256, 0, m->stream>>>(B, m->use_wide ? m->d_wide_logit : nullptr, T, m->batch_has_label ? m->d_label : nullptr,
+                                              m->dbatch.weight, m->d_logits, need_grad ? m->d_dlogit : nullptr, m->d_loss_part);
+    loss_final_kernel<<<1, 32, 0, m->stream>>>(m->d_loss_part, blocks, m->d_loss);
+    m->launches += 2;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int mlp_backward(WdModel* m) {
+    const int B = m->dbatch.B;
+    if (!m->use_deep) return WD_OK;
+    const int rts = (B + 127) / 128;
+    const int Bk = (B + 15) / 16 * 16;                                // reduction length of wgrad
+    bool dx0_written = false;
+    const bool need_dx0 = !m->tables.empty();
+    for (auto& tw : m->towers) {
+        std::vector<char> written(tw.n_hidden, 0);
+        auto grad_dst = [&](int src, float** p, int* ld, int* acc) {
+            if (src < 0) { *p = m->d_dX0; *ld = m->d0_phys; *acc = dx0_written ? 1 : 0; dx0_written = true; }
+            else { *p = tw.layers[src].dH; *ld = tw.layers[src].N_phys; *acc = written[src] ? 1 : 0; written[src] = 1; }
+        };
+        // ---- logits layer
+        Layer& LL = tw.layers[tw.n_hidden];
+        const DenseTensor& tk = m->dense[LL.t_kernel];
+        const DenseTensor& tb = m->dense[LL.t_bias];
+        for (int s = 0; s < LL.n_in_segs; ++s) {
+            const Seg& sg = LL.segs[s];
+            const float* src = src_ptr(m, tw, sg.src, false);
+            int ld = src_ld(m, tw, sg.src, false);
+            dim3 g((sg.width_phys + 255) / 256, rts);
+            logits_wgrad_kernel<<<g, 256, 0, m->stream>>>(B, sg.width_phys, src, ld, m->d_dlogit, m->d_gpart + tk.gpart_off + sg.k_off,
+                                                         tk.gstride, s == 0 ? m->d_gpart + tb.gpart_off : nullptr, tb.gstride);
+            m->launches++;
+            if (sg.src < 0 && !need_dx0) continue;
+            float* dst; int dld, acc;
+            grad_dst(sg.src, &dst, &dld, &acc);
+            logits_dgrad_kernel<<<grid_for((int64_t)B * sg.width_phys / 4, 256), 256, 0, m->stream>>>(
+                B, sg.width_phys, m->d_dlogit, m->d_P + tk.off + sg.k_off, dst, dld, acc);
+            m->launches++;
+        }
+        // ---- hidden layers, last to first
+        for (int l = tw.n_hidden - 1; l >= 0; --l) {
+            Layer& L = tw.layers[l];
+            const DenseTensor& tkn = m->dense[L.t_kernel];
+            float* pb = m->d_gpart + m->dense[L.t_bias].gpart_off;
+            float* pg = L.t_gamma >= 0 ? m->d_gpart + m->dense[L.t_gamma].gpart_off : nullptr;
+            float* pbe = L.t_beta >= 0 ? m->d_gpart + m->dense[L.t_beta].gpart_off : nullptr;
+            if (!written[l]) {                                        // layer output unused downstream (cannot happen for valid modes)
+                WD_CUDA(cudaMemsetAsync(L.dH, 0, (size_t)m->max_batch_pad * L.N_phys * sizeof(float), m->stream));
+            }
+            dim3 g((L.N_phys + 31) / 32, rts);
+            act_bn_bwd_kernel<<<g, 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
+                                                       L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
+                                                       m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride);
+            m->launches++;
+            for (int s = 0; s < L.n_in_segs; ++s) {
+                const Seg& sg = L.segs[s];
+                // weight gradient of the rows fed by this segment: [width_phys, N] = srcT * dZT^T, split over the batch
+                GemmA A{};
+                A.n = 1; A.ptr[0] = src_ptr(m, tw, sg.src, true); A.ld[0] = m->ldt; A.k[0] = Bk;
+                Epi ep{};
+                ep.C = m->d_gpart + tkn.gpart_off + (int64_t)sg.k_off * L.N_phys; ep.ldc = L.N_phys; ep.split_stride = tkn.gstride;
+                int ks = ((Bk + m->wgrad_splits - 1) / m->wgrad_splits + 15) / 16 * 16;
+                int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, m->ldt, sg.width_phys, L.N_phys, ep, m->wgrad_splits, ks);
+                if (rc) return rc;
+                // data gradient into the source
+                if (sg.src < 0 && !need_dx0) continue;
+                float* dst; int dld, acc;
+                grad_dst(sg.src, &dst, &dld, &acc);
+                GemmA A2{};
+                A2.n = 1; A2.ptr[0] = L.dZ; A2.ld[0] = L.N_phys; A2.k[0] = L.N_phys;
+                Epi e2{};
+                e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
+                rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2);
+                if (rc) return rc;
+            }
+        }
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int dense_reduce_grads(WdModel* m) {
+    if (m->dense_count == 0) return WD_OK;
+    const int rts = (m->dbatch.B + 127) / 128;
+    dense_reduce_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count,
+                                                                             m->d_gpart, m->d_G, rts);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int dense_apply(WdModel* m) {
+    if (m->dense_count == 0) return WD_OK;
+    OptParamsD d{m->dnn_opt.kind, m->dnn_opt.lr, m->dnn_opt.l1, m->dnn_opt.l2};
+    OptParamsD l{m->lin_opt.kind, m->lin_opt.lr, m->lin_opt.l1, m->lin_opt.l2};
+    int lin_tensor = m->use_wide ? 0 : -1;                       // tensor 0 is the wide bias when the wide part exists
+    dense_apply_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_G,
+                                                                            m->d_P, m->d_S1, m->d_S2, m->d_Wt, d, l, lin_tensor);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+}  // namespace wd

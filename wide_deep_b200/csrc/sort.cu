@@ -1,0 +1,259 @@
+// Device primitives for the sparse backward: exclusive scan and a stable LSD radix sort of (key, value)
+// pairs whose length lives in DEVICE memory (no host sync between the id stage and the backward).
+//
+// The sort groups the step's (row id -> occurrence) pairs so that every touched table row gets exactly
+// one optimizer update from the ordered sum of its gradients — TensorFlow's "sum duplicates, apply once"
+// semantics for IndexedSlices — without float atomics (bit-reproducible run to run).
+#include "common.cuh"
+
+namespace wd {
+
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) >= d) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x multiple of 32, <= 1024); returns exclusive
+// prefix, *total = block sum.  smem: 33 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int* smem, int* total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < nw ? smem[lane] : 0;
+        int si = warp_incl_scan(s);
+        smem[lane] = si - s;
+        if (lane == 31) smem[32] = si;
+    }
+    __syncthreads();
+    int r = inc - v + smem[w];
+    *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+// Phase 1: per-chunk exclusive scan in place + chunk totals; the last block to finish scans the totals.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chunks_kernel(int32_t* data, int64_t n, int32_t* chunk_sums,
+                                                                   int32_t* counter) {
+    __shared__ int sm[33];
+    __shared__ bool is_last;
+    int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? data[base + i] : 0;
+        s += v[i];
+    }
+    int tot;
+    int ex = block_excl_scan(s, sm, &tot);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) {
+        chunk_sums[blockIdx.x] = tot;
+        __threadfence();
+        int t = atomicAdd(counter, 1);
+        is_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // scan chunk_sums[0..gridDim.x) in place (exclusive), total at chunk_sums[gridDim.x]
+    int carry = 0;
+    for (int off = 0; off < (int)gridDim.x; off += SCAN_THREADS) {
+        int i = off + threadIdx.x;
+        int x = i < (int)gridDim.x ? ((volatile int32_t*)chunk_sums)[i] : 0;
+        int t2;
+        int e = block_excl_scan(x, sm, &t2);
+        if (i < (int)gridDim.x) chunk_sums[i] = e + carry;
+        carry += t2;
+    }
+    if (threadIdx.x == 0) {
+        chunk_sums[gridDim.x] = carry;
+        *counter = 0;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(int32_t* data, int64_t n, const int32_t* chunk_sums,
+                                                                int nchunks, int32_t* total_out) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int add = chunk_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) data[base + i] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = chunk_sums[nchunks];
+        data[n] = tot;                 // CSR sentinel
+        if (total_out) *total_out = tot;
+    }
+}
+
+// In-place exclusive scan of data[0..n) (n known on host); data[n] and *total_out receive the total.
+int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out) {
+    int nchunks = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (nchunks < 1) nchunks = 1;
+    int32_t* sums = (int32_t*)m->d_scan_tmp;
+    scan_chunks_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(data, n, sums, m->d_sort_counter);
+    scan_add_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(data, n, sums, nchunks, total_out);
+    m->launches += 2;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// ------------------------------------------------------------------------------------------ radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS_PER_WARP = 512;                 // 16 rounds of 32
+constexpr int RS_TILE = RS_WARPS * RS_ITEMS_PER_WARP;  // 4096 keys per tile
+constexpr int RS_MAX_BINS = 1024;
+
+// Per-tile digit histogram -> hist[bin * ntiles + tile]; last block turns hist into exclusive offsets.
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,
+                                                             int shift, int bins, int ntiles_cap, int32_t* hist,
+                                                             int32_t* counter) {
+    extern __shared__ int sh[];           // bins
+    __shared__ int sm[33];
+    __shared__ bool is_last;
+    const int n = *d_n;
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    const int tile = blockIdx.x;
+    if (tile < ntiles) {
+        for (int i = threadIdx.x; i < bins; i += RS_THREADS) sh[i] = 0;
+        __syncthreads();
+        int base = tile * RS_TILE;
+        for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+            int j = base + i;
+            if (j < n) atomicAdd(&sh[(keys[j] >> shift) & (bins - 1)], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < bins; i += RS_THREADS) hist[i * ntiles_cap + tile] = sh[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int t = atomicAdd(counter, 1);
+        is_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // exclusive scan over (bin major, tile minor) of the first `ntiles` tiles of each bin
+    int carry = 0;
+    const int total = bins * ntiles;
+    for (int off = 0; off < total; off += RS_THREADS * 4) {
+        int v[4], s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int i = off + threadIdx.x * 4 + k;
+            int idx = (i / ntiles) * ntiles_cap + (i % ntiles);
+            v[k] = i < total ? ((volatile int32_t*)hist)[idx] : 0;
+            s += v[k];
+        }
+        int tot;
+        int e = block_excl_scan(s, sm, &tot) + carry;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int i = off + threadIdx.x * 4 + k;
+            if (i < total) hist[(i / ntiles) * ntiles_cap + (i % ntiles)] = e;
+            e += v[k];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// Stable scatter of one tile.
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                const int32_t* __restrict__ d_n, int shift, int bins,
+                                                                int ntiles_cap, const int32_t* __restrict__ hist) {
+    extern __shared__ int wh[];           // [RS_WARPS][bins]
+    const int n = *d_n;
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    const int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) wh[i] = 0;
+    __syncthreads();
+    const int wbase = tile * RS_TILE + w * RS_ITEMS_PER_WARP;
+    int* my = wh + w * bins;
+    // phase A: per-warp histogram
+    for (int r = 0; r < RS_ITEMS_PER_WARP; r += 32) {
+        int j = wbase + r + lane;
+        if (j < n) atomicAdd(&my[(keys_in[j] >> shift) & (bins - 1)], 1);
+    }
+    __syncthreads();
+    // phase B: warp bases = global tile offset + counts of earlier warps
+    for (int b = threadIdx.x; b < bins; b += RS_THREADS) {
+        int run = hist[b * ntiles_cap + tile];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            int c = wh[ww * bins + b];
+            wh[ww * bins + b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase C: ordered rounds; rank inside a round by match_any
+    for (int r = 0; r < RS_ITEMS_PER_WARP; r += 32) {
+        int j = wbase + r + lane;
+        bool valid = j < n;
+        uint32_t k = valid ? keys_in[j] : 0u;
+        uint32_t v = valid ? vals_in[j] : 0u;
+        int d = valid ? (int)((k >> shift) & (bins - 1)) : bins;    // invalid lanes get a digit nobody shares
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        int pos = 0;
+        if (valid) pos = my[d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) my[d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            keys_out[pos] = k;
+            vals_out[pos] = v;
+        }
+    }
+}
+
+// Sort pairs (m->d_sk[which], m->d_sv[which]) of length *m->d_nnz by the low `bits` bits of the key.
+// On return the sorted pairs are in d_sk/d_sv (buffers are swapped as needed).
+int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
+    if (bits < 1) bits = 1;
+    int passes = (bits + 9) / 10;
+    int per = (bits + passes - 1) / passes;
+    int bins = 1 << per;
+    int ntiles_cap = (int)((m->max_nnz + RS_TILE - 1) / RS_TILE);
+    if ((int64_t)bins * ntiles_cap > m->sort_hist_cap) {
+        set_error("radix sort histogram capacity too small");
+        return WD_ESTATE;
+    }
+    for (int p = 0; p < passes; ++p) {
+        int shift = p * per;
+        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins,
+                                                                                  ntiles_cap, m->d_sort_hist,
+                                                                                  m->d_sort_counter);
+        rs_scatter_kernel<<<ntiles_cap, RS_THREADS, RS_WARPS * bins * sizeof(int), m->stream>>>(
+            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, ntiles_cap,
+            m->d_sort_hist);
+        m->launches += 2;
+        std::swap(m->d_sk[which], m->d_sk2[which]);
+        std::swap(m->d_sv[which], m->d_sv2[which]);
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+}  // namespace wd

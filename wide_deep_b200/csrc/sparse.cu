@@ -1,0 +1,425 @@
+// Sparse half of the step: wide linear logit, multihot embedding gather + mean-pool, and the backward
+// scatter of both fused with their per-row optimizers.
+//
+//   wide_fwd_kernel        tf.feature_column.linear_model(sparse_combiner='sum')   (reference linear.py:29-36)
+//   emb_pool_fwd_kernel    embedding_column(combiner='mean') inside input_layer     (reference dnn.py:88-90;
+//                          safe_embedding_lookup_sparse: empty bag -> zeros)
+//   seg_* / *_apply        SparseSegmentMeanGrad + SparseApplyAdagrad / SparseApplyFtrl (reference
+//                          joint.py:234-247 minimize()): one update per touched row from the
+//                          ordered sum of its gradients.
+// HBM-bound kernels: 16-byte vector loads through the read-only path, several rows in flight per lane
+// group, rows are 16..256 B records {w | optimizer slots} so forward touches one line and backward one
+// contiguous record.
+#include "common.cuh"
+
+namespace wd {
+
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------- wide forward
+// one warp per example: sum of w[row] over the example's wide ids (+ bias)
+__global__ void __launch_bounds__(256) wide_fwd_kernel(int B, int C, const int32_t* __restrict__ offs,
+                                                       const uint32_t* __restrict__ e_wide, const float4* __restrict__ wide,
+                                                       const float* __restrict__ bias, float* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float b0 = bias[0];
+    for (int b = warp; b < B; b += nwarps) {
+        int s = offs[(int64_t)b * C], e = offs[(int64_t)(b + 1) * C];
+        float acc = 0.f;
+        for (int j = s + lane; j < e; j += 32) {
+            uint32_t r = e_wide[j];
+            if (r != kInvalidRow) acc += __ldg(&wide[r].x);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[b] = acc + b0;
+    }
+}
+
+// --------------------------------------------------------------------------------------- embedding forward
+// All tables of one width D (G = D/4 lanes per bag, float4 per lane).  Bag = (example b, table k).
+// NARROW: one G-lane group per bag, 32/G bags per warp in flight (single-valued / short bags).
+// WIDE (full warp per bag): the 32/G groups take interleaved ids, then a shuffle tree combines them
+// (long multihot bags).
+template <int G, bool WIDEBAG>
+__global__ void __launch_bounds__(256) emb_pool_fwd_kernel(int B, int C, int ntab, const int32_t* __restrict__ tab_ids,
+                                                           float* const* __restrict__ tab_data,
+                                                           const int32_t* __restrict__ tab_stride,
+                                                           const int32_t* __restrict__ tab_x0, const int32_t* __restrict__ tab_col,
+                                                           const int64_t* __restrict__ tab_row_base,
+                                                           const int32_t* __restrict__ offs, const uint32_t* __restrict__ e_emb,
+                                                           float* __restrict__ X0, int ld) {
+    constexpr int GROUPS = 32 / G;
+    const int lane = threadIdx.x & 31, lig = lane % G, grp = lane / G;
+    const int64_t nbags = (int64_t)B * ntab;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (!WIDEBAG) {
+        for (int64_t bag = gwarp * GROUPS + grp; bag < nbags; bag += nwarp * GROUPS) {
+            int b = (int)(bag / ntab), t = tab_ids[bag % ntab];
+            int c = tab_col[t];
+            int s = offs[(int64_t)b * C + c], e = offs[(int64_t)b * C + c + 1];
+            const float* base = tab_data[t] + lig * 4;
+            const int stride = tab_stride[t];
+            const int64_t rb = tab_row_base[t];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = s;
+            for (; j + 4 <= e; j += 4) {                         // 4 rows in flight per group
+                float4 v0 = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
+                float4 v1 = ldg_nc_f4(base + (int64_t)(e_emb[j + 1] - rb) * stride);
+                float4 v2 = ldg_nc_f4(base + (int64_t)(e_emb[j + 2] - rb) * stride);
+                float4 v3 = ldg_nc_f4(base + (int64_t)(e_emb[j + 3] - rb) * stride);
+                acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            }
+            for (; j < e; ++j) {
+                float4 v = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            int n = e - s;
+            if (n > 1) {
+                float inv = 1.f / (float)n;                      // combiner='mean'
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+            }
+            *reinterpret_cast<float4*>(X0 + (int64_t)b * ld + tab_x0[t] + lig * 4) = acc;
+        }
+    } else {
+        for (int64_t bag = gwarp; bag < nbags; bag += nwarp) {
+            int b = (int)(bag / ntab), t = tab_ids[bag % ntab];
+            int c = tab_col[t];
+            int s = offs[(int64_t)b * C + c], e = offs[(int64_t)b * C + c + 1];
+            const float* base = tab_data[t] + lig * 4;
+            const int stride = tab_stride[t];
+            const int64_t rb = tab_row_base[t];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = s + grp;
+            for (; j + 3 * GROUPS < e; j += 4 * GROUPS) {
+                float4 v0 = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
+                float4 v1 = ldg_nc_f4(base + (int64_t)(e_emb[j + GROUPS] - rb) * stride);
+                float4 v2 = ldg_nc_f4(base + (int64_t)(e_emb[j + 2 * GROUPS] - rb) * stride);
+                float4 v3 = ldg_nc_f4(base + (int64_t)(e_emb[j + 3 * GROUPS] - rb) * stride);
+                acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            }
+            for (; j < e; j += GROUPS) {
+                float4 v = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+#pragma unroll
+            for (int d = G; d < 32; d <<= 1) {                  // segmented (per lane-in-group) shuffle reduction
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
+            }
+            int n = e - s;
+            if (n > 1) {
+                float inv = 1.f / (float)n;
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+            }
+            if (grp == 0) *reinterpret_cast<float4*>(X0 + (int64_t)b * ld + tab_x0[t] + lig * 4) = acc;
+        }
+    }
+}
+
+template <int G>
+static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
+    int ntab = m->dim_ntables[di];
+    int64_t nbags = (int64_t)m->dbatch.B * ntab;
+    int64_t warps = widebag ? nbags : (nbags + (32 / G) - 1) / (32 / G);
+    int grid = grid_for(warps * 32, 256, 148 * 8);
+    if (widebag)
+        emb_pool_fwd_kernel<G, true><<<grid, 256, 0, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_tables[di],
+            m->d_tab_data, m->d_tab_stride, m->d_tab_x0, m->d_tab_col, m->d_tab_row_base, m->d_col_offs, m->d_e_emb, m->d_X0, m->d0_phys);
+    else
+        emb_pool_fwd_kernel<G, false><<<grid, 256, 0, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_tables[di],
+            m->d_tab_data, m->d_tab_stride, m->d_tab_x0, m->d_tab_col, m->d_tab_row_base, m->d_col_offs, m->d_e_emb, m->d_X0, m->d0_phys);
+    m->launches++;
+}
+
+int sparse_forward(WdModel* m) {
+    const int B = m->dbatch.B;
+    if (m->use_wide) {
+        wide_fwd_kernel<<<grid_for((int64_t)B * 32, 256), 256, 0, m->stream>>>(B, m->n_columns, m->d_col_offs, m->d_e_wide,
+                                                                              m->d_wide, m->d_P + m->dense[0].off, m->d_wide_logit);
+        m->launches++;
+    }
+    if (m->use_deep) {
+        // heuristic: average bag length from the key count of the batch decides narrow vs full-warp bags
+        bool widebag = m->max_nnz > 0 && (m->keys_cap / (int64_t)(m->max_batch * (m->n_cat_fields > 0 ? m->n_cat_fields : 1))) >= 8;
+        for (int di = 0; di < m->n_dims; ++di) {
+            switch (m->dims[di] / 4) {
+                case 1: launch_emb_fwd<1>(m, di, false); break;
+                case 2: launch_emb_fwd<2>(m, di, widebag); break;
+                case 4: launch_emb_fwd<4>(m, di, widebag); break;
+                case 8: launch_emb_fwd<8>(m, di, widebag); break;
+                case 16: launch_emb_fwd<16>(m, di, widebag); break;
+                case 32: launch_emb_fwd<32>(m, di, true); break;
+                default: set_error("unsupported embedding width %d (supported: 4,8,16,32,64,128)", m->dims[di]); return WD_EUNSUPPORTED;
+            }
+        }
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// ------------------------------------------------------------------------------------ backward: grouping
+// keys/values for the two sorts: which = 0 embedding rows, 1 wide rows.  Non-participating entries get the
+// key `invalid` (= 1 << bits) so they sort behind every real row.
+__global__ void sort_keys_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ e_row, uint32_t invalid,
+                                 uint32_t* keys, uint32_t* vals) {
+    int n = *d_nnz;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t r = e_row[i];
+        keys[i] = r == kInvalidRow ? invalid : r;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// flags[i] = 1 if sorted key i starts a new valid segment; counts valid entries
+__global__ void seg_flag_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ keys, uint32_t invalid,
+                                int32_t* flags, int64_t cap) {
+    int n = *d_nnz;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+        int f = 0;
+        if (i < n) {
+            uint32_t k = keys[i];
+            f = (k != invalid && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+        }
+        flags[i] = f;
+    }
+}
+
+// after the exclusive scan of flags (pos = flags): scatter segment starts and unique rows; segment end sentinel
+__global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ keys, uint32_t invalid,
+                                   const int32_t* __restrict__ pos, int32_t* ustart, uint32_t* urow,
+                                   const int32_t* __restrict__ d_nuniq) {
+    int n = *d_nnz;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t k = keys[i];
+        bool head = (k != invalid && (i == 0 || keys[i - 1] != k));
+        if (head) {
+            ustart[pos[i]] = i;
+            urow[pos[i]] = k;
+        }
+        // the first invalid entry (or n) terminates the last valid segment
+        bool last_valid = (k != invalid) && (i == n - 1 || keys[i + 1] == invalid);
+        if (last_valid) ustart[*d_nuniq] = i + 1;
+    }
+}
+
+// ---- per unique embedding row: g = sum over occurrences of dX0[b, x0_off : x0_off + dim] / bag_size
+// One G-lane group per unique row; occurrences visited in sorted (= entry) order -> deterministic.
+__global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart,
+                                                           const uint32_t* __restrict__ urow, const uint32_t* __restrict__ svals,
+                                                           const int32_t* __restrict__ e_bc, const int32_t* __restrict__ offs,
+                                                           int C, const int32_t* __restrict__ col_table,
+                                                           const int32_t* __restrict__ tab_dim, const int32_t* __restrict__ tab_x0,
+                                                           const float* __restrict__ dX0, int ld, float* __restrict__ ugrad, int width) {
+    // 8 lanes per row, each lane covers float4 chunks lig, lig+8, ... of the row
+    const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
+    const int nu = *d_nuniq;
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+    const int64_t gstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 4;
+    for (int64_t u = g0; u < nu; u += gstep) {
+        int s = ustart[u], e = ustart[u + 1];
+        int bc0 = e_bc[svals[s]];
+        int t = col_table[bc0 % C];
+        int dim = tab_dim[t], x0 = tab_x0[t];
+        for (int q = lig; q * 4 < width; q += 8) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q * 4 < dim) {
+                for (int j = s; j < e; ++j) {
+                    int bc = e_bc[svals[j]];
+                    int b = bc / C;
+                    int n = offs[bc + 1] - offs[bc];
+                    float4 v = *reinterpret_cast<const float4*>(dX0 + (int64_t)b * ld + x0 + q * 4);
+                    float inv = 1.f / (float)n;
+                    acc.x += v.x * inv; acc.y += v.y * inv; acc.z += v.z * inv; acc.w += v.w * inv;
+                }
+            }
+            *reinterpret_cast<float4*>(ugrad + (int64_t)u * width + q * 4) = acc;
+        }
+    }
+}
+
+// wide: g = sum over occurrences of dlogit[b]; one thread per unique row
+__global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart,
+                                     const uint32_t* __restrict__ svals, const int32_t* __restrict__ e_bc, int C,
+                                     const float* __restrict__ dlogit, float* __restrict__ ugrad) {
+    const int nu = *d_nuniq;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+        int s = ustart[u], e = ustart[u + 1];
+        float acc = 0.f;
+        for (int j = s; j < e; ++j) acc += dlogit[e_bc[svals[j]] / C];
+        ugrad[u] = acc;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- optimizers
+struct OptParams { int kind; float lr, l1, l2, init_acc; };
+
+__device__ __forceinline__ void opt_update(const OptParams& o, float g, float& w, float& s1, float& s2) {
+    if (o.kind == WD_OPT_ADAGRAD) {                 // tf.train.AdagradOptimizer: acc += g^2; w -= lr*g/sqrt(acc)
+        s1 += g * g;
+        w -= o.lr * g / sqrtf(s1);
+    } else if (o.kind == WD_OPT_FTRL) {             // tf.train.FtrlOptimizer, lr_power = -0.5
+        float n1 = s1 + g * g;
+        float z1 = s2 + g - (sqrtf(n1) - sqrtf(s1)) / o.lr * w;
+        float wn = 0.f;
+        if (fabsf(z1) > o.l1) wn = (copysignf(o.l1, z1) - z1) / (sqrtf(n1) / o.lr + 2.f * o.l2);
+        w = wn; s1 = n1; s2 = z1;
+    } else {
+        w -= o.lr * g;
+    }
+}
+
+// embedding rows: record = [w[dim] | s1[dim] | s2[dim]]
+__global__ void __launch_bounds__(256) emb_apply_kernel(const int32_t* __restrict__ d_nuniq, const uint32_t* __restrict__ urow,
+                                                        const float* __restrict__ ugrad, int width, int ntab,
+                                                        const int64_t* __restrict__ tab_row_base, float* const* __restrict__ tab_data,
+                                                        const int32_t* __restrict__ tab_dim, const int32_t* __restrict__ tab_stride,
+                                                        OptParams o) {
+    const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
+    const int nu = *d_nuniq;
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+    const int64_t gstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 4;
+    for (int64_t u = g0; u < nu; u += gstep) {
+        int64_t row = urow[u];
+        int lo = 0, hi = ntab - 1;                  // table of this global row (tables are few: binary search)
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (tab_row_base[mid] <= row) lo = mid; else hi = mid - 1;
+        }
+        const int dim = tab_dim[lo], stride = tab_stride[lo];
+        float* rec = tab_data[lo] + (row - tab_row_base[lo]) * stride;
+        const int nslots = stride / dim - 1;
+        for (int q = lig; q * 4 < dim; q += 8) {
+            float4 g = *reinterpret_cast<const float4*>(ugrad + (int64_t)u * width + q * 4);
+            float4 w = *reinterpret_cast<float4*>(rec + q * 4);
+            float4 s1 = nslots >= 1 ? *reinterpret_cast<float4*>(rec + dim + q * 4) : make_float4(0, 0, 0, 0);
+            float4 s2 = nslots >= 2 ? *reinterpret_cast<float4*>(rec + 2 * dim + q * 4) : make_float4(0, 0, 0, 0);
+            opt_update(o, g.x, w.x, s1.x, s2.x);
+            opt_update(o, g.y, w.y, s1.y, s2.y);
+            opt_update(o, g.z, w.z, s1.z, s2.z);
+            opt_update(o, g.w, w.w, s1.w, s2.w);
+            *reinterpret_cast<float4*>(rec + q * 4) = w;
+            if (nslots >= 1) *reinterpret_cast<float4*>(rec + dim + q * 4) = s1;
+            if (nslots >= 2) *reinterpret_cast<float4*>(rec + 2 * dim + q * 4) = s2;
+        }
+    }
+}
+
+// wide rows: record {w, s1, s2, -}; also the bias record (dense gradient = sum of dlogit)
+__global__ void wide_apply_kernel(const int32_t* __restrict__ d_nuniq, const uint32_t* __restrict__ urow,
+                                  const float* __restrict__ ugrad, float4* __restrict__ wide, OptParams o) {
+    const int nu = *d_nuniq;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+        float4 r = wide[urow[u]];
+        opt_update(o, ugrad[u], r.x, r.y, r.z);
+        wide[urow[u]] = r;
+    }
+}
+
+static OptParams make_opt(const WdOptimizer& o) { return OptParams{o.kind, o.lr, o.l1, o.l2, o.init_acc}; }
+
+// sort (row, occurrence) pairs by row and find the unique rows; e_row: per-occurrence row ids (kInvalidRow = skip)
+static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row) {
+    const uint32_t invalid = 1u << m->sort_bits[which];
+    int g = grid_for(m->max_nnz, 256);
+    sort_keys_kernel<<<g, 256, 0, m->stream>>>(d_n, e_row, invalid, m->d_sk[which], m->d_sv[which]);
+    m->launches++;
+    int rc = radix_sort_pairs(m, which, m->sort_bits[which] + 1, d_n);
+    if (rc) return rc;
+    int32_t* flags = (int32_t*)m->d_sk2[which];               // ping-pong buffer is free after the sort
+    seg_flag_kernel<<<g, 256, 0, m->stream>>>(d_n, m->d_sk[which], invalid, flags, m->max_nnz);
+    m->launches++;
+    rc = exclusive_scan_i32(m, flags, m->max_nnz, m->d_nuniq[which]);
+    if (rc) return rc;
+    seg_compact_kernel<<<g, 256, 0, m->stream>>>(d_n, m->d_sk[which], invalid, flags, m->d_ustart[which], m->d_urow[which], m->d_nuniq[which]);
+    m->launches++;
+    return WD_OK;
+}
+
+// out[u] = sum over the segment of in[sv[j]] (rows of `width` floats); one thread per (unique row, float4 chunk)
+__global__ void merged_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, const uint32_t* __restrict__ svals,
+                                  const float* __restrict__ in, float* __restrict__ out, int width) {
+    const int nu = *d_nuniq;
+    const int64_t total = (int64_t)nu * width;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int u = (int)(t / width), q = (int)(t % width);
+        float acc = 0.f;
+        for (int j = ustart[u]; j < ustart[u + 1]; ++j) acc += in[(int64_t)svals[j] * width + q];
+        out[t] = acc;
+    }
+}
+
+// Replace the gradient list `which` by the row-wise sum of an external (rows, grads) list, e.g. the
+// all-gathered lists of every rank: keeps "sum duplicates, apply once" across data-parallel replicas.
+int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int64_t n) {
+    if (n > m->max_nnz) { set_error("merged sparse list has %lld rows, capacity %lld", (long long)n, (long long)m->max_nnz); return WD_EINVAL; }
+    int32_t n32 = (int32_t)n;
+    WD_CUDA(cudaMemcpyAsync(m->d_nvalid[which], &n32, 4, cudaMemcpyHostToDevice, m->stream));
+    int rc = group_rows(m, which, m->d_nvalid[which], (const uint32_t*)rows);
+    if (rc) return rc;
+    const int width = which == 0 ? m->emb_max_dim : 1;
+    merged_sum_kernel<<<grid_for(std::max<int64_t>(n, 1) * width, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_sv[which],
+                                                                                           (const float*)grads, m->d_ugrad[which], width);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// sort + per-row gradient sums for both tables; leaves (urow, ugrad, nuniq) ready for exchange / apply
+int sparse_backward_reduce(WdModel* m) {
+    int rc;
+    if (m->use_deep && !m->tables.empty()) {
+        if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
+        emb_grad_sum_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
+            m->d_nuniq[0], m->d_ustart[0], m->d_urow[0], m->d_sv[0], m->d_e_bc, m->d_col_offs, m->n_columns, m->dplan.col_emb_table,
+            m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
+        m->launches++;
+        m->sparse_overridden[0] = false;
+    }
+    if (m->use_wide) {
+        if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
+        wide_grad_sum_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_sv[1], m->d_e_bc,
+                                                                             m->n_columns, m->d_dlogit, m->d_ugrad[1]);
+        m->launches++;
+        m->sparse_overridden[1] = false;
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int sparse_apply(WdModel* m) {
+    if (m->use_deep && !m->tables.empty()) {
+        emb_apply_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
+            m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim, (int)m->tables.size(), m->d_tab_row_base, m->d_tab_data,
+            m->d_tab_dim, m->d_tab_stride, make_opt(m->dnn_opt));
+        m->launches++;
+    }
+    if (m->use_wide) {
+        wide_apply_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_urow[1], m->d_ugrad[1], m->d_wide,
+                                                                          make_opt(m->lin_opt));
+        m->launches++;
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+}  // namespace wd
