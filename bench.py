@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — CTR examples/sec of the Wide&Deep train step on N B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (CPU restatement of the reference step)
+
+Workload (config.workload): BASELINE.json configs[1] / [2] — synthetic Criteo shape, 13 dense + 26 categorical
+(Criteo-Kaggle cardinalities, 33.76 M embedding rows x 32), wide = 26 hash columns + 13 bucketized + 8 crosses
+@ 1 M buckets, MLP 1024-512-256 (relu, BN affine), Adagrad deep / FTRL wide, 8192 examples per GPU per step
+(weak scaling).  One "step" = ids + forward + sum-reduced sigmoid-CE + backward + both optimizers.
+
+JSON keys beyond the base contract:
+  value     examples/s with the step's inputs already resident in HBM (a ring of distinct batches, so the
+            rows each step touches are not the ones left in L2 by the previous step)
+  e2e       the same metric through the public host-buffer call (wd_train_step): pinned-host -> device copy of
+            the batch and device -> host read of the loss inside the timed region, every step
+  roofline  dominant kernel (MLP GEMMs) as achieved TFLOP/s vs the measured dense-bf16 tensor peak, timed live
+            with CUDA events on the model stream; `kernels` carries the same for the embedding gather (HBM)
+  cpu_baseline  the oracle (CPU restatement of the reference; TensorFlow itself cannot run here) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 8192
+RING = 8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == str(self.index):
+                self.rows.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def workload(n_gpus, per_gpu_batch):
+    from wide_deep_b200 import synthetic
+    fc, cross, model, emb = synthetic.criteo_conf()
+    n_cat = sum(1 for c in fc.values() if c["type"] == "category")
+    n_dense = len(fc) - n_cat
+    P = (n_cat * emb + n_dense) * 1024 + 1024 * 512 + 512 * 256 + 256
+    return fc, cross, model, emb, n_cat, n_dense, P
+
+
+def config_dict(n_gpus, per_gpu_batch):
+    return {"workload": "synthetic Criteo shape: 13 dense + 26 categorical (Criteo-Kaggle cardinalities, 33.76M rows), emb 32, "
+                        "wide 26 hash + 13 bucketized + 8 crosses@1M, MLP 1024-512-256 relu+BN, Adagrad/FTRL; train step",
+            "global_batch": per_gpu_batch * n_gpus, "per_gpu_batch": per_gpu_batch,
+            "parallelism": "dp%d" % n_gpus if n_gpus > 1 else "single",
+            "tables": "replicated", "ids": "uniform",
+            "l2": "ring of %d distinct resident batches; touched rows per step ~60 MB, tables 8.6 GB >> 126 MB L2" % RING}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32):
+    """Time the CPU restatement (oracle) on the same workload; returns (examples/s, seconds per step)."""
+    import torch
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    from oracle import model as OM
+    from wide_deep_b200 import synthetic
+    fc, cross, model, emb, n_cat, n_dense, _ = workload(1, batch_rows)
+    om = OM.OracleModel(fc, cross, model, "wide_deep", embedding_dim_override=emb, acc=acc).init(1)
+    cats = [f for f, c in fc.items() if c["type"] == "category"]
+    dense_names = [f for f, c in fc.items() if c["type"] == "continuous"]
+    times = []
+    for s in range(warmup + steps):
+        keys, dense, label = synthetic.criteo_batch_arrays(fc, batch_rows, step=s)
+        raw = {f: (np.arange(batch_rows + 1, dtype=np.int64), np.ascontiguousarray(keys[:, j])) for j, f in enumerate(cats)}
+        for j, f in enumerate(dense_names):
+            raw[f] = np.ascontiguousarray(dense[:, j])
+        t0 = time.perf_counter()
+        om.train_step(raw, label)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return batch_rows / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = 2048                     # bounded sample of the same workload (same tables, smaller batch)
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    v, sec = oracle_examples_per_sec(rows, steps, warm, threads)
+    sample = "%d steps of %d examples (same tables/config), %d threads" % (steps, rows, threads)
+    out = {"impl": "reference", "metric": "CTR examples/sec (train step)", "value": v, "unit": "examples/s", "n_gpus": args.gpus,
+           "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_dict(1, rows),
+           "cpu_baseline": {"value": v, "unit": "examples/s", "cores": threads, "kind": "port", "sample": sample,
+                            "note": "CPU restatement of the reference step (numpy/scipy oracle); TensorFlow 1.x is not installable here"},
+           "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="examples per GPU per step")
+    ap.add_argument("--engine", default=os.environ.get("WD_GEMM_ENGINE", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from wide_deep_b200 import synthetic
+    from wide_deep_b200.model import Batch, WideDeepModel
+    from wide_deep_b200.plan import Plan
+    B = args.batch
+    fc, cross, model_conf, emb, n_cat, n_dense, P = workload(world, B)
+    n_cols = n_cat + n_dense + len(cross)
+    plan = Plan(fc, cross, model_conf, "wide_deep", max_batch=B, embedding_dim_override=emb, gemm_engine=args.engine,
+                max_nnz=B * n_cols * (world if world > 1 else 1), max_keys=B * n_cat)
+    model = WideDeepModel(plan, device=local)
+    model.init(seed=0x5EED0005)          # identical replicas on every rank
+    trainer = None
+    if world > 1:
+        from wide_deep_b200.parallel import DataParallelTrainer
+        trainer = DataParallelTrainer(model)
+
+    # distinct batches per (rank, ring slot) in pinned host memory
+    host = []
+    for s in range(RING):
+        keys, dense, label = synthetic.criteo_batch_arrays(fc, B, step=rank * 1000 + s)
+        tk = torch.from_numpy(keys.view(np.int64).reshape(-1).copy()).pin_memory()
+        td = torch.from_numpy(dense.copy()).pin_memory()
+        tl = torch.from_numpy(label.copy()).pin_memory()
+        host.append((Batch(B, tk.numpy().view(np.uint64), None, td.numpy(), tl.numpy()), (tk, td, tl)))
+    for s in range(RING):
+        model.upload_slot(s, host[s][0])
+    model.sync()
+    stream = torch.cuda.ExternalStream(model.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        model.sync()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident(i):
+        if trainer:
+            trainer.step_slot(i % RING)
+        else:
+            model.train_step_slot(i % RING, want_loss=False)
+
+    def step_e2e(i):
+        if trainer:
+            trainer.step(host[i % RING][0])
+        else:
+            model.train_step(host[i % RING][0])
+
+    launches0 = model.launch_count()
+    for i in range(args.warmup):
+        step_resident(i)
+    model.sync()
+    per_step_launches = (model.launch_count() - launches0) // max(args.warmup, 1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(step_resident, args.steps)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # per-kernel timings (CUDA events between stages on the model stream), a few profiled steps
+    phases = {}
+    if not trainer:
+        model.set_profile(True)
+        nprof = 5
+        for i in range(nprof):
+            model.train_step_slot(i % RING, want_loss=True)
+            for k, v in model.last_timings().items():
+                phases[k] = phases.get(k, 0.0) + v / nprof
+        model.set_profile(False)
+
+    if rank == 0:
+        peaks = load_peaks()
+        gb = B * world
+        value = gb * args.steps / (ms / 1e3)
+        e2e = gb * args.steps / (ms_e2e / 1e3)
+        out = {"metric": "CTR examples/sec (train step)", "value": value, "unit": "examples/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, B),
+               "e2e": {"value": e2e, "unit": "examples/s", "ms_per_step": ms_e2e / args.steps,
+                       "h2d_bytes_per_step": host[0][0].h2d_bytes(), "d2h_bytes_per_step": 8},
+               "gpu_launches": int(per_step_launches * args.steps), "launches_per_step": int(per_step_launches),
+               "clocks": clk, "gemm_engine": args.engine}
+        if phases:
+            gemm_ms = sum(v for k, v in phases.items() if k.startswith("gemm_"))
+            flops = 6.0 * B * P                                   # 2BP forward + 4BP backward
+            ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+            out["roofline"] = {"kernel": "mlp gemm (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
+                               "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                               "peak_source": peaks["source"] + " dense bf16 (sustained); fp32-exact engines cannot exceed 1/6 of it (3xTF32)",
+                               "share_of_step": gemm_ms / phases.get("total", 1.0)}
+            gather_bytes = B * (n_cat * (4 * emb + 4) + 4 * n_cat + 4 * n_cat * emb)       # SURVEY 8(d) K3 formula
+            g_ms = phases.get("emb_fwd", 0.0)
+            g_ach = gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+            out["kernels"] = {"emb_gather_pool_fwd": {"bound": "hbm", "achieved": g_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                      "frac": g_ach / peaks["hbm_gbs"], "algorithmic_bytes": gather_bytes, "ms": g_ms},
+                              "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v, sec = oracle_examples_per_sec(2048, 3, 1, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
+                                   "sample": "3 steps of 2048 examples, same tables/config (oracle, fp32 accumulate)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -141,6 +141,10 @@ int wd_forward(WdModel *m, const WdBatch *batch, float *logits_out, float *loss_
  * resident batch (the e2e number uses wd_train_step with host buffers). */
 int wd_batch_upload(WdModel *m, const WdBatch *batch);
 int wd_train_step_resident(WdModel *m, float *loss_out);
+/* Ring of device-resident batches (slot in [0, 64); buffers are allocated on first use): lets a caller
+ * prefetch batch i+1 while step i runs, and lets the benchmark step through distinct resident batches. */
+int wd_batch_upload_slot(WdModel *m, int slot, const WdBatch *batch);
+int wd_train_step_slot(WdModel *m, int slot, float *loss_out);   /* loss_out NULL: enqueue only, no sync */
 int wd_forward_resident(WdModel *m, float *logits_out, float *loss_out);
 
 /* Split step for data-parallel training (multi-GPU): phase 1 computes gradients and leaves
@@ -148,6 +152,7 @@ int wd_forward_resident(WdModel *m, float *logits_out, float *loss_out);
  *   sparse grads : unique rows + summed grads for the embedding and the wide tables
  * phase 2 applies the optimizers.  wd_sparse_* expose the device buffers for the exchange. */
 int wd_step_backward(WdModel *m, const WdBatch *batch_or_null, float *loss_out);
+int wd_step_backward_slot(WdModel *m, int slot, float *loss_out);
 int wd_step_apply(WdModel *m);
 int64_t wd_dense_grad_count(WdModel *m);
 void *wd_dense_grad_ptr(WdModel *m);          /* device pointer */
@@ -178,9 +183,11 @@ int wd_debug_column_ids(WdModel *m, int32_t *offsets_out, int64_t offsets_cap, i
 int wd_debug_deep_input(WdModel *m, float *out, int64_t cap);
 /* Kernel launch counter (launches of this library's kernels since creation). */
 int64_t wd_launch_count(WdModel *m);
-/* Per-phase device timings of the last step in milliseconds (CUDA events on the model stream):
- * [0] h2d [1] ids [2] gather+wide fwd [3] mlp fwd+loss [4] mlp bwd [5] sparse bwd [6] dense opt [7] total */
-int wd_last_timings(WdModel *m, float *out8);
+/* Per-phase device timings of the last synchronised step in milliseconds (CUDA events recorded on the model
+ * stream between the stages, enabled by wd_set_profile).  Returns the number of phases n and fills
+ * ms_out[0..min(n,cap)): [0] = whole step, [i] = the phase ending at mark wd_timing_name(m, i). */
+int wd_last_timings(WdModel *m, float *ms_out, int cap);
+const char *wd_timing_name(WdModel *m, int i);
 int wd_set_profile(WdModel *m, int enable);
 void *wd_stream(WdModel *m);
 int wd_sync(WdModel *m);

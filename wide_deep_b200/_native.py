@@ -49,6 +49,7 @@ SYMBOLS = {
     "wd_train_step_resident": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "wd_forward_resident": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),
     "wd_step_backward": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "wd_step_backward_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "wd_step_apply": (ctypes.c_int, [_vp]),
     "wd_dense_grad_count": (_i64, [_vp]),
     "wd_dense_grad_ptr": (_vp, [_vp]),
@@ -64,7 +65,10 @@ SYMBOLS = {
     "wd_debug_column_ids": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, ctypes.POINTER(_i64)]),
     "wd_debug_deep_input": (ctypes.c_int, [_vp, _vp, _i64]),
     "wd_launch_count": (_i64, [_vp]),
-    "wd_last_timings": (ctypes.c_int, [_vp, _vp]),
+    "wd_last_timings": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "wd_timing_name": (ctypes.c_char_p, [_vp, ctypes.c_int]),
+    "wd_batch_upload_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "wd_train_step_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "wd_set_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "wd_stream": (_vp, [_vp]),
     "wd_sync": (ctypes.c_int, [_vp]),

@@ -99,7 +99,7 @@ extern "C" int wd_model_destroy(WdModel* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
-    if (m->timer.enabled || m->timer.ev[0]) for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
+    for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
     for (size_t i = 0; i < g_extra.size(); ++i)
         if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
@@ -544,16 +544,42 @@ static int check_ready(WdModel* m) {
     WD_CUDA(cudaSetDevice(m->device));
     return WD_OK;
 }
-static void tick(WdModel* m, int i) { if (m->timer.enabled) cudaEventRecord(m->timer.ev[i], m->stream); }
+static void timer_begin(WdModel* m) {
+    if (!m->timer.enabled) return;
+    m->timer.n = 0;
+    mark(m, "start");
+}
 
-extern "C" int wd_batch_upload(WdModel* m, const WdBatch* b) {
-    int rc = check_ready(m);
-    if (rc) return rc;
+// make batch slot `s` current (allocating its buffers on first use); slot 0 aliases the model's own buffers
+static int select_slot(WdModel* m, int s) {
+    if (s < 0 || s >= 64) { set_error("batch slot %d out of range [0, 64)", s); return WD_EINVAL; }
+    if (m->slots.empty()) {
+        BatchSlot b0;
+        b0.off = m->d_cat_offsets; b0.keys = m->d_cat_keys; b0.dense = m->d_dense; b0.label = m->d_label; b0.weight = m->d_weight;
+        m->slots.push_back(b0);
+    }
+    while ((int)m->slots.size() <= s) {
+        BatchSlot b;
+        int rc;
+        const int64_t Bm = m->max_batch;
+        if ((rc = dev_alloc(m, &b.off, Bm * std::max(m->n_cat_fields, 1) + 1))) return rc;
+        if ((rc = dev_alloc(m, &b.keys, m->keys_cap))) return rc;
+        if ((rc = dev_alloc(m, &b.dense, Bm * std::max(m->n_dense_fields, 1)))) return rc;
+        if ((rc = dev_alloc(m, &b.label, Bm))) return rc;
+        if ((rc = dev_alloc(m, &b.weight, Bm))) return rc;
+        m->slots.push_back(b);
+    }
+    BatchSlot& b = m->slots[s];
+    m->d_cat_offsets = b.off; m->d_cat_keys = b.keys; m->d_dense = b.dense; m->d_label = b.label; m->d_weight = b.weight;
+    if (b.filled) { m->dbatch = b.view; m->batch_has_label = b.has_label; }
+    return WD_OK;
+}
+
+static int upload_current(WdModel* m, const WdBatch* b) {
     if (!b || b->batch_size <= 0 || b->batch_size > m->max_batch) { set_error("batch_size %d outside (0, %d]", b ? b->batch_size : -1, m->max_batch); return WD_EINVAL; }
     const int B = b->batch_size, F = m->n_cat_fields, Nd = m->n_dense_fields;
     int64_t nnz = b->cat_offsets ? b->nnz : (int64_t)B * F;
     if (nnz > m->keys_cap) { set_error("batch has %lld keys, capacity %lld (raise max_keys)", (long long)nnz, (long long)m->keys_cap); return WD_EINVAL; }
-    tick(m, 0);
     if (F > 0) {
         if (b->cat_offsets) WD_CUDA(cudaMemcpyAsync(m->d_cat_offsets, b->cat_offsets, ((int64_t)B * F + 1) * 4, cudaMemcpyHostToDevice, m->stream));
         if (nnz > 0) WD_CUDA(cudaMemcpyAsync(m->d_cat_keys, b->cat_keys, nnz * 8, cudaMemcpyHostToDevice, m->stream));
@@ -568,15 +594,28 @@ extern "C" int wd_batch_upload(WdModel* m, const WdBatch* b) {
     m->dbatch.label = b->label ? m->d_label : nullptr;
     m->dbatch.weight = b->weight ? m->d_weight : nullptr;
     m->batch_has_label = b->label != nullptr;
-    tick(m, 1);
+    mark(m, "h2d");
     return WD_OK;
 }
+
+extern "C" int wd_batch_upload_slot(WdModel* m, int slot, const WdBatch* b) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if ((rc = select_slot(m, slot))) return rc;
+    if ((rc = upload_current(m, b))) return rc;
+    m->slots[slot].view = m->dbatch;
+    m->slots[slot].has_label = m->batch_has_label;
+    m->slots[slot].filled = true;
+    return WD_OK;
+}
+extern "C" int wd_batch_upload(WdModel* m, const WdBatch* b) { return wd_batch_upload_slot(m, 0, b); }
 
 static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
     int32_t* flags_host = reinterpret_cast<int32_t*>(m->h_loss_pinned + 4);
     WD_CUDA(cudaMemcpyAsync(m->h_loss_pinned, m->d_loss, 4, cudaMemcpyDeviceToHost, m->stream));
     WD_CUDA(cudaMemcpyAsync(flags_host, m->d_flags, 4, cudaMemcpyDeviceToHost, m->stream));
     if (logits_out) WD_CUDA(cudaMemcpyAsync(logits_out, m->d_logits, (int64_t)m->dbatch.B * 4, cudaMemcpyDeviceToHost, m->stream));
+    mark(m, "d2h");
     WD_CUDA(cudaStreamSynchronize(m->stream));
     if (flags_host[0] & 1) {
         cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
@@ -585,8 +624,11 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
     }
     if (loss_out) *loss_out = m->batch_has_label ? m->h_loss_pinned[0] : 0.f;
     if (m->timer.enabled) {
-        for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&m->last_ms[i], m->timer.ev[i], m->timer.ev[i + 1]);
-        cudaEventElapsedTime(&m->last_ms[7], m->timer.ev[0], m->timer.ev[7]);
+        PhaseTimer& t = m->timer;
+        for (int i = 1; i < t.n; ++i) cudaEventElapsedTime(&t.ms[i], t.ev[i - 1], t.ev[i]);
+        t.ms[0] = 0.f;
+        if (t.n > 1) cudaEventElapsedTime(&t.ms[0], t.ev[0], t.ev[t.n - 1]);   // [0] = total
+        t.n_last = t.n;
     }
     return WD_OK;
 }
@@ -594,23 +636,23 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
 static int forward_core(WdModel* m, bool train) {
     int rc;
     if ((rc = ids_prepare(m))) return rc;
-    tick(m, 2);
+    mark(m, "ids");
     if ((rc = sparse_forward(m))) return rc;
-    tick(m, 3);
     if ((rc = mlp_forward(m, train))) return rc;
+    mark(m, "mlp_other");
     if ((rc = loss_forward(m, train))) return rc;
-    tick(m, 4);
+    mark(m, "head");
     return WD_OK;
 }
 
 static int backward_core(WdModel* m) {
     int rc;
     if ((rc = mlp_backward(m))) return rc;
+    mark(m, "mlp_other");
     if ((rc = wide_bias_grad(m))) return rc;
     if ((rc = dense_reduce_grads(m))) return rc;
-    tick(m, 5);
+    mark(m, "dense_reduce");
     if ((rc = sparse_backward_reduce(m))) return rc;
-    tick(m, 6);
     m->grads_pending = true;
     return WD_OK;
 }
@@ -618,17 +660,16 @@ static int backward_core(WdModel* m) {
 static int apply_core(WdModel* m) {
     int rc;
     if ((rc = sparse_apply(m))) return rc;
+    mark(m, "sparse_apply");
     if ((rc = dense_apply(m))) return rc;
-    tick(m, 7);
+    mark(m, "dense_apply");
     m->grads_pending = false;
     return WD_OK;
 }
 
-extern "C" int wd_train_step_resident(WdModel* m, float* loss_out) {
-    int rc = check_ready(m);
-    if (rc) return rc;
+static int train_current(WdModel* m, float* loss_out) {
+    int rc;
     if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
-    if (!m->timer.enabled) {} else { /* events 0,1 recorded by upload; keep ordering when resident */ cudaEventRecord(m->timer.ev[0], m->stream); cudaEventRecord(m->timer.ev[1], m->stream); }
     if ((rc = forward_core(m, true))) return rc;
     if ((rc = backward_core(m))) return rc;
     if ((rc = apply_core(m))) return rc;
@@ -636,33 +677,65 @@ extern "C" int wd_train_step_resident(WdModel* m, float* loss_out) {
     return WD_OK;
 }
 
-extern "C" int wd_train_step(WdModel* m, const WdBatch* b, float* loss_out) {
-    int rc = wd_batch_upload(m, b);
+extern "C" int wd_train_step_slot(WdModel* m, int slot, float* loss_out) {
+    int rc = check_ready(m);
     if (rc) return rc;
-    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
-    if ((rc = forward_core(m, true))) return rc;
-    if ((rc = backward_core(m))) return rc;
-    if ((rc = apply_core(m))) return rc;
-    return finish_step(m, loss_out, nullptr);
+    if ((rc = select_slot(m, slot))) return rc;
+    if (!m->slots[slot].filled) { set_error("batch slot %d was never uploaded", slot); return WD_ESTATE; }
+    timer_begin(m);
+    return train_current(m, loss_out);
+}
+extern "C" int wd_train_step_resident(WdModel* m, float* loss_out) { return wd_train_step_slot(m, 0, loss_out); }
+
+extern "C" int wd_train_step(WdModel* m, const WdBatch* b, float* loss_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if ((rc = select_slot(m, 0))) return rc;
+    timer_begin(m);
+    if ((rc = upload_current(m, b))) return rc;
+    m->slots[0].view = m->dbatch; m->slots[0].has_label = m->batch_has_label; m->slots[0].filled = true;
+    float dummy;
+    return train_current(m, loss_out ? loss_out : &dummy);
 }
 
 extern "C" int wd_forward_resident(WdModel* m, float* logits_out, float* loss_out) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if ((rc = select_slot(m, 0))) return rc;
+    timer_begin(m);
     if ((rc = forward_core(m, false))) return rc;
     return finish_step(m, loss_out, logits_out);
 }
 
 extern "C" int wd_forward(WdModel* m, const WdBatch* b, float* logits_out, float* loss_out) {
-    int rc = wd_batch_upload(m, b);
+    int rc = check_ready(m);
     if (rc) return rc;
+    if ((rc = select_slot(m, 0))) return rc;
+    timer_begin(m);
+    if ((rc = upload_current(m, b))) return rc;
+    m->slots[0].view = m->dbatch; m->slots[0].has_label = m->batch_has_label; m->slots[0].filled = true;
     if ((rc = forward_core(m, false))) return rc;
     return finish_step(m, loss_out, logits_out);
+}
+
+
+extern "C" int wd_step_backward_slot(WdModel* m, int slot, float* loss_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if ((rc = select_slot(m, slot))) return rc;
+    if (!m->slots[slot].filled) { set_error("batch slot %d was never uploaded", slot); return WD_ESTATE; }
+    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    timer_begin(m);
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    if (loss_out) return finish_step(m, loss_out, nullptr);
+    return WD_OK;
 }
 
 extern "C" int wd_step_backward(WdModel* m, const WdBatch* b, float* loss_out) {
     int rc = b ? wd_batch_upload(m, b) : check_ready(m);
     if (rc) return rc;
+    timer_begin(m);
     if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
     if ((rc = forward_core(m, true))) return rc;
     if ((rc = backward_core(m))) return rc;
@@ -756,10 +829,15 @@ extern "C" int wd_debug_deep_input(WdModel* m, float* out, int64_t cap) {
     return WD_OK;
 }
 extern "C" int64_t wd_launch_count(WdModel* m) { return m ? m->launches : 0; }
-extern "C" int wd_last_timings(WdModel* m, float* out8) {
-    if (!m || !out8) return WD_EINVAL;
-    memcpy(out8, m->last_ms, sizeof(m->last_ms));
-    return WD_OK;
+extern "C" int wd_last_timings(WdModel* m, float* ms_out, int cap) {
+    if (!m) return WD_EINVAL;
+    int n = m->timer.n_last;
+    for (int i = 0; i < n && i < cap; ++i) ms_out[i] = m->timer.ms[i];
+    return n;
+}
+extern "C" const char* wd_timing_name(WdModel* m, int i) {
+    if (!m || i < 0 || i >= m->timer.n_last) return "";
+    return i == 0 ? "total" : m->timer.name[i];
 }
 extern "C" int wd_set_profile(WdModel* m, int enable) {
     if (!m) return WD_EINVAL;

@@ -111,9 +111,21 @@ struct Tower {
     float* logit;                // [max_batch]
 };
 
-struct PhaseTimer {
-    cudaEvent_t ev[9];
+struct PhaseTimer {          // named CUDA-event marks on the model stream (wd_set_profile)
+    static constexpr int kMax = 160;
+    cudaEvent_t ev[kMax];
+    const char* name[kMax];
+    float ms[kMax];
+    int n = 0, n_last = 0;
     bool enabled = false;
+};
+
+struct BatchSlot {           // one device-resident batch (ring used by benchmarks / prefetch)
+    int32_t* off = nullptr;
+    uint64_t* keys = nullptr;
+    float *dense = nullptr, *label = nullptr, *weight = nullptr;
+    DevBatch view{};
+    bool has_label = false, filled = false;
 };
 
 }  // namespace wd
@@ -219,7 +231,7 @@ struct WdModel {
 
     int64_t launches = 0;
     wd::PhaseTimer timer;
-    float last_ms[8] = {0};
+    std::vector<wd::BatchSlot> slots;        // slot 0 aliases the d_cat_* buffers above
     bool initialized = false;
     bool grads_pending = false;
 };
@@ -259,6 +271,15 @@ int dev_alloc(WdModel* m, T** p, int64_t count, bool zero = true) {
     m->bytes_allocated += count * (int64_t)sizeof(T);
     *p = (T*)q;
     return WD_OK;
+}
+
+// record a named mark on the model stream (no-op unless profiling is on)
+inline void mark(WdModel* m, const char* name) {
+    PhaseTimer& t = m->timer;
+    if (!t.enabled || t.n >= PhaseTimer::kMax) return;
+    t.name[t.n] = name;
+    cudaEventRecord(t.ev[t.n], m->stream);
+    t.n++;
 }
 
 inline int grid_for(int64_t n, int block, int cap = 148 * 16) {

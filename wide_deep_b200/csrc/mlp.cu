@@ -209,11 +209,14 @@ static void launch_gemm(WdModel* m, int mode, const GemmA& A, const float* B, in
 int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len);
 
 static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits = 1, int ksplit_len = 0) {
+    static const char* kNames[3] = {"gemm_fwd", "gemm_dgrad", "gemm_wgrad"};
+    mark(m, "mlp_other");
     if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
         int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
-        if (rc != WD_EUNSUPPORTED) return rc;
+        if (rc != WD_EUNSUPPORTED) { mark(m, kNames[mode]); return rc; }
     }
     launch_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
+    mark(m, kNames[mode]);
     return WD_OK;
 }
 

@@ -157,6 +157,7 @@ int sparse_forward(WdModel* m) {
         wide_fwd_kernel<<<grid_for((int64_t)B * 32, 256), 256, 0, m->stream>>>(B, m->n_columns, m->d_col_offs, m->d_e_wide,
                                                                               m->d_wide, m->d_P + m->dense[0].off, m->d_wide_logit);
         m->launches++;
+        mark(m, "wide_fwd");
     }
     if (m->use_deep) {
         // heuristic: average bag length from the key count of the batch decides narrow vs full-warp bags
@@ -172,6 +173,7 @@ int sparse_forward(WdModel* m) {
                 default: set_error("unsupported embedding width %d (supported: 4,8,16,32,64,128)", m->dims[di]); return WD_EUNSUPPORTED;
             }
         }
+        mark(m, "emb_fwd");
     }
     WD_CUDA(cudaGetLastError());
     return WD_OK;
@@ -389,17 +391,21 @@ int sparse_backward_reduce(WdModel* m) {
     int rc;
     if (m->use_deep && !m->tables.empty()) {
         if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
+        mark(m, "emb_group");
         emb_grad_sum_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
             m->d_nuniq[0], m->d_ustart[0], m->d_urow[0], m->d_sv[0], m->d_e_bc, m->d_col_offs, m->n_columns, m->dplan.col_emb_table,
             m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
         m->launches++;
+        mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
     }
     if (m->use_wide) {
         if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
+        mark(m, "wide_group");
         wide_grad_sum_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_sv[1], m->d_e_bc,
                                                                              m->n_columns, m->d_dlogit, m->d_ugrad[1]);
         m->launches++;
+        mark(m, "wide_grad_sum");
         m->sparse_overridden[1] = false;
     }
     WD_CUDA(cudaGetLastError());

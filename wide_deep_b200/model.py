@@ -148,6 +148,11 @@ class WideDeepModel(object):
         check(self._lib.wd_step_backward(self._h, ctypes.byref(c) if c is not None else None, ctypes.byref(loss)))
         return loss.value
 
+    def step_backward_slot(self, slot):
+        loss = ctypes.c_float()
+        check(self._lib.wd_step_backward_slot(self._h, int(slot), ctypes.byref(loss)))
+        return loss.value
+
     def step_apply(self):
         check(self._lib.wd_step_apply(self._h))
         self.global_step += 1
@@ -202,10 +207,26 @@ class WideDeepModel(object):
         check(self._lib.wd_set_profile(self._h, 1 if on else 0))
 
     def last_timings(self):
-        out = np.zeros(8, dtype=np.float32)
-        check(self._lib.wd_last_timings(self._h, out.ctypes.data))
-        keys = ["h2d", "ids", "sparse_fwd", "mlp_fwd_loss", "mlp_bwd", "sparse_bwd", "apply", "total"]
-        return dict(zip(keys, (float(v) for v in out)))
+        """OrderedDict phase -> ms of the last synchronised step ('total' first); needs set_profile(True)."""
+        from collections import OrderedDict
+        out = np.zeros(64, dtype=np.float32)
+        n = self._lib.wd_last_timings(self._h, out.ctypes.data, 64)
+        res = OrderedDict()
+        for i in range(max(n, 0)):
+            name = self._lib.wd_timing_name(self._h, i).decode()
+            res[name] = res.get(name, 0.0) + float(out[i])
+        return res
+
+    def upload_slot(self, slot, batch: Batch):
+        c = batch.to_c()
+        check(self._lib.wd_batch_upload_slot(self._h, int(slot), ctypes.byref(c)))
+        self._rows_hint = batch.batch_size
+
+    def train_step_slot(self, slot, want_loss=True):
+        loss = ctypes.c_float()
+        check(self._lib.wd_train_step_slot(self._h, int(slot), ctypes.byref(loss) if want_loss else None))
+        self.global_step += 1
+        return loss.value if want_loss else None
 
     def stream(self):
         return int(self._lib.wd_stream(self._h) or 0)
