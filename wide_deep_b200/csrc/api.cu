@@ -369,6 +369,10 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_ugrad[w], (m->max_nnz + 8) * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         if ((rc = dev_alloc(m, &m->d_nuniq[w], 4))) return rc;
         if ((rc = dev_alloc(m, &m->d_nvalid[w], 4))) return rc;
+        m->cpart_cap = 2 * (m->max_nnz / 64) + 64;
+        if ((rc = dev_alloc(m, &m->d_choff[w], m->max_nnz + 8))) return rc;
+        if ((rc = dev_alloc(m, &m->d_nchunks[w], 4))) return rc;
+        if ((rc = dev_alloc(m, &m->d_cpart[w], m->cpart_cap * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         m->sparse_cap[w] = m->max_nnz;
     }
     m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1);

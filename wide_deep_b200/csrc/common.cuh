@@ -220,6 +220,10 @@ struct WdModel {
     float* d_ugrad[2] = {nullptr, nullptr};     // [cap, width]
     int32_t* d_nuniq[2] = {nullptr, nullptr};   // device scalars
     int32_t* d_nvalid[2] = {nullptr, nullptr};
+    int32_t* d_choff[2] = {nullptr, nullptr};   // chunk offsets of hot rows (exclusive scan)
+    int32_t* d_nchunks[2] = {nullptr, nullptr};
+    float* d_cpart[2] = {nullptr, nullptr};     // chunk partial sums
+    int64_t cpart_cap = 0;
     int64_t sparse_cap[2] = {0, 0};
     bool sparse_overridden[2] = {false, false};
     int64_t sparse_override_n[2] = {0, 0};

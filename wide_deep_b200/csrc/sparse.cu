@@ -224,51 +224,124 @@ __global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint
     }
 }
 
-// ---- per unique embedding row: g = sum over occurrences of dX0[b, x0_off : x0_off + dim] / bag_size
-// One G-lane group per unique row; occurrences visited in sorted (= entry) order -> deterministic.
-__global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart,
-                                                           const uint32_t* __restrict__ urow, const uint32_t* __restrict__ svals,
+// ---- per unique row: g = ordered sum of its occurrences' gradients.
+// Rows touched at most kChunk times are summed by one lane group directly.  Hotter rows (small tables,
+// skewed ids) are split into chunks of kChunk occurrences that are summed in parallel and then combined in
+// chunk order, so the result stays deterministic and no single group walks thousands of occurrences.
+constexpr int kChunk = 64;
+
+// mch[u] = number of chunks of a multi-chunk row, 0 for rows summed directly (and for u >= nuniq)
+__global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, int32_t* mch, int64_t cap) {
+    const int nu = *d_nuniq;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += (int64_t)gridDim.x * blockDim.x) {
+        int v = 0;
+        if (u < nu) {
+            int len = ustart[u + 1] - ustart[u];
+            if (len > kChunk) v = (len + kChunk - 1) / kChunk;
+        }
+        mch[u] = v;
+    }
+}
+
+__device__ __forceinline__ int chunk_owner(const int32_t* __restrict__ choff, int nu, int c) {
+    int lo = 0, hi = nu;                         // last u with choff[u] <= c
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (choff[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// embedding rows: contribution of occurrence j = dX0[b, x0_off : x0_off + dim] / bag_size(b, column)
+// 8 lanes per work item, each lane covers float4 chunks lig, lig+8, ... of the row
+template <bool CHUNKED>
+__global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nitems, const int32_t* __restrict__ d_nuniq,
+                                                           const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
+                                                           const uint32_t* __restrict__ svals,
                                                            const int32_t* __restrict__ e_bc, const int32_t* __restrict__ offs,
                                                            int C, const int32_t* __restrict__ col_table,
                                                            const int32_t* __restrict__ tab_dim, const int32_t* __restrict__ tab_x0,
-                                                           const float* __restrict__ dX0, int ld, float* __restrict__ ugrad, int width) {
-    // 8 lanes per row, each lane covers float4 chunks lig, lig+8, ... of the row
+                                                           const float* __restrict__ dX0, int ld, float* __restrict__ out, int width) {
     const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
-    const int nu = *d_nuniq;
+    const int nitems = *d_nitems, nu = *d_nuniq;
     const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
     const int64_t gstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 4;
-    for (int64_t u = g0; u < nu; u += gstep) {
-        int s = ustart[u], e = ustart[u + 1];
+    for (int64_t it = g0; it < nitems; it += gstep) {
+        int s, e;
+        if (!CHUNKED) {
+            s = ustart[it]; e = ustart[it + 1];
+            if (e - s > kChunk) continue;                     // summed by the chunked pass
+        } else {
+            int u = chunk_owner(choff, nu, (int)it);
+            s = ustart[u] + ((int)it - choff[u]) * kChunk;
+            e = min(ustart[u + 1], s + kChunk);
+        }
         int bc0 = e_bc[svals[s]];
         int t = col_table[bc0 % C];
         int dim = tab_dim[t], x0 = tab_x0[t];
         for (int q = lig; q * 4 < width; q += 8) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (q * 4 < dim) {
-                for (int j = s; j < e; ++j) {
+                int j = s;
+                for (; j + 4 <= e; j += 4) {                  // 4 gradient rows in flight
+                    int bcs[4]; float4 v[4]; float inv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) bcs[r] = e_bc[svals[j + r]];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        v[r] = *reinterpret_cast<const float4*>(dX0 + (int64_t)(bcs[r] / C) * ld + x0 + q * 4);
+                        inv[r] = 1.f / (float)(offs[bcs[r] + 1] - offs[bcs[r]]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { acc.x += v[r].x * inv[r]; acc.y += v[r].y * inv[r]; acc.z += v[r].z * inv[r]; acc.w += v[r].w * inv[r]; }
+                }
+                for (; j < e; ++j) {
                     int bc = e_bc[svals[j]];
-                    int b = bc / C;
-                    int n = offs[bc + 1] - offs[bc];
-                    float4 v = *reinterpret_cast<const float4*>(dX0 + (int64_t)b * ld + x0 + q * 4);
-                    float inv = 1.f / (float)n;
+                    float4 v = *reinterpret_cast<const float4*>(dX0 + (int64_t)(bc / C) * ld + x0 + q * 4);
+                    float inv = 1.f / (float)(offs[bc + 1] - offs[bc]);
                     acc.x += v.x * inv; acc.y += v.y * inv; acc.z += v.z * inv; acc.w += v.w * inv;
                 }
             }
-            *reinterpret_cast<float4*>(ugrad + (int64_t)u * width + q * 4) = acc;
+            *reinterpret_cast<float4*>(out + (int64_t)it * width + q * 4) = acc;
         }
     }
 }
 
-// wide: g = sum over occurrences of dlogit[b]; one thread per unique row
-__global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart,
-                                     const uint32_t* __restrict__ svals, const int32_t* __restrict__ e_bc, int C,
-                                     const float* __restrict__ dlogit, float* __restrict__ ugrad) {
+// ugrad[u] = sum of the row's chunk partials in chunk order (multi-chunk rows only)
+__global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ choff,
+                                                            const float* __restrict__ cpart, float* __restrict__ ugrad, int width) {
     const int nu = *d_nuniq;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
-        int s = ustart[u], e = ustart[u + 1];
+    const int64_t total = (int64_t)nu * width;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int u = (int)(t / width), q = (int)(t % width);
+        int c0 = choff[u], c1 = choff[u + 1];
+        if (c1 == c0) continue;
+        float acc = 0.f;
+        for (int c = c0; c < c1; ++c) acc += cpart[(int64_t)c * width + q];
+        ugrad[t] = acc;
+    }
+}
+
+// wide rows: contribution of occurrence j = dlogit[b]; one thread per work item
+template <bool CHUNKED>
+__global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nitems, const int32_t* __restrict__ d_nuniq,
+                                     const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
+                                     const uint32_t* __restrict__ svals, const int32_t* __restrict__ e_bc, int C,
+                                     const float* __restrict__ dlogit, float* __restrict__ out) {
+    const int nitems = *d_nitems, nu = *d_nuniq;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+        int s, e;
+        if (!CHUNKED) {
+            s = ustart[it]; e = ustart[it + 1];
+            if (e - s > kChunk) continue;
+        } else {
+            int u = chunk_owner(choff, nu, it);
+            s = ustart[u] + (it - choff[u]) * kChunk;
+            e = min(ustart[u + 1], s + kChunk);
+        }
         float acc = 0.f;
         for (int j = s; j < e; ++j) acc += dlogit[e_bc[svals[j]] / C];
-        ugrad[u] = acc;
+        out[it] = acc;
     }
 }
 
@@ -392,19 +465,37 @@ int sparse_backward_reduce(WdModel* m) {
     if (m->use_deep && !m->tables.empty()) {
         if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
         mark(m, "emb_group");
-        emb_grad_sum_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
-            m->d_nuniq[0], m->d_ustart[0], m->d_urow[0], m->d_sv[0], m->d_e_bc, m->d_col_offs, m->n_columns, m->dplan.col_emb_table,
-            m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
-        m->launches++;
+        {
+            int g = grid_for(m->max_nnz, 256);
+            chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->max_nnz);
+            m->launches++;
+            if ((rc = exclusive_scan_i32(m, m->d_choff[0], m->max_nnz, m->d_nchunks[0]))) return rc;
+            int ge = grid_for(m->max_nnz * 8, 256);
+            emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
+            emb_grad_sum_kernel<true><<<grid_for(m->cpart_cap * 8, 256), 256, 0, m->stream>>>(m->d_nchunks[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_cpart[0], m->emb_max_dim);
+            chunk_combine_kernel<<<grid_for(m->max_nnz * (int64_t)m->emb_max_dim / 4, 256), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
+            m->launches += 3;
+        }
         mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
     }
     if (m->use_wide) {
         if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
         mark(m, "wide_group");
-        wide_grad_sum_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_sv[1], m->d_e_bc,
-                                                                             m->n_columns, m->d_dlogit, m->d_ugrad[1]);
-        m->launches++;
+        {
+            int g = grid_for(m->max_nnz, 256);
+            chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->max_nnz);
+            m->launches++;
+            if ((rc = exclusive_scan_i32(m, m->d_choff[1], m->max_nnz, m->d_nchunks[1]))) return rc;
+            wide_grad_sum_kernel<false><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                                  m->n_columns, m->d_dlogit, m->d_ugrad[1]);
+            wide_grad_sum_kernel<true><<<grid_for(m->cpart_cap, 256), 256, 0, m->stream>>>(m->d_nchunks[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                                                          m->n_columns, m->d_dlogit, m->d_cpart[1]);
+            chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1);
+            m->launches += 3;
+        }
         mark(m, "wide_grad_sum");
         m->sparse_overridden[1] = false;
     }
