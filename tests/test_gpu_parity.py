@@ -202,3 +202,50 @@ def test_eval_metrics():
     got, exp = pm.eval_finish(), acc.result()
     for k in exp:
         assert abs(got[k] - exp[k]) <= 2e-4 * max(abs(exp[k]), 1.0), "%s: %g vs %g" % (k, got[k], exp[k])
+
+
+# ------------------------------------------------------------------------------------ tcgen05 engine
+def _engine_pair(engine, hidden, mode, B, seed):
+    fc, cross, model = small_conf(hidden=hidden, mode=mode)
+    om = OM.OracleModel(fc, cross, model, "wide_deep").init(seed)
+    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64, max_keys=B * 64, gemm_engine=engine)
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    return fc, om, plan, pm
+
+
+@pytest.mark.parametrize("mode", ["simple", "dense", "first_dense"])
+def test_tc3x_engine_train_parity(mode):
+    """tcgen05 kind::tf32 with the 3-pass hi/lo split must meet the same 1e-4 bar as the fp32 FFMA engine."""
+    B = 300
+    fc, om, plan, pm = _engine_pair("tc3x", (128, 96, 64), mode, B, seed=41)
+    rng = np.random.default_rng(43)
+    for step in range(3):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        loss = pm.train_step(to_product_batch(plan, raw, label))
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    for name in pm.tensor_names():
+        got, exp = pm.get_tensor(name), om.params[name]
+        scale = max(float(np.abs(exp).max()), 1e-3)
+        assert np.max(np.abs(got - exp)) <= 2e-4 * scale, "%s: %g (scale %g)" % (name, np.max(np.abs(got - exp)), scale)
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    logits, _ = pm.forward(to_product_batch(plan, raw, label))
+    _, cache = om.forward(raw)
+    np.testing.assert_array_less(np.abs(logits - cache["logits"]), 5 * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+
+
+def test_tc1x_engine_is_close_but_not_parity_grade():
+    """Single-pass tf32 is offered as a fast mode only: it must be roughly right (1e-2) — and the test documents
+    that it does not meet the parity bar, which is why bench.py never uses it."""
+    B = 256
+    fc, om, plan, pm = _engine_pair("tc1x", (128, 64), "simple", B, seed=47)
+    rng = np.random.default_rng(49)
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    logits, _ = pm.forward(to_product_batch(plan, raw, label))
+    _, cache = om.forward(raw)
+    err = np.abs(logits - cache["logits"]) / np.maximum(np.abs(cache["logits"]), 1.0)
+    assert err.max() < 2e-2

@@ -141,7 +141,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     m->max_batch = d->max_batch; m->max_batch_pad = pad_to(d->max_batch, 128);
     m->ldt = m->max_batch_pad;
     m->row_tiles = m->max_batch_pad / 128;
-    m->gemm_engine = d->gemm_engine == WD_GEMM_AUTO ? WD_GEMM_FFMA : d->gemm_engine;
+    m->gemm_engine = d->gemm_engine == WD_GEMM_AUTO ? WD_GEMM_TC3X : d->gemm_engine;
     m->max_nnz = d->max_nnz > 0 ? d->max_nnz : (int64_t)d->max_batch * std::max(C, 1) * 2;
     m->keys_cap = d->max_keys > 0 ? d->max_keys : (int64_t)d->max_batch * std::max(d->n_cat_fields, 1) * 4;
     if (m->lin_opt.kind == WD_OPT_FTRL && m->lin_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
@@ -491,8 +491,9 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
     const cudaMemcpyKind dir = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
     if (kind == WD_T_WIDE_COL) {
         float* dev = reinterpret_cast<float*>(m->d_wide + m->col_wide_base[index]) + slot;
-        if (to_device) WD_CUDA(cudaMemcpy2D(dev, 16, host, 4, 4, count, dir));
-        else WD_CUDA(cudaMemcpy2D(host, 4, dev, 16, 4, count, dir));
+        if (to_device) WD_CUDA(cudaMemcpy2DAsync(dev, 16, host, 4, 4, count, dir, m->stream));
+        else WD_CUDA(cudaMemcpy2DAsync(host, 4, dev, 16, 4, count, dir, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
         return WD_OK;
     }
     if (kind == WD_T_EMB_TABLE) {
@@ -500,13 +501,15 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
         if (slot * tb.dim >= tb.stride) { set_error("table has no optimizer slot %d", slot); return WD_EINVAL; }
         float* dev = tb.data + slot * tb.dim;
         const size_t lw = (size_t)tb.dim_logical * 4;
-        if (to_device) WD_CUDA(cudaMemcpy2D(dev, (size_t)tb.stride * 4, host, lw, lw, tb.rows, dir));
-        else WD_CUDA(cudaMemcpy2D(host, lw, dev, (size_t)tb.stride * 4, lw, tb.rows, dir));
+        if (to_device) WD_CUDA(cudaMemcpy2DAsync(dev, (size_t)tb.stride * 4, host, lw, lw, tb.rows, dir, m->stream));
+        else WD_CUDA(cudaMemcpy2DAsync(host, lw, dev, (size_t)tb.stride * 4, lw, tb.rows, dir, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
         return WD_OK;
     }
     float* arena = slot == 0 ? m->d_P : (slot == 1 ? m->d_S1 : m->d_S2);
     if (kind == WD_T_WIDE_BIAS) {
-        WD_CUDA(cudaMemcpy(to_device ? (void*)(arena + m->dense[0].off) : host, to_device ? host : (void*)(arena + m->dense[0].off), 4, dir));
+        WD_CUDA(cudaMemcpyAsync(to_device ? (void*)(arena + m->dense[0].off) : host, to_device ? host : (void*)(arena + m->dense[0].off), 4, dir, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
         return WD_OK;
     }
     int di;
@@ -516,7 +519,10 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
     Layer& L = m->towers[x->did_tower[index]].layers[x->did_layer[index]];
     std::vector<float> phys(t.count, 0.f);
     float* h = (float*)host;
-    if (!to_device || slot > 0) WD_CUDA(cudaMemcpy(phys.data(), arena + t.off, t.count * 4, cudaMemcpyDeviceToHost));
+    if (!to_device || slot > 0) {
+        WD_CUDA(cudaMemcpyAsync(phys.data(), arena + t.off, t.count * 4, cudaMemcpyDeviceToHost, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
+    }
     if (sub == WD_D_KERNEL) {
         int64_t lk = 0;
         for (int s = 0; s < L.n_in_segs; ++s) {
@@ -536,7 +542,10 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
         for (int n = 0; n < L.N; ++n) { if (to_device) phys[n] = h[n]; else h[n] = phys[n]; }
     }
     if (to_device) {
-        WD_CUDA(cudaMemcpy(arena + t.off, phys.data(), t.count * 4, cudaMemcpyHostToDevice));
+        // all copies go through the model stream: a pageable cudaMemcpy on the NULL stream may still be in flight when a
+        // kernel on this (non-blocking) stream starts
+        WD_CUDA(cudaMemcpyAsync(arena + t.off, phys.data(), t.count * 4, cudaMemcpyHostToDevice, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
         if (slot == 0 && t.wt_off >= 0) return dense_refresh_transposes(m);
     }
     return WD_OK;
@@ -831,6 +840,17 @@ extern "C" int wd_debug_deep_input(WdModel* m, float* out, int64_t cap) {
     WD_CUDA(cudaStreamSynchronize(m->stream));
     WD_CUDA(cudaMemcpy(out, m->d_X0, n * 4, cudaMemcpyDeviceToHost));
     return WD_OK;
+}
+extern "C" int wd_debug_hidden(WdModel* m, int tower, int layer, float* out, int64_t cap) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (tower < 0 || tower >= (int)m->towers.size() || layer < 0 || layer >= m->towers[tower].n_hidden) { set_error("no such hidden layer"); return WD_EINVAL; }
+    Layer& L = m->towers[tower].layers[layer];
+    int64_t n = (int64_t)m->dbatch.B * L.N_phys;
+    if (cap < n) { set_error("buffer too small"); return WD_EINVAL; }
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    WD_CUDA(cudaMemcpy(out, L.H, n * 4, cudaMemcpyDeviceToHost));
+    return L.N_phys;
 }
 extern "C" int64_t wd_launch_count(WdModel* m) { return m ? m->launches : 0; }
 extern "C" int wd_last_timings(WdModel* m, float* ms_out, int cap) {

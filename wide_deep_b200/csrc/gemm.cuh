@@ -1,0 +1,59 @@
+// Shared GEMM interface of the MLP engines (FFMA in mlp.cu, tcgen05 in gemm_tc.cu): operand descriptions,
+// epilogue description and the activation functions (reference python/lib/utils/model_util.py:28-59).
+#pragma once
+#include "common.cuh"
+
+namespace wd {
+
+// --------------------------------------------------------------------------------------------- activations
+__device__ __forceinline__ float act_fwd(int kind, float z) {
+    switch (kind) {
+        case WD_ACT_RELU: return fmaxf(z, 0.f);
+        case WD_ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
+        case WD_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+        case WD_ACT_TANH: return tanhf(z);
+        case WD_ACT_LEAKY_RELU: return z > 0.f ? z : 0.2f * z;
+        case WD_ACT_ELU: return z > 0.f ? z : expm1f(z);
+        case WD_ACT_SELU: return 1.0507009873554805f * (z > 0.f ? z : 1.6732632423543772f * expm1f(z));
+        case WD_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+        case WD_ACT_SOFTSIGN: return z / (1.f + fabsf(z));
+    }
+    return z;
+}
+// derivative expressed through the stored post-activation value a
+__device__ __forceinline__ float act_bwd(int kind, float a) {
+    switch (kind) {
+        case WD_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+        case WD_ACT_RELU6: return (a > 0.f && a < 6.f) ? 1.f : 0.f;
+        case WD_ACT_SIGMOID: return a * (1.f - a);
+        case WD_ACT_TANH: return 1.f - a * a;
+        case WD_ACT_LEAKY_RELU: return a > 0.f ? 1.f : 0.2f;
+        case WD_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+        case WD_ACT_SELU: return a > 0.f ? 1.0507009873554805f : a + 1.0507009873554805f * 1.6732632423543772f;
+        case WD_ACT_SOFTPLUS: return 1.f - expf(-a);
+        case WD_ACT_SOFTSIGN: { float t = 1.f - fabsf(a); return t * t; }
+    }
+    return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------- FFMA GEMM
+struct GemmA {                         // A operand: up to kMaxSegs K-contiguous segments
+    int n;
+    const float* ptr[kMaxSegs];
+    int ld[kMaxSegs];
+    int k[kMaxSegs];                   // multiple of 16
+};
+enum { EPI_FWD = 0, EPI_STORE = 1, EPI_WGRAD = 2 };
+struct Epi {
+    float* C; int ldc;                 // STORE / WGRAD target
+    int accumulate;                    // STORE: C += acc
+    float* A_out; float* H_out; int ldh;   // FWD outputs
+    float* HT; int ldt;                // FWD transposed output (nullable)
+    const float *bias, *gamma, *beta;
+    int n_logical, act, bn;
+    int m_valid;                       // rows >= m_valid are written as zero (transposed padding)
+    int64_t split_stride;              // WGRAD: floats between split partials
+};
+
+
+}  // namespace wd

@@ -110,6 +110,7 @@ int metrics_setup() {
     for (int i = 0; i < kNumThr - 2; ++i) thr[i + 1] = (float)((i + 1) * 1.0 / (kNumThr - 1));
     thr[kNumThr - 1] = (float)(1.0 + 1e-7);
     WD_CUDA(cudaMemcpyToSymbol(c_thr, thr, sizeof(thr)));
+    WD_CUDA(cudaDeviceSynchronize());
     return WD_OK;
 }
 

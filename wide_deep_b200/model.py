@@ -200,6 +200,13 @@ class WideDeepModel(object):
         check(self._lib.wd_debug_deep_input(self._h, out.ctypes.data, out.size))
         return out
 
+    def hidden_output(self, tower, layer, batch_size):
+        out = np.empty(batch_size * 4096, dtype=np.float32)
+        n = self._lib.wd_debug_hidden(self._h, tower, layer, out.ctypes.data, out.size)
+        if n < 0:
+            check(n)
+        return out[:batch_size * n].reshape(batch_size, n)
+
     def launch_count(self):
         return int(self._lib.wd_launch_count(self._h))
 
