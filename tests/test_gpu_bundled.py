@@ -1,0 +1,111 @@
+"""BASELINE.json configs[0]: the bundled conf/*.yaml + data/ fixtures through the product (C++ loader + CUDA step)
+against the oracle (its own TSV parser + numpy step), and the drop-in entry points end to end."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bundled_conf_train_and_eval_parity():
+    from oracle import model as OM, tsv as otsv
+    from oracle.metrics import EvalAccumulator
+    from tests.helpers import copy_params_to_product
+    from wide_deep_b200.config import Config
+    from wide_deep_b200.dataset import TsvReader
+    from wide_deep_b200.model import WideDeepModel
+    from wide_deep_b200.plan import compile_plan
+    cfg = Config()
+    B = 64
+    fc, cc = cfg.read_feature_conf(), cfg.read_cross_feature_conf()
+    plan = compile_plan(cfg, "wide_deep", B, tf_compat_pad=True, max_nnz=B * 2048, max_keys=B * 512)
+    om = OM.OracleModel(fc, cc, cfg.model, "wide_deep", tf_compat_pad=True).init(123)
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    reader = TsvReader(cfg, plan)
+    lines = open(os.path.join(ROOT, "data", "train", "train1")).read().split("\n")
+    lines = [l for l in lines if l]
+    for step in range(4):
+        chunk = lines[step * B:(step + 1) * B]
+        batch = reader.parse(chunk)
+        raw, lab = otsv.parse_lines(chunk, cfg.read_schema(), fc)
+        if step == 0:                       # ids of every wide column, bit-exact, incl. multihot crosses with '' padding (Q2)
+            pm.forward(batch)
+            offs, ids = pm.column_ids()
+            ref = om.transform(raw)
+            C = len(plan.columns)
+            for ci, col in enumerate(plan.columns):
+                if col.name in ref:
+                    ro, ri = ref[col.name]
+                    for b in range(B):
+                        assert np.array_equal(ids[offs[b * C + ci]:offs[b * C + ci + 1]], ri[ro[b]:ro[b + 1]]), (col.name, b)
+        loss = pm.train_step(batch)
+        ref_loss, _ = om.train_step(raw, lab)
+        assert abs(loss - ref_loss) <= 1e-4 * max(abs(ref_loss), 1.0), (step, loss, ref_loss)
+    # evaluation metrics on the eval fixture
+    elines = [l for l in open(os.path.join(ROOT, "data", "eval", "eval1")).read().split("\n") if l][:128]
+    acc = EvalAccumulator()
+    pm.eval_reset()
+    for i in range(0, len(elines), B):
+        chunk = elines[i:i + B]
+        pm.eval_accumulate(reader.parse(chunk))
+        raw, lab = otsv.parse_lines(chunk, cfg.read_schema(), fc)
+        _, cache = om.forward(raw)
+        acc.update(cache["logits"].astype(np.float32), lab)
+    got, exp = pm.eval_finish(), acc.result()
+    for k in exp:
+        assert abs(got[k] - exp[k]) <= 2e-4 * max(abs(exp[k]), 1.0), (k, got[k], exp[k])
+
+
+def test_entry_points_train_then_eval(tmp_path):
+    """python/train.py (dynamic_train over data/train/{train1,train2}) then python/eval.py: same flags, sorted
+    metric printout with the head's ten keys (reference train.py:147-148, eval.py:82-83)."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    mdir = str(tmp_path / "model")
+    r = subprocess.run([sys.executable, "train.py", "--model_dir", mdir, "--train_epochs", "1", "--batch_size", "64"],
+                       cwd=os.path.join(ROOT, "python"), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for key in ["accuracy:", "accuracy_baseline:", "auc:", "auc_precision_recall:", "average_loss:", "label/mean:", "loss:",
+                "precision:", "prediction/mean:", "recall:"]:
+        assert key in r.stdout, key
+    assert "Using dynamic train mode." in r.stdout
+    assert any(f.startswith("model.ckpt-") for f in os.listdir(os.path.join(mdir, "wide_deep")))
+    r2 = subprocess.run([sys.executable, "eval.py", "--model_dir", mdir, "--batch_size", "64"],
+                        cwd=os.path.join(ROOT, "python"), env=env, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert "average_loss:" in r2.stdout and "global_step:" in r2.stdout
+    r3 = subprocess.run([sys.executable, "pred.py", "--model_dir", mdir, "--data_dir", "../data/pred", "--batch_size", "64"],
+                        cwd=os.path.join(ROOT, "python"), env=env, capture_output=True, text=True, timeout=600)
+    assert r3.returncode == 0 and r3.stdout.count("Prediction is") == 64, r3.stdout[-1000:] + r3.stderr[-1000:]
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from wide_deep_b200.config import Config
+    from wide_deep_b200.dataset import input_fn
+    from wide_deep_b200.estimator import build_custom_estimator
+    cfg = Config()
+    est = build_custom_estimator(str(tmp_path / "m"), "wide_deep", config=cfg, max_batch=64)
+    data = os.path.join(ROOT, "data", "test", "test2")
+    est.train(input_fn=lambda: input_fn(data, None, "train", 64, config=cfg, plan=est.plan))
+    m1 = est.evaluate(input_fn=lambda: input_fn(data, None, "eval", 64, config=cfg, plan=est.plan))
+    est2 = build_custom_estimator(str(tmp_path / "m"), "wide_deep", config=cfg, max_batch=64)       # restores latest
+    m2 = est2.evaluate(input_fn=lambda: input_fn(data, None, "eval", 64, config=cfg, plan=est2.plan))
+    assert m1 == m2 and m2["global_step"] == 1
+
+
+def test_device_fingerprint64_bit_exact(native_lib):
+    import random
+    from oracle import hashing as H
+    rnd = random.Random(11)
+    strs = [bytes(rnd.randrange(256) for _ in range(n)) for n in list(range(0, 140)) + [300, 1000, 5000]]
+    buf = np.frombuffer(b"".join(strs) + b"\0", dtype=np.uint8).copy()
+    offs = np.zeros(len(strs) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum([len(s) for s in strs])
+    out = np.zeros(len(strs), dtype=np.uint64)
+    rc = native_lib.wd_fingerprint64_device(buf.ctypes.data, offs.ctypes.data, len(strs), out.ctypes.data)
+    assert rc == 0
+    assert [int(v) for v in out] == [H.fingerprint64(s) for s in strs]
