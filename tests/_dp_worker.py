@@ -1,0 +1,70 @@
+"""Worker for tests/test_gpu_multi.py (launched by torch.distributed.run): every rank trains its row shard with the
+data-parallel trainer; rank 0 also trains a single-GPU model on the concatenated batch and compares parameters."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from oracle import model as OM
+    from tests.helpers import copy_params_to_product, random_raw_batch, to_product_batch
+    from tests.test_gpu_parity import small_conf
+    from tests.test_parallel_gloo import slice_raw
+    from wide_deep_b200.model import WideDeepModel
+    from wide_deep_b200.parallel import DataParallelTrainer, shard_rows
+    from wide_deep_b200.plan import Plan
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fc, cross, model = small_conf(hidden=(64, 32))
+    B = 96 * world
+    om = OM.OracleModel(fc, cross, model, "wide_deep").init(5)
+    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64 * world, max_keys=B * 64)
+    pm = WideDeepModel(plan, device=local)
+    copy_params_to_product(om, pm)
+    trainer = DataParallelTrainer(pm)
+    single = None
+    if rank == 0:
+        single = WideDeepModel(plan, device=local)
+        copy_params_to_product(om, single)
+    rng = np.random.default_rng(77)
+    for step in range(3):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        lo, hi = shard_rows(B, rank, world)
+        trainer.step(to_product_batch(plan, slice_raw(raw, lo, hi), label[lo:hi]))
+        if single is not None:
+            single.train_step(to_product_batch(plan, raw, label))
+    pm.sync()
+    ok = True
+    if rank == 0:
+        for name in pm.tensor_names():
+            a, b = pm.get_tensor(name), single.get_tensor(name)
+            scale = max(float(np.abs(b).max()), 1e-3)
+            if np.max(np.abs(a - b)) > 2e-5 * scale:
+                print("MISMATCH", name, np.max(np.abs(a - b)), scale)
+                ok = False
+    # replicas must stay identical across ranks
+    for name in pm.tensor_names()[:6]:
+        t = torch.from_numpy(pm.get_tensor(name)).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(t, ref):
+            print("REPLICA DIVERGED", name, rank)
+            ok = False
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DP_OK" if flag.item() == 0 else "DP_FAIL")
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

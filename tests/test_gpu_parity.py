@@ -249,3 +249,20 @@ def test_tc1x_engine_is_close_but_not_parity_grade():
     _, cache = om.forward(raw)
     err = np.abs(logits - cache["logits"]) / np.maximum(np.abs(cache["logits"]), 1.0)
     assert err.max() < 2e-2
+
+
+def test_tc3x_wide_tiles_and_presplit_weights():
+    """Hidden widths that are multiples of 256 take the 128x256-tile path with pre-split (hi/lo) weights."""
+    B = 700
+    fc, om, plan, pm = _engine_pair("tc3x", (512, 256), "simple", B, seed=53)
+    rng = np.random.default_rng(59)
+    for step in range(2):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        loss = pm.train_step(to_product_batch(plan, raw, label))
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    for name in pm.tensor_names():
+        got, exp = pm.get_tensor(name), om.params[name]
+        scale = max(float(np.abs(exp).max()), 1e-3)
+        assert np.max(np.abs(got - exp)) <= 2e-4 * scale, "%s: %g (scale %g)" % (name, np.max(np.abs(got - exp)), scale)

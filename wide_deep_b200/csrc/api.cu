@@ -279,6 +279,11 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             const int32_t* dp;
             if ((rc = upload_vec(m, ids.data(), (int64_t)ids.size(), &dp))) return rc;
             m->d_dim_tables[i] = (int32_t*)dp;
+            std::vector<TabDesc> descs;
+            for (int t : ids) descs.push_back(TabDesc{m->tables[t].data, m->tables[t].row_base, m->tables[t].stride, m->tables[t].x0_off, m->tables[t].col, m->tables[t].dim});
+            const TabDesc* dd;
+            if ((rc = upload_vec(m, descs.data(), (int64_t)descs.size(), &dd))) return rc;
+            m->d_dim_desc[i] = (TabDesc*)dd;
         }
         const int64_t actn = (int64_t)m->max_batch_pad * d->d0_phys;
         if ((rc = dev_alloc(m, &m->d_X0, actn))) return rc;
@@ -349,6 +354,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_G, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_gpart, m->gpart_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_Wt, std::max<int64_t>(m->wt_count, 1)))) return rc;
+        if ((rc = dev_alloc(m, &m->d_Wsplit, std::max<int64_t>(4 * m->wt_count, 1)))) return rc;
         const DenseTensor* dp;
         if ((rc = upload_vec(m, m->dense.data(), (int64_t)m->dense.size(), &dp))) return rc;
         m->d_dense_desc = (DenseTensor*)dp;
@@ -369,13 +375,13 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_ugrad[w], (m->max_nnz + 8) * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         if ((rc = dev_alloc(m, &m->d_nuniq[w], 4))) return rc;
         if ((rc = dev_alloc(m, &m->d_nvalid[w], 4))) return rc;
-        m->cpart_cap = 2 * (m->max_nnz / 64) + 64;
+        m->cpart_cap = 2 * (m->max_nnz / 16) + 64;        // kChunk = 16 (sparse.cu)
         if ((rc = dev_alloc(m, &m->d_choff[w], m->max_nnz + 8))) return rc;
         if ((rc = dev_alloc(m, &m->d_nchunks[w], 4))) return rc;
         if ((rc = dev_alloc(m, &m->d_cpart[w], m->cpart_cap * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         m->sparse_cap[w] = m->max_nnz;
     }
-    m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1);
+    m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1) + 4 * 1024 + 64;
     if ((rc = dev_alloc(m, &m->d_sort_hist, m->sort_hist_cap))) return rc;
     if ((rc = metrics_setup())) return rc;
     if ((rc = init_sparse_tables(m, 0, 0))) return rc;           // slots = initial accumulator, weights 0

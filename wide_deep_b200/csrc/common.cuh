@@ -69,6 +69,12 @@ struct EmbTable {
     int stride;              // dim * (1 + nslots)
 };
 
+struct TabDesc {            // per-table descriptor grouped by width (one 32-byte load in the gather kernels)
+    float* data;
+    int64_t row_base;
+    int stride, x0, col, dim;
+};
+
 struct DenseTensor {         // one trainable dense tensor inside the dense arena
     int64_t off;             // offset in arena (floats)
     int64_t count;           // physical element count
@@ -185,6 +191,7 @@ struct WdModel {
     int n_dims = 0;
     int dims[wd::kMaxDims];                  // distinct widths
     int32_t* d_dim_tables[wd::kMaxDims];     // table ids per width (device)
+    wd::TabDesc* d_dim_desc[wd::kMaxDims];    // descriptors of the same tables
     int dim_ntables[wd::kMaxDims];
     // device table descriptors
     float** d_tab_data = nullptr;
@@ -198,6 +205,7 @@ struct WdModel {
     std::vector<wd::DenseTensor> dense;
     int64_t dense_count = 0, gpart_count = 0, wt_count = 0;
     float *d_P = nullptr, *d_S1 = nullptr, *d_S2 = nullptr, *d_G = nullptr, *d_gpart = nullptr, *d_Wt = nullptr;
+    float* d_Wsplit = nullptr;               // [W_hi | W_lo | Wt_hi | Wt_lo], each wt_count floats (3xTF32 pre-split weights)
     wd::DenseTensor* d_dense_desc = nullptr;
     int row_tiles = 0;                       // max_batch_pad / 128
     int wgrad_splits = 4;
@@ -234,6 +242,7 @@ struct WdModel {
     int64_t eval_batches = 0;
 
     int64_t launches = 0;
+    int cur_layer = 0;                       // layer being launched (names the profiling marks)
     wd::PhaseTimer timer;
     std::vector<wd::BatchSlot> slots;        // slot 0 aliases the d_cat_* buffers above
     bool initialized = false;

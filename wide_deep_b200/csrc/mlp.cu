@@ -13,6 +13,8 @@
 // which is why activations and gradients are also kept transposed.  This file holds the fp32 CUDA-core
 // (FFMA) engine — exact fp32 products, used as the parity engine and as the reference the tcgen05 engine
 // (gemm_tc.cu) is validated against.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -157,13 +159,19 @@ static void launch_gemm(WdModel* m, int mode, const GemmA& A, const float* B, in
 }
 
 // tcgen05 engine (gemm_tc.cu); returns WD_EUNSUPPORTED when the shape is not covered
-int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len);
+int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len,
+            const float* B_hi, const float* B_lo);
 
-static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits = 1, int ksplit_len = 0) {
-    static const char* kNames[3] = {"gemm_fwd", "gemm_dgrad", "gemm_wgrad"};
+static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits = 1, int ksplit_len = 0,
+                    const float* B_hi = nullptr, const float* B_lo = nullptr) {
+    static const char* kNamesL[3][4] = {{"gemm_fwd_l0", "gemm_fwd_l1", "gemm_fwd_l2", "gemm_fwd_l3+"},
+                                        {"gemm_dgrad_l0", "gemm_dgrad_l1", "gemm_dgrad_l2", "gemm_dgrad_l3+"},
+                                        {"gemm_wgrad_l0", "gemm_wgrad_l1", "gemm_wgrad_l2", "gemm_wgrad_l3+"}};
+    const char* kNames[3] = {kNamesL[0][m->cur_layer < 3 ? m->cur_layer : 3], kNamesL[1][m->cur_layer < 3 ? m->cur_layer : 3],
+                             kNamesL[2][m->cur_layer < 3 ? m->cur_layer : 3]};
     mark(m, "mlp_other");
     if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
-        int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
+        int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len, B_hi, B_lo);
         if (rc != WD_EUNSUPPORTED) { mark(m, kNames[mode]); return rc; }
     }
     launch_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
@@ -382,9 +390,17 @@ __device__ __forceinline__ void opt_update_d(const OptParamsD& o, float g, float
     }
 }
 // applies the optimizer over the dense arena; kernels also refresh their transposed copy Wt[n][k]
+// hi/lo split of a weight for the 3xTF32 engine (same split the GEMM applies to activations in shared memory)
+__device__ __forceinline__ void store_split(float* __restrict__ Wsplit, int64_t wt_count, int64_t wt_off, int64_t e, int64_t et, float w) {
+    float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u), lo = w - hi;
+    Wsplit[wt_off + e] = hi;                       // W  [K, N] hi
+    Wsplit[wt_count + wt_off + e] = lo;            // W  [K, N] lo
+    Wsplit[2 * wt_count + wt_off + et] = hi;       // Wt [N, K] hi
+    Wsplit[3 * wt_count + wt_off + et] = lo;       // Wt [N, K] lo
+}
 __global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ G,
                                    float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ Wt,
-                                   OptParamsD dnn, OptParamsD lin, int lin_tensor) {
+                                   float* __restrict__ Wsplit, int64_t wt_count, OptParamsD dnn, OptParamsD lin, int lin_tensor) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nt - 1;
         while (lo < hi) {
@@ -400,11 +416,13 @@ __global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, in
             int64_t e = i - t.off;
             int k = (int)(e / t.cols), n = (int)(e % t.cols);
             Wt[t.wt_off + (int64_t)n * t.rows + k] = w;
+            store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, w);
         }
     }
 }
 // Wt refresh only (after init / tensor upload)
-__global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ P, float* __restrict__ Wt) {
+__global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ P, float* __restrict__ Wt,
+                                       float* __restrict__ Wsplit, int64_t wt_count) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nt - 1;
         while (lo < hi) {
@@ -416,12 +434,13 @@ __global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt
             int64_t e = i - t.off;
             int k = (int)(e / t.cols), n = (int)(e % t.cols);
             Wt[t.wt_off + (int64_t)n * t.rows + k] = P[i];
+            store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, P[i]);
         }
     }
 }
 int dense_refresh_transposes(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
-    dense_transpose_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_P, m->d_Wt);
+    dense_transpose_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_P, m->d_Wt, m->d_Wsplit, m->wt_count);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
@@ -449,6 +468,7 @@ int mlp_forward(WdModel* m, bool train) {
     for (auto& tw : m->towers) {
         for (int l = 0; l < tw.n_hidden; ++l) {
             Layer& L = tw.layers[l];
+            m->cur_layer = l;
             GemmA A{};
             A.n = L.n_in_segs;
             for (int s = 0; s < L.n_in_segs; ++s) {
@@ -463,8 +483,10 @@ int mlp_forward(WdModel* m, bool train) {
             ep.gamma = L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr;
             ep.beta = L.t_beta >= 0 ? m->d_P + m->dense[L.t_beta].off : nullptr;
             ep.n_logical = L.N; ep.act = m->activation; ep.bn = m->batch_norm; ep.m_valid = B;
-            const float* Wt = m->d_Wt + m->dense[L.t_kernel].wt_off;
-            int rc = run_gemm(m, EPI_FWD, A, Wt, L.K_phys, B, L.N_phys, ep);
+            { static const int dbg = getenv("WD_EPI_DBG") ? atoi(getenv("WD_EPI_DBG")) : 0; ep.dbg = dbg; }
+            const int64_t wo = m->dense[L.t_kernel].wt_off;
+            const float* Wt = m->d_Wt + wo;
+            int rc = run_gemm(m, EPI_FWD, A, Wt, L.K_phys, B, L.N_phys, ep, 1, 0, m->d_Wsplit + 2 * m->wt_count + wo, m->d_Wsplit + 3 * m->wt_count + wo);
             if (rc) return rc;
         }
         Layer& LL = tw.layers[tw.n_hidden];
@@ -533,6 +555,7 @@ int mlp_backward(WdModel* m) {
         // ---- hidden layers, last to first
         for (int l = tw.n_hidden - 1; l >= 0; --l) {
             Layer& L = tw.layers[l];
+            m->cur_layer = l;
             const DenseTensor& tkn = m->dense[L.t_kernel];
             float* pb = m->d_gpart + m->dense[L.t_bias].gpart_off;
             float* pg = L.t_gamma >= 0 ? m->d_gpart + m->dense[L.t_gamma].gpart_off : nullptr;
@@ -563,7 +586,9 @@ int mlp_backward(WdModel* m) {
                 A2.n = 1; A2.ptr[0] = L.dZ; A2.ld[0] = L.N_phys; A2.k[0] = L.N_phys;
                 Epi e2{};
                 e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
-                rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2);
+                const int64_t woff = tkn.wt_off + (int64_t)sg.k_off * L.N_phys;
+                rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
+                              m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff);
                 if (rc) return rc;
             }
         }
@@ -588,7 +613,7 @@ int dense_apply(WdModel* m) {
     OptParamsD l{m->lin_opt.kind, m->lin_opt.lr, m->lin_opt.l1, m->lin_opt.l2};
     int lin_tensor = m->use_wide ? 0 : -1;                       // tensor 0 is the wide bias when the wide part exists
     dense_apply_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_G,
-                                                                            m->d_P, m->d_S1, m->d_S2, m->d_Wt, d, l, lin_tensor);
+                                                                            m->d_P, m->d_S1, m->d_S2, m->d_Wt, m->d_Wsplit, m->wt_count, d, l, lin_tensor);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;

@@ -118,74 +118,61 @@ constexpr int RS_ITEMS_PER_WARP = 512;                 // 16 rounds of 32
 constexpr int RS_TILE = RS_WARPS * RS_ITEMS_PER_WARP;  // 4096 keys per tile
 constexpr int RS_MAX_BINS = 1024;
 
-// Per-tile digit histogram -> hist[bin * ntiles + tile]; last block turns hist into exclusive offsets.
+// Per-tile digit histogram -> hist[tile * bins + bin] (tile-major, coalesced) and global per-bin totals gtot[bin].
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,
-                                                             int shift, int bins, int ntiles_cap, int32_t* hist,
-                                                             int32_t* counter) {
+                                                             int shift, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot) {
     extern __shared__ int sh[];           // bins
-    __shared__ int sm[33];
-    __shared__ bool is_last;
-    const int n = *d_n;
-    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
-    const int tile = blockIdx.x;
-    if (tile < ntiles) {
-        for (int i = threadIdx.x; i < bins; i += RS_THREADS) sh[i] = 0;
-        __syncthreads();
-        int base = tile * RS_TILE;
-        for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
-            int j = base + i;
-            if (j < n) atomicAdd(&sh[(keys[j] >> shift) & (bins - 1)], 1);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < bins; i += RS_THREADS) hist[i * ntiles_cap + tile] = sh[i];
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        int t = atomicAdd(counter, 1);
-        is_last = (t == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // exclusive scan over (bin major, tile minor) of the first `ntiles` tiles of each bin
-    int carry = 0;
-    const int total = bins * ntiles;
-    for (int off = 0; off < total; off += RS_THREADS * 4) {
-        int v[4], s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int i = off + threadIdx.x * 4 + k;
-            int idx = (i / ntiles) * ntiles_cap + (i % ntiles);
-            v[k] = i < total ? ((volatile int32_t*)hist)[idx] : 0;
-            s += v[k];
-        }
-        int tot;
-        int e = block_excl_scan(s, sm, &tot) + carry;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int i = off + threadIdx.x * 4 + k;
-            if (i < total) hist[(i / ntiles) * ntiles_cap + (i % ntiles)] = e;
-            e += v[k];
-        }
-        carry += tot;
-    }
-    if (threadIdx.x == 0) *counter = 0;
-}
-
-// Stable scatter of one tile.
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in,
-                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                                const int32_t* __restrict__ d_n, int shift, int bins,
-                                                                int ntiles_cap, const int32_t* __restrict__ hist) {
-    extern __shared__ int wh[];           // [RS_WARPS][bins]
     const int n = *d_n;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     const int tile = blockIdx.x;
     if (tile >= ntiles) return;
+    for (int i = threadIdx.x; i < bins; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const int base = tile * RS_TILE;
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        int j = base + i;
+        if (j < n) atomicAdd(&sh[(keys[j] >> shift) & (bins - 1)], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += RS_THREADS) {
+        int c = sh[i];
+        hist[(int64_t)tile * bins + i] = c;
+        if (c) atomicAdd(&gtot[i], c);
+    }
+}
+
+// Stable scatter of one tile.  The tile first derives its own output bases: exclusive scan of the global bin totals
+// plus the counts of the same bin in all earlier tiles (coalesced column sums over the tile-major histogram), so no
+// serial scan kernel sits between the histogram and the scatter.
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                const int32_t* __restrict__ d_n, int shift, int bins,
+                                                                const int32_t* __restrict__ hist, const int32_t* __restrict__ gtot) {
+    extern __shared__ int wh[];           // [RS_WARPS][bins] then tilebase[bins]
+    __shared__ int sm[33];
+    const int n = *d_n;
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    const int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    int* tilebase = wh + RS_WARPS * bins;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- tile bases: thread owns `per` consecutive bins
+    {
+        const int per = bins / RS_THREADS > 0 ? bins / RS_THREADS : 1;       // bins is a power of two >= 2
+        const int b0 = threadIdx.x * per;
+        int tot[4] = {0, 0, 0, 0}, prev[4] = {0, 0, 0, 0};
+        int s = 0;
+        if (b0 < bins) {
+            for (int k = 0; k < per; ++k) { tot[k] = gtot[b0 + k]; s += tot[k]; }
+            for (int t = 0; t < tile; ++t)
+                for (int k = 0; k < per; ++k) prev[k] += hist[(int64_t)t * bins + b0 + k];
+        }
+        int blocktot;
+        int run = block_excl_scan(s, sm, &blocktot);
+        if (b0 < bins)
+            for (int k = 0; k < per; ++k) { tilebase[b0 + k] = run + prev[k]; run += tot[k]; }
+    }
     for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) wh[i] = 0;
     __syncthreads();
     const int wbase = tile * RS_TILE + w * RS_ITEMS_PER_WARP;
@@ -196,9 +183,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
         if (j < n) atomicAdd(&my[(keys_in[j] >> shift) & (bins - 1)], 1);
     }
     __syncthreads();
-    // phase B: warp bases = global tile offset + counts of earlier warps
+    // phase B: warp bases = tile base + counts of earlier warps
     for (int b = threadIdx.x; b < bins; b += RS_THREADS) {
-        int run = hist[b * ntiles_cap + tile];
+        int run = tilebase[b];
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) {
             int c = wh[ww * bins + b];
@@ -228,26 +215,28 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
     }
 }
 
-// Sort pairs (m->d_sk[which], m->d_sv[which]) of length *m->d_nnz by the low `bits` bits of the key.
+// Sort pairs (m->d_sk[which], m->d_sv[which]) of length *d_n by the low `bits` bits of the key.
 // On return the sorted pairs are in d_sk/d_sv (buffers are swapped as needed).
+// Cost note: every scatter tile sums the histograms of the tiles before it (O(tiles^2 * bins) loads in total):
+// fine up to a few million keys per step; beyond that this needs a hierarchical scan.
 int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     if (bits < 1) bits = 1;
     int passes = (bits + 9) / 10;
     int per = (bits + passes - 1) / passes;
+    if (per < 8) per = 8;                                   // bins >= 256 so every thread owns at least one bin
     int bins = 1 << per;
     int ntiles_cap = (int)((m->max_nnz + RS_TILE - 1) / RS_TILE);
-    if ((int64_t)bins * ntiles_cap > m->sort_hist_cap) {
+    if ((int64_t)bins * ntiles_cap + 4 * 1024 > m->sort_hist_cap) {
         set_error("radix sort histogram capacity too small");
         return WD_ESTATE;
     }
+    int32_t* gtot = m->d_sort_hist + (int64_t)bins * ntiles_cap;        // [passes][bins]
+    WD_CUDA(cudaMemsetAsync(gtot, 0, (size_t)passes * bins * sizeof(int32_t), m->stream));
     for (int p = 0; p < passes; ++p) {
         int shift = p * per;
-        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins,
-                                                                                  ntiles_cap, m->d_sort_hist,
-                                                                                  m->d_sort_counter);
-        rs_scatter_kernel<<<ntiles_cap, RS_THREADS, RS_WARPS * bins * sizeof(int), m->stream>>>(
-            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, ntiles_cap,
-            m->d_sort_hist);
+        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
+        rs_scatter_kernel<<<ntiles_cap, RS_THREADS, (RS_WARPS + 1) * bins * sizeof(int), m->stream>>>(
+            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
         m->launches += 2;
         std::swap(m->d_sk[which], m->d_sk2[which]);
         std::swap(m->d_sv[which], m->d_sv2[which]);

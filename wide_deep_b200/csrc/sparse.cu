@@ -136,9 +136,68 @@ __global__ void __launch_bounds__(256) emb_pool_fwd_kernel(int B, int C, int nta
     }
 }
 
+// Warp per example (short bags).  The warp walks the example's bags of this width in rounds of 32/G bags and
+// issues the loads of RMAX rounds back to back: offsets, then first ids, then first rows — every lane group keeps
+// RMAX independent 16-byte row loads in flight instead of one dependent chain at a time.
+template <int G, int RMAX>
+__global__ void __launch_bounds__(256) emb_pool_fwd_rows_kernel(int B, int C, int ntab, const TabDesc* __restrict__ desc,
+                                                                const int32_t* __restrict__ offs, const uint32_t* __restrict__ e_emb,
+                                                                float* __restrict__ X0, int ld) {
+    constexpr int GROUPS = 32 / G;
+    const int lane = threadIdx.x & 31, lig = lane % G, grp = lane / G;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int b = gwarp; b < B; b += nwarp) {
+        const int32_t* orow = offs + (int64_t)b * C;
+        float* xrow = X0 + (int64_t)b * ld;
+        for (int k0 = 0; k0 < ntab; k0 += GROUPS * RMAX) {
+            TabDesc d[RMAX];
+            int s[RMAX], n[RMAX];
+            float4 acc[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int k = k0 + r * GROUPS + grp;
+                n[r] = -1;
+                if (k < ntab) {
+                    d[r] = desc[k];
+                    s[r] = orow[d[r].col];
+                    n[r] = orow[d[r].col + 1] - s[r];
+                }
+            }
+            uint32_t id0[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) id0[r] = n[r] > 0 ? e_emb[s[r]] : 0u;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n[r] > 0) acc[r] = ldg_nc_f4(d[r].data + (int64_t)(id0[r] - d[r].row_base) * d[r].stride + lig * 4);
+            }
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (n[r] > 1) {                                  // multihot bag: remaining rows, then the mean
+                    for (int j = 1; j < n[r]; ++j) {
+                        float4 v = ldg_nc_f4(d[r].data + (int64_t)(e_emb[s[r] + j] - d[r].row_base) * d[r].stride + lig * 4);
+                        acc[r].x += v.x; acc[r].y += v.y; acc[r].z += v.z; acc[r].w += v.w;
+                    }
+                    const float inv = 1.f / (float)n[r];
+                    acc[r].x *= inv; acc[r].y *= inv; acc[r].z *= inv; acc[r].w *= inv;
+                }
+                if (n[r] >= 0) *reinterpret_cast<float4*>(xrow + d[r].x0 + lig * 4) = acc[r];
+            }
+        }
+    }
+}
+
 template <int G>
 static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
     int ntab = m->dim_ntables[di];
+    if (!widebag) {
+        constexpr int RMAX = G >= 16 ? 4 : 8;
+        int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148 * 8);
+        emb_pool_fwd_rows_kernel<G, RMAX><<<grid, 256, 0, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_desc[di], m->d_col_offs,
+                                                                        m->d_e_emb, m->d_X0, m->d0_phys);
+        m->launches++;
+        return;
+    }
     int64_t nbags = (int64_t)m->dbatch.B * ntab;
     int64_t warps = widebag ? nbags : (nbags + (32 / G) - 1) / (32 / G);
     int grid = grid_for(warps * 32, 256, 148 * 8);
@@ -228,7 +287,7 @@ __global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint
 // Rows touched at most kChunk times are summed by one lane group directly.  Hotter rows (small tables,
 // skewed ids) are split into chunks of kChunk occurrences that are summed in parallel and then combined in
 // chunk order, so the result stays deterministic and no single group walks thousands of occurrences.
-constexpr int kChunk = 64;
+constexpr int kChunk = 16;
 
 // mch[u] = number of chunks of a multi-chunk row, 0 for rows summed directly (and for u >= nuniq)
 __global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, int32_t* mch, int64_t cap) {
