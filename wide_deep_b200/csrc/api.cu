@@ -100,6 +100,9 @@ extern "C" int wd_model_destroy(WdModel* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
     for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
+    if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
+    if (m->ev_ids) cudaEventDestroy(m->ev_ids);
+    if (m->ev_sorted) cudaEventDestroy(m->ev_sorted);
     if (m->stream) cudaStreamDestroy(m->stream);
     for (size_t i = 0; i < g_extra.size(); ++i)
         if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
@@ -407,6 +410,9 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     m->device = device;
     memset(m->timer.ev, 0, sizeof(m->timer.ev));
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sorted, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
     int rc = build_model(d, m, x);
     if (rc) { wd_model_destroy(m); return rc; }
@@ -652,10 +658,26 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
     return WD_OK;
 }
 
+// launch the id-only grouping of the sparse backward on the side stream (overlaps forward + backward of the towers)
+static int group_async(WdModel* m) {
+    if (m->timer.enabled) return WD_OK;                      // profiling: keep everything on one stream (done before the reduce)
+    WD_CUDA(cudaEventRecord(m->ev_ids, m->stream));
+    WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_ids, 0));
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->stream2;
+    int rc = sparse_group(m);
+    m->stream = main_stream;
+    if (rc) return rc;
+    WD_CUDA(cudaEventRecord(m->ev_sorted, m->stream2));
+    m->sorted_pending = true;
+    return WD_OK;
+}
+
 static int forward_core(WdModel* m, bool train) {
     int rc;
     if ((rc = ids_prepare(m))) return rc;
     mark(m, "ids");
+    if (train && (rc = group_async(m))) return rc;
     if ((rc = sparse_forward(m))) return rc;
     if ((rc = mlp_forward(m, train))) return rc;
     mark(m, "mlp_other");
@@ -671,6 +693,10 @@ static int backward_core(WdModel* m) {
     if ((rc = wide_bias_grad(m))) return rc;
     if ((rc = dense_reduce_grads(m))) return rc;
     mark(m, "dense_reduce");
+    if (m->sorted_pending) {
+        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sorted, 0));
+        m->sorted_pending = false;
+    } else if ((rc = sparse_group(m))) return rc;
     if ((rc = sparse_backward_reduce(m))) return rc;
     m->grads_pending = true;
     return WD_OK;

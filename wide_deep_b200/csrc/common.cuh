@@ -154,6 +154,9 @@ struct WdModel {
     int gemm_engine = 0;
 
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // side stream: the id-only part of the sparse backward overlaps the towers
+    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr;
+    bool sorted_pending = false;
     wd::DevPlan dplan{};
     std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
     int64_t bytes_allocated = 0;
@@ -253,7 +256,8 @@ namespace wd {
 // ---- kernels / stages implemented in the .cu files (all enqueue on m->stream)
 int ids_prepare(WdModel* m);                                     // ids.cu
 int sparse_forward(WdModel* m);                                  // sparse.cu: wide logit + embedding pooling + numerics
-int sparse_backward_reduce(WdModel* m);                          // sparse.cu: sort + per-row gradient sums
+int sparse_group(WdModel* m);                                    // sparse.cu: sort (row, occurrence) pairs, unique rows, chunks
+int sparse_backward_reduce(WdModel* m);                          // sparse.cu: per-row gradient sums
 int sparse_apply(WdModel* m);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
 int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
 int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0

@@ -519,42 +519,51 @@ int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int
 }
 
 // sort + per-row gradient sums for both tables; leaves (urow, ugrad, nuniq) ready for exchange / apply
-int sparse_backward_reduce(WdModel* m) {
+// Stage 1 of the sparse backward: group the step's (row, occurrence) pairs by row for both table spaces and lay out
+// the hot-row chunks.  Depends only on the ids of the batch (not on any gradient), so api.cu runs it on a side stream
+// concurrently with the towers' forward/backward.
+int sparse_group(WdModel* m) {
     int rc;
+    const int g = grid_for(m->max_nnz, 256);
     if (m->use_deep && !m->tables.empty()) {
         if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
+        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->max_nnz);
+        m->launches++;
+        if ((rc = exclusive_scan_i32(m, m->d_choff[0], m->max_nnz, m->d_nchunks[0]))) return rc;
         mark(m, "emb_group");
-        {
-            int g = grid_for(m->max_nnz, 256);
-            chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->max_nnz);
-            m->launches++;
-            if ((rc = exclusive_scan_i32(m, m->d_choff[0], m->max_nnz, m->d_nchunks[0]))) return rc;
-            int ge = grid_for(m->max_nnz * 8, 256);
-            emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
-                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
-            emb_grad_sum_kernel<true><<<grid_for(m->cpart_cap * 8, 256), 256, 0, m->stream>>>(m->d_nchunks[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
-                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_cpart[0], m->emb_max_dim);
-            chunk_combine_kernel<<<grid_for(m->max_nnz * (int64_t)m->emb_max_dim / 4, 256), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
-            m->launches += 3;
-        }
+    }
+    if (m->use_wide) {
+        if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
+        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->max_nnz);
+        m->launches++;
+        if ((rc = exclusive_scan_i32(m, m->d_choff[1], m->max_nnz, m->d_nchunks[1]))) return rc;
+        mark(m, "wide_group");
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// Stage 2: per-row gradient sums for both tables; leaves (urow, ugrad, nuniq) ready for exchange / apply
+int sparse_backward_reduce(WdModel* m) {
+    const int g = grid_for(m->max_nnz, 256);
+    if (m->use_deep && !m->tables.empty()) {
+        int ge = grid_for(m->max_nnz * 8, 256);
+        emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+            m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
+        emb_grad_sum_kernel<true><<<grid_for(m->cpart_cap * 8, 256), 256, 0, m->stream>>>(m->d_nchunks[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+            m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_cpart[0], m->emb_max_dim);
+        chunk_combine_kernel<<<grid_for(m->max_nnz * (int64_t)m->emb_max_dim / 4, 256), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
+        m->launches += 3;
         mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
     }
     if (m->use_wide) {
-        if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
-        mark(m, "wide_group");
-        {
-            int g = grid_for(m->max_nnz, 256);
-            chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->max_nnz);
-            m->launches++;
-            if ((rc = exclusive_scan_i32(m, m->d_choff[1], m->max_nnz, m->d_nchunks[1]))) return rc;
-            wide_grad_sum_kernel<false><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
-                                                                  m->n_columns, m->d_dlogit, m->d_ugrad[1]);
-            wide_grad_sum_kernel<true><<<grid_for(m->cpart_cap, 256), 256, 0, m->stream>>>(m->d_nchunks[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
-                                                                                          m->n_columns, m->d_dlogit, m->d_cpart[1]);
-            chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1);
-            m->launches += 3;
-        }
+        wide_grad_sum_kernel<false><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                              m->n_columns, m->d_dlogit, m->d_ugrad[1]);
+        wide_grad_sum_kernel<true><<<grid_for(m->cpart_cap, 256), 256, 0, m->stream>>>(m->d_nchunks[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                                                      m->n_columns, m->d_dlogit, m->d_cpart[1]);
+        chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1);
+        m->launches += 3;
         mark(m, "wide_grad_sum");
         m->sparse_overridden[1] = false;
     }
