@@ -184,7 +184,7 @@ def main():
     trainer = None
     if world > 1:
         from wide_deep_b200.parallel import DataParallelTrainer
-        trainer = DataParallelTrainer(model)
+        trainer = DataParallelTrainer(model, fixed_rows=(B * n_cat, B * n_cols))
 
     # distinct batches per (rank, ring slot) in pinned host memory
     host = []

@@ -158,7 +158,9 @@ int64_t wd_dense_grad_count(WdModel *m);
 void *wd_dense_grad_ptr(WdModel *m);          /* device pointer */
 /* Sparse gradient lists after wd_step_backward.  which: 0 = embedding rows, 1 = wide rows.
  * rows: device uint32[n] global row ids (sorted unique), grads: device float[n*width] (width 1 for wide,
- * max table dim for embeddings, rows of narrower tables are zero padded). */
+ * max table dim for embeddings, rows of narrower tables are zero padded).  Entries [n, capacity) of `rows` hold
+ * 0xFFFFFFFF (skipped by wd_sparse_set), so a fixed-size exchange needs no count: pass n = NULL to skip the
+ * host synchronisation that reading the count requires. */
 int wd_sparse_grads(WdModel *m, int which, void **rows, void **grads, int64_t *n, int32_t *width, int64_t *capacity);
 /* Replace the sparse gradient list by a merged one (rows need not be unique or sorted). */
 int wd_sparse_set(WdModel *m, int which, const void *rows_dev, const void *grads_dev, int64_t n);

@@ -28,7 +28,8 @@ def main():
     plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64 * world, max_keys=B * 64)
     pm = WideDeepModel(plan, device=local)
     copy_params_to_product(om, pm)
-    trainer = DataParallelTrainer(pm)
+    fixed = (96 * 64, 96 * 64) if os.environ.get("WD_DP_FIXED") else None
+    trainer = DataParallelTrainer(pm, fixed_rows=fixed)
     single = None
     if rank == 0:
         single = WideDeepModel(plan, device=local)

@@ -9,12 +9,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_data_parallel_equals_single_gpu():
+@pytest.mark.parametrize("fixed", [False, True])
+def test_two_gpu_data_parallel_equals_single_gpu(fixed):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29641", os.path.join(ROOT, "tests", "_dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ)
+    if fixed:
+        env["WD_DP_FIXED"] = "1"          # asynchronous fixed-size exchange (no host-side counts)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -802,12 +802,14 @@ extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads,
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    int32_t nu = 0;
-    WD_CUDA(cudaStreamSynchronize(m->stream));
-    WD_CUDA(cudaMemcpy(&nu, m->d_nuniq[which], 4, cudaMemcpyDeviceToHost));
+    if (n) {                                   // the count needs a sync; pass n = NULL for the asynchronous fixed-size exchange
+        int32_t nu = 0;
+        WD_CUDA(cudaStreamSynchronize(m->stream));
+        WD_CUDA(cudaMemcpy(&nu, m->d_nuniq[which], 4, cudaMemcpyDeviceToHost));
+        *n = nu;
+    }
     if (rows) *rows = m->d_urow[which];
     if (grads) *grads = m->d_ugrad[which];
-    if (n) *n = nu;
     if (width) *width = which == 0 ? m->emb_max_dim : 1;
     if (capacity) *capacity = m->sparse_cap[which];
     return WD_OK;
@@ -817,7 +819,9 @@ extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const 
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    return merge_sparse(m, which, rows_dev, grads_dev, n);
+    if ((rc = merge_sparse(m, which, rows_dev, grads_dev, n))) return rc;
+    // hot-row chunk layout is not used by the apply kernels; nothing else to rebuild
+    return WD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- eval

@@ -10,6 +10,8 @@
 // HBM-bound kernels: 16-byte vector loads through the read-only path, several rows in flight per lane
 // group, rows are 16..256 B records {w | optimizer slots} so forward touches one line and backward one
 // contiguous record.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wd {
@@ -187,9 +189,168 @@ __global__ void __launch_bounds__(256) emb_pool_fwd_rows_kernel(int B, int C, in
     }
 }
 
+// --------------------------------------------------------------------------------- TMA-staged gather (short bags)
+// Warp per example, rows staged in shared memory by 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global with
+// mbarrier complete_tx): every lane issues the copies of "its" table's rows, so a warp has the whole example (e.g.
+// 26 x 128 B) in flight with a handful of instructions and no registers tied up; a ring of NBUF staging buffers per
+// warp keeps several examples in flight.  Single-valued bags whose columns are adjacent in the deep input (the
+// Criteo shape) are written back with ONE bulk store (cp.async.bulk.global.shared::cta) straight from the staging
+// buffer; otherwise lane groups pool the staged rows (mean) and store float4s.
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sm_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra W_DONE;\n\t"
+        "bra W_LOOP;\n\t"
+        "W_DONE:\n\t}" ::"r"(sm_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) emb_pool_fwd_tma_kernel(int B, int C, int ntab, const TabDesc* __restrict__ desc,
+                                                               const int32_t* __restrict__ offs, const uint32_t* __restrict__ e_emb,
+                                                               float* __restrict__ X0, int ld, int buf_bytes, int nbuf, int contiguous) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    constexpr int ROWB = G * 16;                         // bytes per embedding row
+    constexpr int GROUPS = 32 / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slots = buf_bytes / ROWB;
+    uint8_t* wbase = tsm + (size_t)warp * nbuf * buf_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)8 * nbuf * buf_bytes) + warp * 8;      // up to 8 buffers per warp
+    if (lane == 0)
+        for (int i = 0; i < nbuf; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int nex = gwarp < B ? (B - gwarp + nwarp - 1) / nwarp : 0;   // examples of this warp
+
+    // per-lane state of an in-flight example (tables lane, lane+32, ... only the first 32 tables use the TMA path)
+    auto issue = [&](int i) -> int {                 // stage example i of this warp; returns total entries (or -1: too many)
+        const int b = gwarp + i * nwarp;
+        const int buf = i % nbuf;
+        const int32_t* orow = offs + (int64_t)b * C;
+        int s = 0, n = 0;
+        TabDesc d{};
+        if (lane < ntab) { d = desc[lane]; s = orow[d.col]; n = orow[d.col + 1] - s; }
+        int pos = n;                                   // exclusive prefix of n over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pos, o); if (lane >= o) pos += t; }
+        const int total = __shfl_sync(0xffffffffu, pos, 31);
+        pos -= n;
+        if (total > slots) {                           // does not fit the staging buffer: keep the barrier phase in step, drain with direct loads
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(&bars[buf])), "r"(0u) : "memory");
+            return -1;
+        }
+        uint8_t* bbase = wbase + (size_t)buf * buf_bytes;
+        for (int j = 0; j < n; ++j) {
+            const float* src = d.data + (int64_t)(e_emb[s + j] - d.row_base) * d.stride;
+            bulk_g2s(bbase + (size_t)(pos + j) * ROWB, src, ROWB, &bars[buf]);
+        }
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(&bars[buf])), "r"((uint32_t)(total * ROWB)) : "memory");
+        return total;
+    };
+
+    const int depth = nbuf - 1 > 0 ? nbuf - 1 : 1;      // examples in flight ahead of the one being drained
+    for (int i = 0; i < nex && i < depth; ++i) {
+        if (issue(i) < 0) { /* handled when drained (falls back to direct loads) */ }
+    }
+    for (int i = 0; i < nex; ++i) {
+        const int b = gwarp + i * nwarp;
+        const int buf = i % nbuf;
+        const int32_t* orow = offs + (int64_t)b * C;
+        float* xrow = X0 + (int64_t)b * ld;
+        // recompute this example's layout (cheap, L1/L2 hits) instead of carrying it across the pipeline
+        int s = 0, n = 0;
+        TabDesc d{};
+        if (lane < ntab) { d = desc[lane]; s = orow[d.col]; n = orow[d.col + 1] - s; }
+        int pos = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pos, o); if (lane >= o) pos += t; }
+        const int total = __shfl_sync(0xffffffffu, pos, 31);
+        pos -= n;
+        const bool staged = total <= slots;
+        uint8_t* bbase = wbase + (size_t)buf * buf_bytes;
+        mbar_wait_parity(&bars[buf], (uint32_t)((i / nbuf) & 1));
+        const bool all_single = __all_sync(0xffffffffu, lane >= ntab || n == 1);
+        if (staged && all_single && contiguous) {
+            // the staging buffer already is the example's slice of the deep input
+            if (lane == 0) {
+                bulk_s2g(xrow + desc[0].x0, bbase, (uint32_t)(ntab * ROWB));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            const int lig = lane % G, grp = lane / G;
+            for (int k0 = 0; k0 < ntab; k0 += GROUPS) {
+                const int k = k0 + grp;
+                const int kk = k < ntab ? k : 0;
+                const int pk = __shfl_sync(0xffffffffu, pos, kk), nk = __shfl_sync(0xffffffffu, n, kk), sk = __shfl_sync(0xffffffffu, s, kk);
+                if (k < ntab) {
+                    const TabDesc dk = desc[k];
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < nk; ++j) {
+                        float4 v = staged ? *reinterpret_cast<const float4*>(bbase + (size_t)(pk + j) * ROWB + lig * 16)
+                                          : ldg_nc_f4(dk.data + (int64_t)(e_emb[sk + j] - dk.row_base) * dk.stride + lig * 4);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    if (nk > 1) { const float inv = 1.f / (float)nk; acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+                    *reinterpret_cast<float4*>(xrow + dk.x0 + lig * 4) = acc;
+                }
+            }
+        }
+        __syncwarp();
+        // refill: example i + depth goes into buffer (i + depth) % nbuf == the buffer drained one iteration ago (or this
+        // one when nbuf == depth + 1 ... ) -> wait until its bulk store has finished reading shared memory
+        const int nxt = i + depth;
+        if (nxt < nex) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            issue(nxt);
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int G>
 static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
     int ntab = m->dim_ntables[di];
+    static const int gather_mode = getenv("WD_GATHER") ? atoi(getenv("WD_GATHER")) : 1;     // 0: LDG kernel, 1: TMA-staged kernel
+    if (!widebag && gather_mode == 1 && ntab <= 32) {
+        const int rowb = G * 16;
+        int buf_bytes = ((ntab * rowb * 5 / 4 + 1023) / 1024) * 1024;             // 25% head-room for multihot bags (larger ones use direct loads)
+        if (buf_bytes < 1024) buf_bytes = 1024;
+        int nbuf = (int)((200 * 1024) / (8 * (int64_t)buf_bytes));
+        if (nbuf > 6) nbuf = 6;
+        if (nbuf >= 2) {
+            // tables of this width adjacent in the deep input, in descriptor order?  (host check once per model would do; cheap here)
+            int contiguous = 1;
+            int prev = -1;
+            for (auto& tb : m->tables)
+                if (tb.dim == m->dims[di]) {
+                    if (prev >= 0 && tb.x0_off != prev + tb.dim) contiguous = 0;
+                    prev = tb.x0_off;
+                }
+            size_t smem = (size_t)8 * nbuf * buf_bytes + 8 * 8 * sizeof(uint64_t);
+            static bool configured[wd::kMaxDims] = {false};
+            if (!configured[di]) {
+                cudaFuncSetAttribute(emb_pool_fwd_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured[di] = true;
+            }
+            int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148);
+            emb_pool_fwd_tma_kernel<G><<<grid, 256, smem, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_desc[di], m->d_col_offs, m->d_e_emb,
+                                                                   m->d_X0, m->d0_phys, buf_bytes, nbuf, contiguous);
+            m->launches++;
+            return;
+        }
+    }
     if (!widebag) {
         constexpr int RMAX = G >= 16 ? 4 : 8;
         int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148 * 8);
@@ -290,13 +451,16 @@ __global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint
 constexpr int kChunk = 16;
 
 // mch[u] = number of chunks of a multi-chunk row, 0 for rows summed directly (and for u >= nuniq)
-__global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, int32_t* mch, int64_t cap) {
+// (also pads the unique-row list with kInvalidRow up to its capacity, so fixed-size exchanges need no host-side count)
+__global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, int32_t* mch, uint32_t* urow, int64_t cap) {
     const int nu = *d_nuniq;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += (int64_t)gridDim.x * blockDim.x) {
         int v = 0;
         if (u < nu) {
             int len = ustart[u + 1] - ustart[u];
             if (len > kChunk) v = (len + kChunk - 1) / kChunk;
+        } else {
+            urow[u] = kInvalidRow;
         }
         mch[u] = v;
     }
@@ -527,14 +691,14 @@ int sparse_group(WdModel* m) {
     const int g = grid_for(m->max_nnz, 256);
     if (m->use_deep && !m->tables.empty()) {
         if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
-        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->max_nnz);
+        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_urow[0], m->max_nnz);
         m->launches++;
         if ((rc = exclusive_scan_i32(m, m->d_choff[0], m->max_nnz, m->d_nchunks[0]))) return rc;
         mark(m, "emb_group");
     }
     if (m->use_wide) {
         if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
-        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->max_nnz);
+        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_urow[1], m->max_nnz);
         m->launches++;
         if ((rc = exclusive_scan_i32(m, m->d_choff[1], m->max_nnz, m->d_nchunks[1]))) return rc;
         mark(m, "wide_group");

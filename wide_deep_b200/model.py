@@ -140,18 +140,19 @@ class WideDeepModel(object):
         check(self._lib.wd_forward(self._h, ctypes.byref(c), logits.ctypes.data, ctypes.byref(loss)))
         return logits, (loss.value if batch.label is not None else None)
 
-    def step_backward(self, batch: Batch | None):
+    def step_backward(self, batch: Batch | None, want_loss=True):
         loss = ctypes.c_float()
         c = batch.to_c() if batch is not None else None
         if batch is not None:
             self._rows_hint = batch.batch_size
-        check(self._lib.wd_step_backward(self._h, ctypes.byref(c) if c is not None else None, ctypes.byref(loss)))
-        return loss.value
+        check(self._lib.wd_step_backward(self._h, ctypes.byref(c) if c is not None else None,
+                                         ctypes.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
 
-    def step_backward_slot(self, slot):
+    def step_backward_slot(self, slot, want_loss=True):
         loss = ctypes.c_float()
-        check(self._lib.wd_step_backward_slot(self._h, int(slot), ctypes.byref(loss)))
-        return loss.value
+        check(self._lib.wd_step_backward_slot(self._h, int(slot), ctypes.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
 
     def step_apply(self):
         check(self._lib.wd_step_apply(self._h))
@@ -161,12 +162,13 @@ class WideDeepModel(object):
         """(device pointer, float count) of the dense gradient arena after step_backward."""
         return int(self._lib.wd_dense_grad_ptr(self._h) or 0), int(self._lib.wd_dense_grad_count(self._h))
 
-    def sparse_grads(self, which):
+    def sparse_grads(self, which, want_count=True):
+        """(rows ptr, grads ptr, n or None, width, capacity).  want_count=False does not synchronise."""
         rows, grads = ctypes.c_void_p(), ctypes.c_void_p()
         n, cap, width = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
-        check(self._lib.wd_sparse_grads(self._h, which, ctypes.byref(rows), ctypes.byref(grads), ctypes.byref(n),
-                                        ctypes.byref(width), ctypes.byref(cap)))
-        return rows.value, grads.value, n.value, width.value, cap.value
+        check(self._lib.wd_sparse_grads(self._h, which, ctypes.byref(rows), ctypes.byref(grads),
+                                        ctypes.byref(n) if want_count else None, ctypes.byref(width), ctypes.byref(cap)))
+        return rows.value, grads.value, (n.value if want_count else None), width.value, cap.value
 
     def sparse_set(self, which, rows_ptr, grads_ptr, n):
         check(self._lib.wd_sparse_set(self._h, which, ctypes.c_void_p(rows_ptr), ctypes.c_void_p(grads_ptr), int(n)))

@@ -84,9 +84,14 @@ def wrap_device(ptr, shape, dtype, device):
 
 
 class DataParallelTrainer(object):
-    """Drives one WideDeepModel per rank.  ``step(batch)`` = wd_step_backward -> collectives -> wd_step_apply."""
+    """Drives one WideDeepModel per rank.  ``step(batch)`` = wd_step_backward -> collectives -> wd_step_apply.
 
-    def __init__(self, model, group=None):
+    ``fixed_rows`` = (K_emb, K_wide): static per-rank upper bounds on the number of touched rows per step (e.g.
+    batch x embedding columns).  With them the exchange is fully asynchronous: the library pads its row lists with
+    INVALID_ROW up to capacity, every rank all-gathers exactly K rows, and no count ever travels to the host.  Without
+    them the trainer falls back to the count-based (synchronising) exchange."""
+
+    def __init__(self, model, group=None, fixed_rows=None):
         self.model, self.group = model, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device("cuda", model.device)
@@ -94,6 +99,18 @@ class DataParallelTrainer(object):
         ptr, n = model.dense_grad()
         self.dense_grad = wrap_device(ptr, (n,), torch.float32, self.device) if n else None
         self.lists = [w for w, on in ((0, model.plan.use_deep and len(model.plan.tables) > 0), (1, model.plan.use_wide)) if on]
+        self.fixed = None
+        if fixed_rows is not None:
+            self.fixed = {}
+            for which in self.lists:
+                rows_ptr, grads_ptr, _, width, cap = model.sparse_grads(which, want_count=False)
+                K = int(min(fixed_rows[which], cap))
+                self.fixed[which] = dict(
+                    K=K,
+                    rows=wrap_device(rows_ptr, (cap,), torch.int32, self.device)[:K],
+                    grads=wrap_device(grads_ptr, (cap, width), torch.float32, self.device)[:K],
+                    all_r=torch.empty((self.world * K,), dtype=torch.int32, device=self.device),
+                    all_g=torch.empty((self.world * K, width), dtype=torch.float32, device=self.device))
 
     def _collectives(self):
         m = self.model
@@ -101,6 +118,12 @@ class DataParallelTrainer(object):
             if self.dense_grad is not None:
                 dist.all_reduce(self.dense_grad, op=dist.ReduceOp.SUM, group=self.group)
             for which in self.lists:
+                if self.fixed is not None:
+                    f = self.fixed[which]
+                    dist.all_gather_into_tensor(f["all_r"], f["rows"], group=self.group)
+                    dist.all_gather_into_tensor(f["all_g"], f["grads"], group=self.group)
+                    m.sparse_set(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), f["all_r"].numel())
+                    continue
                 rows_ptr, grads_ptr, n, width, cap = m.sparse_grads(which)
                 rows = wrap_device(rows_ptr, (cap,), torch.int32, self.device)
                 grads = wrap_device(grads_ptr, (cap, width), torch.float32, self.device)
@@ -110,15 +133,15 @@ class DataParallelTrainer(object):
                 self._keep = (all_r, all_g)        # alive until the apply kernels have run
                 m.sync()
 
-    def step(self, batch):
-        loss = self.model.step_backward(batch)
+    def step(self, batch, want_loss=True):
+        loss = self.model.step_backward(batch, want_loss=want_loss and self.fixed is None)
         self._collectives()
         self.model.step_apply()
         return loss
 
-    def step_slot(self, slot):
+    def step_slot(self, slot, want_loss=True):
         m = self.model
-        loss = m.step_backward_slot(slot)
+        loss = m.step_backward_slot(slot, want_loss=want_loss and self.fixed is None)
         self._collectives()
         m.step_apply()
         return loss
