@@ -305,3 +305,81 @@ def test_criteo_shape_scaled_down():
     logits, _ = pm.forward(Batch(B, keys.reshape(-1), None, dense, label))
     _, cache = om.forward(raw)
     np.testing.assert_array_less(np.abs(logits - cache["logits"]), 5 * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+
+
+def test_long_multihot_bags_resdnn():
+    """BASELINE.json configs[3] in miniature: one hashed multihot slot (Poisson(30) ids per row, clipped to [1, 96]),
+    64-wide embedding, ResDnn 4 x 64 ('resnet' connections).  Exercises the full-warp gather with the warp-shuffle
+    segmented mean, duplicate ids inside a bag, and the chunked hot-row gradient sums."""
+    from oracle import hashing as OH
+    from wide_deep_b200.model import Batch
+    fc = OrderedDict()
+    fc["tags"] = dict(type="category", transform="hash_bucket", parameter=5000)
+    fc["x"] = dict(type="continuous", transform="standard", parameter=dict(normalization=[0.0, 1.0], boundaries=[-1, 0, 1]))
+    model = dict(linear_optimizer="Ftrl", linear_initial_learning_rate=0.05, dnn_hidden_units=[64, 64, 64, 64],
+                 dnn_connected_mode="resnet", dnn_optimizer="Adagrad", dnn_initial_learning_rate=0.05,
+                 dnn_activation_function="relu", dnn_dropout=None, dnn_batch_normalization=1)
+    B = 256
+    om = OM.OracleModel(fc, [], model, "wide_deep", embedding_dim_override=64).init(71)
+    plan = Plan(fc, [], model, "wide_deep", max_batch=B, embedding_dim_override=64, max_nnz=B * 128, max_keys=B * 128)
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    rng = np.random.default_rng(73)
+    vocab = OH.fingerprint64_tokens(["t%d" % i for i in range(2000)])
+    for step in range(3):
+        lens = np.clip(rng.poisson(30, size=B), 1, 96)
+        offs = np.zeros(B + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(lens)
+        zipf = (rng.zipf(1.3, size=int(offs[-1])) - 1) % len(vocab)          # skewed: hot rows + duplicates inside bags
+        fps = vocab[zipf]
+        x = rng.standard_normal(B).astype(np.float32)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        raw = {"tags": (offs, fps), "x": x}
+        batch = Batch(B, fps, offs.astype(np.int32), x.reshape(B, 1), label)
+        if step == 0:
+            logits, _ = pm.forward(batch)
+            _, cache = om.forward(raw)
+            np.testing.assert_array_less(np.abs(logits - cache["logits"]), RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+            X = pm.deep_input(B)
+            lo, po, w = plan.deep_layout["tags_embedding"]
+            np.testing.assert_allclose(X[:, po:po + w], cache["X"][:, lo:lo + w], rtol=1e-5, atol=1e-6)
+        loss = pm.train_step(batch)
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    name = "dnn/input_from_feature_columns/input_layer/tags_embedding/embedding_weights"
+    got, exp = pm.get_tensor(name), om.params[name]
+    assert np.max(np.abs(got - exp)) <= 0.03 * 0.05
+
+
+def test_wide_only_hashed_crosses_ftrl():
+    """BASELINE.json configs[4] in miniature: model_type 'wide', many hashed crosses into large bucket spaces, FTRL.
+    The pure sparse-linear path: cross ids bit-exact, FTRL state (w, n, z) after three steps."""
+    fc = OrderedDict()
+    for i in range(6):
+        fc["k%d" % i] = dict(type="category", transform="hash_bucket", parameter=1000 + 17 * i)
+    cross = [(["k%d" % a, "k%d" % b], 200000 + 1000 * (a + b), 0) for a in range(6) for b in range(a + 1, 6)]      # 15 crosses
+    model = dict(linear_optimizer="tf.train.FtrlOptimizer(learning_rate=0.1,l1_regularization_strength=0.5,l2_regularization_strength=1)",
+                 linear_initial_learning_rate=0.05, dnn_hidden_units=[8], dnn_connected_mode="simple", dnn_optimizer="Adagrad",
+                 dnn_initial_learning_rate=0.05, dnn_activation_function="relu", dnn_dropout=None, dnn_batch_normalization=0)
+    B = 2048
+    rng = np.random.default_rng(81)
+    om = OM.OracleModel(fc, cross, model, "wide").init(83)
+    plan = Plan(fc, cross, model, "wide", max_batch=B, max_nnz=B * 32, max_keys=B * 8)
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    for step in range(3):
+        raw = random_raw_batch(fc, B, rng, multihot_max=1, na_rate=0.05)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        batch = to_product_batch(plan, raw, label)
+        if step == 0:
+            pm.forward(batch)
+            check_ids(om, plan, pm, raw, B)
+        loss = pm.train_step(batch)
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    for name in pm.tensor_names():
+        for slot, key in ((0, None), (1, "n"), (2, "z")):
+            got = pm.get_tensor(name, slot=slot)
+            exp = om.params[name] if key is None else om.slots[name][key]
+            sc = max(float(np.abs(exp).max()), 1e-3)
+            assert np.max(np.abs(got - exp)) <= 5e-4 * sc, "%s slot %d: %g (scale %g)" % (name, slot, np.max(np.abs(got - exp)), sc)

@@ -270,20 +270,30 @@ __global__ void logits_dgrad_kernel(int B, int K, const float* __restrict__ dlog
     }
 }
 // logits layer backward, weight part: gpart[rt][koff + k] = sum_{b in row tile} src[b,k] * dlogit[b]; bias likewise
+// block = 64 columns x 4 row groups of 32 rows (one 128-row tile); partial sums combined through shared memory
 __global__ void __launch_bounds__(256) logits_wgrad_kernel(int B, int K, const float* __restrict__ src, int ld,
                                                           const float* __restrict__ dlogit, float* __restrict__ gpart,
                                                           int64_t gstride, float* __restrict__ bias_part, int64_t bias_stride) {
-    int rt = blockIdx.y;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int b0 = rt * 128, b1 = min(B, b0 + 128);
+    __shared__ float red[4][64];
+    __shared__ float dl[128];
+    const int rt = blockIdx.y, kx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const int k = blockIdx.x * 64 + kx;
+    const int b0 = rt * 128;
+    if (threadIdx.x < 128) dl[threadIdx.x] = (b0 + threadIdx.x < B) ? dlogit[b0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    float acc = 0.f;
     if (k < K) {
-        float acc = 0.f;
-        for (int b = b0; b < b1; ++b) acc = fmaf(src[(int64_t)b * ld + k], dlogit[b], acc);
-        gpart[(int64_t)rt * gstride + k] = acc;
+        const int r0 = b0 + ry * 32;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i)
+            if (r0 + i < B) acc = fmaf(src[(int64_t)(r0 + i) * ld + k], dl[ry * 32 + i], acc);
     }
+    red[ry][kx] = acc;
+    __syncthreads();
+    if (ry == 0 && k < K) gpart[(int64_t)rt * gstride + k] = red[0][kx] + red[1][kx] + red[2][kx] + red[3][kx];
     if (bias_part && blockIdx.x == 0 && threadIdx.x == 0) {
         float s = 0.f;
-        for (int b = b0; b < b1; ++b) s += dlogit[b];
+        for (int i = 0; i < 128; ++i) s += dl[i];
         bias_part[(int64_t)rt * bias_stride] = s;
     }
 }
@@ -541,7 +551,7 @@ int mlp_backward(WdModel* m) {
             const Seg& sg = LL.segs[s];
             const float* src = src_ptr(m, tw, sg.src, false);
             int ld = src_ld(m, tw, sg.src, false);
-            dim3 g((sg.width_phys + 255) / 256, rts);
+            dim3 g((sg.width_phys + 63) / 64, rts);
             logits_wgrad_kernel<<<g, 256, 0, m->stream>>>(B, sg.width_phys, src, ld, m->d_dlogit, m->d_gpart + tk.gpart_off + sg.k_off,
                                                          tk.gstride, s == 0 ? m->d_gpart + tb.gpart_off : nullptr, tb.gstride);
             m->launches++;

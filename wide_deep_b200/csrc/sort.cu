@@ -135,15 +135,32 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __r
     }
     __syncthreads();
     for (int i = threadIdx.x; i < bins; i += RS_THREADS) {
-        int c = sh[i];
-        hist[(int64_t)tile * bins + i] = c;
-        if (c) atomicAdd(&gtot[i], c);
+        hist[(int64_t)tile * bins + i] = sh[i];
     }
 }
 
-// Stable scatter of one tile.  The tile first derives its own output bases: exclusive scan of the global bin totals
-// plus the counts of the same bin in all earlier tiles (coalesced column sums over the tile-major histogram), so no
-// serial scan kernel sits between the histogram and the scatter.
+// Column scan: one warp per bin turns the per-tile counts hist[tile][bin] into exclusive prefixes over tiles
+// (32 tiles per shuffle scan); the last lane leaves the bin total in gtot[bin].
+__global__ void __launch_bounds__(256) rs_colscan_kernel(const int32_t* __restrict__ d_n, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot) {
+    const int n = *d_n;
+    const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+    const int bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (bin >= bins) return;
+    int carry = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += 32) {
+        const int t = t0 + lane;
+        const int v = t < ntiles ? hist[(int64_t)t * bins + bin] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+        if (t < ntiles) hist[(int64_t)t * bins + bin] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) gtot[bin] = carry;
+}
+
+// Stable scatter of one tile.  Output base of (tile, bin) = exclusive scan over bins of the bin totals + the tile's
+// prefix inside the bin (both precomputed by rs_colscan_kernel).
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -157,21 +174,17 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
     if (tile >= ntiles) return;
     int* tilebase = wh + RS_WARPS * bins;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- tile bases: thread owns `per` consecutive bins
     {
-        const int per = bins / RS_THREADS > 0 ? bins / RS_THREADS : 1;       // bins is a power of two >= 2
+        const int per = bins / RS_THREADS > 0 ? bins / RS_THREADS : 1;       // bins is a power of two >= 256
         const int b0 = threadIdx.x * per;
-        int tot[4] = {0, 0, 0, 0}, prev[4] = {0, 0, 0, 0};
+        int tot[4] = {0, 0, 0, 0};
         int s = 0;
-        if (b0 < bins) {
+        if (b0 < bins)
             for (int k = 0; k < per; ++k) { tot[k] = gtot[b0 + k]; s += tot[k]; }
-            for (int t = 0; t < tile; ++t)
-                for (int k = 0; k < per; ++k) prev[k] += hist[(int64_t)t * bins + b0 + k];
-        }
         int blocktot;
         int run = block_excl_scan(s, sm, &blocktot);
         if (b0 < bins)
-            for (int k = 0; k < per; ++k) { tilebase[b0 + k] = run + prev[k]; run += tot[k]; }
+            for (int k = 0; k < per; ++k) { tilebase[b0 + k] = run + hist[(int64_t)tile * bins + b0 + k]; run += tot[k]; }
     }
     for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) wh[i] = 0;
     __syncthreads();
@@ -217,8 +230,6 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
 
 // Sort pairs (m->d_sk[which], m->d_sv[which]) of length *d_n by the low `bits` bits of the key.
 // On return the sorted pairs are in d_sk/d_sv (buffers are swapped as needed).
-// Cost note: every scatter tile sums the histograms of the tiles before it (O(tiles^2 * bins) loads in total):
-// fine up to a few million keys per step; beyond that this needs a hierarchical scan.
 int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     if (bits < 1) bits = 1;
     int passes = (bits + 9) / 10;
@@ -231,13 +242,13 @@ int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
         return WD_ESTATE;
     }
     int32_t* gtot = m->d_sort_hist + (int64_t)bins * ntiles_cap;        // [passes][bins]
-    WD_CUDA(cudaMemsetAsync(gtot, 0, (size_t)passes * bins * sizeof(int32_t), m->stream));
     for (int p = 0; p < passes; ++p) {
         int shift = p * per;
         rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
+        rs_colscan_kernel<<<(bins * 32 + 255) / 256, 256, 0, m->stream>>>(d_n, bins, m->d_sort_hist, gtot + p * bins);
         rs_scatter_kernel<<<ntiles_cap, RS_THREADS, (RS_WARPS + 1) * bins * sizeof(int), m->stream>>>(
             m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
-        m->launches += 2;
+        m->launches += 3;
         std::swap(m->d_sk[which], m->d_sk2[which]);
         std::swap(m->d_sv[which], m->d_sv2[which]);
     }

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) emb_pool_fwd_kernel(int B, int C, int nta
 // issues the loads of RMAX rounds back to back: offsets, then first ids, then first rows — every lane group keeps
 // RMAX independent 16-byte row loads in flight instead of one dependent chain at a time.
 template <int G, int RMAX>
-__global__ void __launch_bounds__(256) emb_pool_fwd_rows_kernel(int B, int C, int ntab, const TabDesc* __restrict__ desc,
+__global__ void __launch_bounds__(256, 4) emb_pool_fwd_rows_kernel(int B, int C, int ntab, const TabDesc* __restrict__ desc,
                                                                 const int32_t* __restrict__ offs, const uint32_t* __restrict__ e_emb,
                                                                 float* __restrict__ X0, int ld) {
     constexpr int GROUPS = 32 / G;
@@ -322,13 +322,12 @@ __global__ void __launch_bounds__(256) emb_pool_fwd_tma_kernel(int B, int C, int
 template <int G>
 static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
     int ntab = m->dim_ntables[di];
-    static const int gather_mode = getenv("WD_GATHER") ? atoi(getenv("WD_GATHER")) : 1;     // 0: LDG kernel, 1: TMA-staged kernel
+    static const int gather_mode = getenv("WD_GATHER") ? atoi(getenv("WD_GATHER")) : 0;     // 0: LDG kernel (default: measured faster), 1: TMA-staged kernel
     if (!widebag && gather_mode == 1 && ntab <= 32) {
         const int rowb = G * 16;
         int buf_bytes = ((ntab * rowb * 5 / 4 + 1023) / 1024) * 1024;             // 25% head-room for multihot bags (larger ones use direct loads)
         if (buf_bytes < 1024) buf_bytes = 1024;
-        int nbuf = (int)((200 * 1024) / (8 * (int64_t)buf_bytes));
-        if (nbuf > 6) nbuf = 6;
+        int nbuf = 2;                                  // two staging buffers per warp: ~3 blocks (24 warps) per SM at 5 KB buffers
         if (nbuf >= 2) {
             // tables of this width adjacent in the deep input, in descriptor order?  (host check once per model would do; cheap here)
             int contiguous = 1;
@@ -344,7 +343,7 @@ static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
                 cudaFuncSetAttribute(emb_pool_fwd_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 configured[di] = true;
             }
-            int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148);
+            int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148 * 3);
             emb_pool_fwd_tma_kernel<G><<<grid, 256, smem, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_desc[di], m->d_col_offs, m->d_e_emb,
                                                                    m->d_X0, m->d0_phys, buf_bytes, nbuf, contiguous);
             m->launches++;
@@ -352,7 +351,7 @@ static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
         }
     }
     if (!widebag) {
-        constexpr int RMAX = G >= 16 ? 4 : 8;
+        constexpr int RMAX = 4;                       // 4 rounds in flight per lane group at <= 64 registers: 32 warps per SM
         int grid = grid_for((int64_t)m->dbatch.B * 32, 256, 148 * 8);
         emb_pool_fwd_rows_kernel<G, RMAX><<<grid, 256, 0, m->stream>>>(m->dbatch.B, m->n_columns, ntab, m->d_dim_desc[di], m->d_col_offs,
                                                                         m->d_e_emb, m->d_X0, m->d0_phys);
@@ -530,18 +529,47 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
     }
 }
 
-// ugrad[u] = sum of the row's chunk partials in chunk order (multi-chunk rows only)
+// ugrad[u] = sum of the row's chunk partials (multi-chunk rows only).  Each lane checks one unique row; the (rare)
+// multi-chunk rows of a warp are combined by the whole warp: lane l adds chunks l, l+32, ... and a fixed-order shuffle
+// tree adds the 32 lane sums, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ choff,
                                                             const float* __restrict__ cpart, float* __restrict__ ugrad, int width) {
     const int nu = *d_nuniq;
-    const int64_t total = (int64_t)nu * width;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int u = (int)(t / width), q = (int)(t % width);
-        int c0 = choff[u], c1 = choff[u + 1];
-        if (c1 == c0) continue;
-        float acc = 0.f;
-        for (int c = c0; c < c1; ++c) acc += cpart[(int64_t)c * width + q];
-        ugrad[t] = acc;
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = w0 * 32; base < nu; base += nw * 32) {
+        const int64_t u = base + lane;
+        int c0 = 0, c1 = 0;
+        if (u < nu) { c0 = choff[u]; c1 = choff[u + 1]; }
+        unsigned multi = __ballot_sync(0xffffffffu, c1 > c0);
+        while (multi) {
+            const int src = __ffs(multi) - 1;
+            multi &= multi - 1;
+            const int b0 = __shfl_sync(0xffffffffu, c0, src), b1 = __shfl_sync(0xffffffffu, c1, src);
+            const int G = width >> 2;
+            if (width >= 4 && (G & (G - 1)) == 0 && G <= 32) {
+                // G lanes cover one chunk's row (float4 each), 32/G chunks in flight; fixed-order tree over the chunk groups
+                const int lq = lane % G, cg = lane / G, NG = 32 / G;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = b0 + cg; c < b1; c += NG) {
+                    const float4 v = *reinterpret_cast<const float4*>(cpart + (int64_t)c * width + lq * 4);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                for (int d = G; d < 32; d <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
+                }
+                if (cg == 0) *reinterpret_cast<float4*>(ugrad + (base + src) * width + lq * 4) = acc;
+            } else {
+                for (int q = 0; q < width; ++q) {
+                    float acc = 0.f;
+                    for (int c = b0 + lane; c < b1; c += 32) acc += cpart[(int64_t)c * width + q];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                    if (lane == 0) ugrad[(base + src) * width + q] = acc;
+                }
+            }
+        }
     }
 }
 
@@ -716,7 +744,7 @@ int sparse_backward_reduce(WdModel* m) {
             m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
         emb_grad_sum_kernel<true><<<grid_for(m->cpart_cap * 8, 256), 256, 0, m->stream>>>(m->d_nchunks[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
             m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_cpart[0], m->emb_max_dim);
-        chunk_combine_kernel<<<grid_for(m->max_nnz * (int64_t)m->emb_max_dim / 4, 256), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
+        chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
         m->launches += 3;
         mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
