@@ -72,6 +72,7 @@ SYMBOLS = {
     "wd_train_step_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "wd_set_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "wd_stream": (_vp, [_vp]),
+    "wd_stream_sparse": (_vp, [_vp, ctypes.c_int]),
     "wd_sync": (ctypes.c_int, [_vp]),
     "wd_tsv_parse": (_i64, [_vp, ctypes.c_char_p, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32]),
 }

@@ -103,6 +103,8 @@ extern "C" int wd_model_destroy(WdModel* m) {
     if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
     if (m->ev_ids) cudaEventDestroy(m->ev_ids);
     if (m->ev_sorted) cudaEventDestroy(m->ev_sorted);
+    if (m->ev_head) cudaEventDestroy(m->ev_head);
+    if (m->ev_wide) cudaEventDestroy(m->ev_wide);
     if (m->stream) cudaStreamDestroy(m->stream);
     for (size_t i = 0; i < g_extra.size(); ++i)
         if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
@@ -195,12 +197,14 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if ((rc = dev_alloc(m, &m->d_e_id, m->max_nnz))) return rc;
     if ((rc = dev_alloc(m, &m->d_nnz, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_flags, 4))) return rc;
-    if ((rc = dev_alloc(m, &m->d_sort_counter, 4))) return rc;
+    for (int k = 0; k < 2; ++k) if ((rc = dev_alloc(m, &m->d_sort_counter_s[k], 4))) return rc;
     {
         int64_t n = std::max<int64_t>(Bm * std::max(C, 1) + 2, m->max_nnz + 2);
-        int32_t* t;
-        if ((rc = dev_alloc(m, &t, n / 4096 + 8))) return rc;
-        m->d_scan_tmp = t;
+        for (int k = 0; k < 2; ++k) {
+            int32_t* t;
+            if ((rc = dev_alloc(m, &t, n / 4096 + 8))) return rc;
+            m->d_scan_tmp_s[k] = t;
+        }
     }
     if ((rc = dev_alloc(m, &m->d_logits, Bm))) return rc;
     if ((rc = dev_alloc(m, &m->d_dlogit, Bm))) return rc;
@@ -323,7 +327,15 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                 L.t_gamma = L.t_beta = -1;
                 std::vector<int> idx(4, -1);
                 if (hidden) {
-                    L.t_kernel = add_dense(L.K_phys, L.N_phys, m->wgrad_splits, 0, (int64_t)L.K_phys * L.N_phys, true);
+                    // split-K factor of the weight gradient: enough (tile x split) work items to fill one wave of SMs,
+                    // each split still at least 512 batch rows long
+                    {
+                        const int tiles = ((L.K_phys + 127) / 128) * ((L.N_phys + 127) / 128);
+                        int sp = m->wgrad_splits;
+                        while (sp < 32 && tiles * sp * 2 <= 148 && m->max_batch_pad / (sp * 2) >= 512) sp *= 2;   // double only while one wave still holds it
+                        L.wgrad_splits = sp;
+                    }
+                    L.t_kernel = add_dense(L.K_phys, L.N_phys, L.wgrad_splits, 0, (int64_t)L.K_phys * L.N_phys, true);
                     L.t_bias = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
                     if (m->batch_norm) {
                         L.t_gamma = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
@@ -385,7 +397,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         m->sparse_cap[w] = m->max_nnz;
     }
     m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1) + 4 * 1024 + 64;
-    if ((rc = dev_alloc(m, &m->d_sort_hist, m->sort_hist_cap))) return rc;
+    for (int k = 0; k < 2; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
     if ((rc = metrics_setup())) return rc;
     if ((rc = init_sparse_tables(m, 0, 0))) return rc;           // slots = initial accumulator, weights 0
     if ((rc = init_dense_slots(m))) return rc;
@@ -413,6 +425,8 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sorted, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
     int rc = build_model(d, m, x);
     if (rc) { wd_model_destroy(m); return rc; }
@@ -664,9 +678,9 @@ static int group_async(WdModel* m) {
     WD_CUDA(cudaEventRecord(m->ev_ids, m->stream));
     WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_ids, 0));
     cudaStream_t main_stream = m->stream;
-    m->stream = m->stream2;
+    m->stream = m->stream2; m->scratch_sel = 1;
     int rc = sparse_group(m);
-    m->stream = main_stream;
+    m->stream = main_stream; m->scratch_sel = 0;
     if (rc) return rc;
     WD_CUDA(cudaEventRecord(m->ev_sorted, m->stream2));
     m->sorted_pending = true;
@@ -683,11 +697,24 @@ static int forward_core(WdModel* m, bool train) {
     mark(m, "mlp_other");
     if ((rc = loss_forward(m, train))) return rc;
     mark(m, "head");
+    if (train && m->sorted_pending) WD_CUDA(cudaEventRecord(m->ev_head, m->stream));
     return WD_OK;
 }
 
 static int backward_core(WdModel* m) {
     int rc;
+    m->wide_on_side = false;
+    if (m->sorted_pending && m->use_wide) {
+        // the wide gradient sums need only dlogit: run them on the side stream under the towers' backward
+        WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_head, 0));
+        cudaStream_t main_stream = m->stream;
+        m->stream = m->stream2; m->scratch_sel = 1;
+        rc = sparse_reduce_wide(m);
+        m->stream = main_stream; m->scratch_sel = 0;
+        if (rc) return rc;
+        WD_CUDA(cudaEventRecord(m->ev_wide, m->stream2));
+        m->wide_on_side = true;
+    }
     if ((rc = mlp_backward(m))) return rc;
     mark(m, "mlp_other");
     if ((rc = wide_bias_grad(m))) return rc;
@@ -697,13 +724,18 @@ static int backward_core(WdModel* m) {
         WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sorted, 0));
         m->sorted_pending = false;
     } else if ((rc = sparse_group(m))) return rc;
-    if ((rc = sparse_backward_reduce(m))) return rc;
+    if ((rc = sparse_reduce_emb(m))) return rc;
+    if (!m->wide_on_side && (rc = sparse_reduce_wide(m))) return rc;
     m->grads_pending = true;
     return WD_OK;
 }
 
 static int apply_core(WdModel* m) {
     int rc;
+    if (m->wide_on_side) {                                  // wide list (and, in data-parallel runs, its merge) was produced on the side stream
+        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_wide, 0));
+        m->wide_on_side = false;
+    }
     if ((rc = sparse_apply(m))) return rc;
     mark(m, "sparse_apply");
     if ((rc = dense_apply(m))) return rc;
@@ -805,6 +837,7 @@ extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads,
     if (n) {                                   // the count needs a sync; pass n = NULL for the asynchronous fixed-size exchange
         int32_t nu = 0;
         WD_CUDA(cudaStreamSynchronize(m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream2));
         WD_CUDA(cudaMemcpy(&nu, m->d_nuniq[which], 4, cudaMemcpyDeviceToHost));
         *n = nu;
     }
@@ -819,9 +852,16 @@ extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const 
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    if ((rc = merge_sparse(m, which, rows_dev, grads_dev, n))) return rc;
-    // hot-row chunk layout is not used by the apply kernels; nothing else to rebuild
-    return WD_OK;
+    if (which == 1 && m->wide_on_side) {
+        cudaStream_t main_stream = m->stream;
+        m->stream = m->stream2; m->scratch_sel = 1;
+        rc = merge_sparse(m, which, rows_dev, grads_dev, n);
+        m->stream = main_stream; m->scratch_sel = 0;
+        if (rc) return rc;
+        WD_CUDA(cudaEventRecord(m->ev_wide, m->stream2));
+        return WD_OK;
+    }
+    return merge_sparse(m, which, rows_dev, grads_dev, n);
 }
 
 // ------------------------------------------------------------------------------------------------- eval
@@ -905,6 +945,10 @@ extern "C" int wd_set_profile(WdModel* m, int enable) {
     return WD_OK;
 }
 extern "C" void* wd_stream(WdModel* m) { return m ? (void*)m->stream : nullptr; }
+extern "C" void* wd_stream_sparse(WdModel* m, int which) {
+    if (!m) return nullptr;
+    return (which == 1 && m->wide_on_side) ? (void*)m->stream2 : (void*)m->stream;
+}
 extern "C" int wd_sync(WdModel* m) {
     int rc = check_ready(m);
     if (rc) return rc;

@@ -100,6 +100,7 @@ struct Layer {
     int K, K_phys;           // logical / physical input width
     int N, N_phys;           // logical / physical output width (1 for logits)
     int t_kernel, t_bias, t_gamma, t_beta;   // indices into Model::dense (-1 if absent)
+    int wgrad_splits;        // split-K factor of this layer's weight gradient (= gparts of its kernel tensor)
     // activations (hidden layers only), all [max_batch_pad, N_phys] unless noted
     float* A;                // post-activation (pre-BN); == H when no batch norm
     float* H;                // layer output
@@ -155,8 +156,9 @@ struct WdModel {
 
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // side stream: the id-only part of the sparse backward overlaps the towers
-    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr;
-    bool sorted_pending = false;
+    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr, ev_head = nullptr, ev_wide = nullptr;
+    bool sorted_pending = false;             // side stream holds this step's row grouping
+    bool wide_on_side = false;               // wide gradient list (and its merge) lives on the side stream until apply
     wd::DevPlan dplan{};
     std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
     int64_t bytes_allocated = 0;
@@ -181,7 +183,8 @@ struct WdModel {
     int32_t* d_e_id = nullptr;               // [max_nnz] column-local id (debug / parity)
     int32_t* d_nnz = nullptr;                // device scalar: entries this step
     int32_t* d_flags = nullptr;              // device error flags [4]
-    void* d_scan_tmp = nullptr;
+    void* d_scan_tmp_s[2] = {nullptr, nullptr};   // scan / sort scratch, one set per stream (0 main, 1 side)
+    int scratch_sel = 0;
 
     // ---- wide part: record {w, n, z, 0} per row
     float4* d_wide = nullptr;
@@ -223,9 +226,9 @@ struct WdModel {
     // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
     uint32_t *d_sk[2] = {nullptr, nullptr}, *d_sv[2] = {nullptr, nullptr};     // ping-pong keys / values
     uint32_t *d_sk2[2] = {nullptr, nullptr}, *d_sv2[2] = {nullptr, nullptr};
-    int32_t* d_sort_hist = nullptr;
+    int32_t* d_sort_hist_s[2] = {nullptr, nullptr};
     int64_t sort_hist_cap = 0;
-    int32_t* d_sort_counter = nullptr;
+    int32_t* d_sort_counter_s[2] = {nullptr, nullptr};
     uint32_t* d_urow[2] = {nullptr, nullptr};   // unique rows
     int32_t* d_ustart[2] = {nullptr, nullptr};  // segment starts in the sorted list (+1 sentinel)
     float* d_ugrad[2] = {nullptr, nullptr};     // [cap, width]
@@ -257,7 +260,8 @@ namespace wd {
 int ids_prepare(WdModel* m);                                     // ids.cu
 int sparse_forward(WdModel* m);                                  // sparse.cu: wide logit + embedding pooling + numerics
 int sparse_group(WdModel* m);                                    // sparse.cu: sort (row, occurrence) pairs, unique rows, chunks
-int sparse_backward_reduce(WdModel* m);                          // sparse.cu: per-row gradient sums
+int sparse_reduce_emb(WdModel* m);                               // sparse.cu: per-row gradient sums (needs dX0)
+int sparse_reduce_wide(WdModel* m);                              // sparse.cu: per-row gradient sums (needs dlogit only)
 int sparse_apply(WdModel* m);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
 int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
 int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0

@@ -585,8 +585,8 @@ int mlp_backward(WdModel* m) {
                 A.n = 1; A.ptr[0] = src_ptr(m, tw, sg.src, true); A.ld[0] = m->ldt; A.k[0] = Bk;
                 Epi ep{};
                 ep.C = m->d_gpart + tkn.gpart_off + (int64_t)sg.k_off * L.N_phys; ep.ldc = L.N_phys; ep.split_stride = tkn.gstride;
-                int ks = ((Bk + m->wgrad_splits - 1) / m->wgrad_splits + 15) / 16 * 16;
-                int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, m->ldt, sg.width_phys, L.N_phys, ep, m->wgrad_splits, ks);
+                int ks = ((Bk + L.wgrad_splits - 1) / L.wgrad_splits + 31) / 32 * 32;
+                int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, m->ldt, sg.width_phys, L.N_phys, ep, L.wgrad_splits, ks);
                 if (rc) return rc;
                 // data gradient into the source
                 if (sg.src < 0 && !need_dx0) continue;

@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(int32_t* data, i
 int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out) {
     int nchunks = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     if (nchunks < 1) nchunks = 1;
-    int32_t* sums = (int32_t*)m->d_scan_tmp;
-    scan_chunks_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(data, n, sums, m->d_sort_counter);
+    int32_t* sums = (int32_t*)m->d_scan_tmp_s[m->scratch_sel];
+    scan_chunks_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(data, n, sums, m->d_sort_counter_s[m->scratch_sel]);
     scan_add_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(data, n, sums, nchunks, total_out);
     m->launches += 2;
     WD_CUDA(cudaGetLastError());
@@ -241,13 +241,14 @@ int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
         set_error("radix sort histogram capacity too small");
         return WD_ESTATE;
     }
-    int32_t* gtot = m->d_sort_hist + (int64_t)bins * ntiles_cap;        // [passes][bins]
+    int32_t* hist = m->d_sort_hist_s[m->scratch_sel];
+    int32_t* gtot = hist + (int64_t)bins * ntiles_cap;                  // [passes][bins]
     for (int p = 0; p < passes; ++p) {
         int shift = p * per;
-        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
-        rs_colscan_kernel<<<(bins * 32 + 255) / 256, 256, 0, m->stream>>>(d_n, bins, m->d_sort_hist, gtot + p * bins);
+        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
+        rs_colscan_kernel<<<(bins * 32 + 255) / 256, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
         rs_scatter_kernel<<<ntiles_cap, RS_THREADS, (RS_WARPS + 1) * bins * sizeof(int), m->stream>>>(
-            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, m->d_sort_hist, gtot + p * bins);
+            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
         m->launches += 3;
         std::swap(m->d_sk[which], m->d_sk2[which]);
         std::swap(m->d_sv[which], m->d_sv2[which]);

@@ -735,8 +735,8 @@ int sparse_group(WdModel* m) {
     return WD_OK;
 }
 
-// Stage 2: per-row gradient sums for both tables; leaves (urow, ugrad, nuniq) ready for exchange / apply
-int sparse_backward_reduce(WdModel* m) {
+// Stage 2: per-row gradient sums; leaves (urow, ugrad, nuniq) ready for exchange / apply
+int sparse_reduce_emb(WdModel* m) {
     const int g = grid_for(m->max_nnz, 256);
     if (m->use_deep && !m->tables.empty()) {
         int ge = grid_for(m->max_nnz * 8, 256);
@@ -749,6 +749,12 @@ int sparse_backward_reduce(WdModel* m) {
         mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
     }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+int sparse_reduce_wide(WdModel* m) {
+    const int g = grid_for(m->max_nnz, 256);
     if (m->use_wide) {
         wide_grad_sum_kernel<false><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
                                                               m->n_columns, m->d_dlogit, m->d_ugrad[1]);

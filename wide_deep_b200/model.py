@@ -240,5 +240,8 @@ class WideDeepModel(object):
     def stream(self):
         return int(self._lib.wd_stream(self._h) or 0)
 
+    def stream_sparse(self, which):
+        return int(self._lib.wd_stream_sparse(self._h, int(which)) or 0)
+
     def sync(self):
         check(self._lib.wd_sync(self._h))

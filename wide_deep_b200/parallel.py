@@ -99,6 +99,7 @@ class DataParallelTrainer(object):
         ptr, n = model.dense_grad()
         self.dense_grad = wrap_device(ptr, (n,), torch.float32, self.device) if n else None
         self.lists = [w for w, on in ((0, model.plan.use_deep and len(model.plan.tables) > 0), (1, model.plan.use_wide)) if on]
+        self._ext = {}
         self.fixed = None
         if fixed_rows is not None:
             self.fixed = {}
@@ -114,16 +115,26 @@ class DataParallelTrainer(object):
 
     def _collectives(self):
         m = self.model
+        if self.fixed is not None:
+            # asynchronous path: each list is exchanged on the stream that produced it — the wide list is ready while
+            # the towers' backward still runs on the main stream, so its all-gather + merge hide behind that work
+            for which in sorted(self.lists, reverse=True):              # wide (1) first
+                f = self.fixed[which]
+                sptr = m.stream_sparse(which)
+                if sptr not in self._ext:
+                    self._ext[sptr] = torch.cuda.ExternalStream(sptr, device=self.device)
+                with torch.cuda.stream(self._ext[sptr]):
+                    dist.all_gather_into_tensor(f["all_r"], f["rows"], group=self.group)
+                    dist.all_gather_into_tensor(f["all_g"], f["grads"], group=self.group)
+                    m.sparse_set(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), f["all_r"].numel())
+            with torch.cuda.stream(self.stream):
+                if self.dense_grad is not None:
+                    dist.all_reduce(self.dense_grad, op=dist.ReduceOp.SUM, group=self.group)
+            return
         with torch.cuda.stream(self.stream):
             if self.dense_grad is not None:
                 dist.all_reduce(self.dense_grad, op=dist.ReduceOp.SUM, group=self.group)
             for which in self.lists:
-                if self.fixed is not None:
-                    f = self.fixed[which]
-                    dist.all_gather_into_tensor(f["all_r"], f["rows"], group=self.group)
-                    dist.all_gather_into_tensor(f["all_g"], f["grads"], group=self.group)
-                    m.sparse_set(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), f["all_r"].numel())
-                    continue
                 rows_ptr, grads_ptr, n, width, cap = m.sparse_grads(which)
                 rows = wrap_device(rows_ptr, (cap,), torch.int32, self.device)
                 grads = wrap_device(grads_ptr, (cap, width), torch.float32, self.device)
