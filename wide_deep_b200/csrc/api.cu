@@ -6,6 +6,7 @@
 // optimizers.  Nothing here falls back to the CPU: without a CUDA device every entry point returns
 // WD_ENODEVICE.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -97,6 +98,7 @@ extern "C" int wd_model_destroy(WdModel* m) {
     if (!m) return WD_OK;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto& sl : m->slots) if (sl.graph) cudaGraphExecDestroy(sl.graph);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
     for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
@@ -428,6 +430,7 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
+    m->graphs_enabled = getenv("WD_NO_GRAPH") == nullptr;
     int rc = build_model(d, m, x);
     if (rc) { wd_model_destroy(m); return rc; }
     *out = m;
@@ -609,6 +612,7 @@ static int select_slot(WdModel* m, int s) {
         m->slots.push_back(b);
     }
     BatchSlot& b = m->slots[s];
+    m->cur_slot = s;
     m->d_cat_offsets = b.off; m->d_cat_keys = b.keys; m->d_dense = b.dense; m->d_label = b.label; m->d_weight = b.weight;
     if (b.filled) { m->dbatch = b.view; m->batch_has_label = b.has_label; }
     return WD_OK;
@@ -744,12 +748,59 @@ static int apply_core(WdModel* m) {
     return WD_OK;
 }
 
+static int train_eager(WdModel* m) {
+    int rc;
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    return apply_core(m);
+}
+
+static bool same_view(const DevBatch& a, const DevBatch& b) {
+    return a.B == b.B && a.cat_offsets == b.cat_offsets && a.cat_keys == b.cat_keys && a.dense == b.dense && a.label == b.label && a.weight == b.weight;
+}
+
+// One whole train step on the current slot.  After two eager steps the step (both streams, ~65 kernels, no host sync)
+// is captured once into a CUDA graph per batch slot and replayed: launch gaps between the many small kernels
+// disappear and the host cost of a step becomes one cudaGraphLaunch.
 static int train_current(WdModel* m, float* loss_out) {
     int rc;
     if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
-    if ((rc = forward_core(m, true))) return rc;
-    if ((rc = backward_core(m))) return rc;
-    if ((rc = apply_core(m))) return rc;
+    BatchSlot& sl = m->slots[m->cur_slot];
+    const bool can_graph = m->graphs_enabled && !m->timer.enabled;
+    if (can_graph && sl.graph && same_view(sl.graph_view, m->dbatch)) {
+        WD_CUDA(cudaGraphLaunch(sl.graph, m->stream));
+        m->launches += sl.graph_launches;
+        m->grads_pending = false;
+    } else if (can_graph && sl.eager_steps >= 2) {
+        if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }
+        const int64_t l0 = m->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = train_eager(m);
+            cudaError_t e2 = cudaStreamEndCapture(m->stream, &g);
+            if (rc == WD_OK && e2 == cudaSuccess && g) e = cudaGraphInstantiate(&sl.graph, g, 0);
+            else e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
+            if (g) cudaGraphDestroy(g);
+        }
+        if (e != cudaSuccess || !sl.graph) {            // capture not possible here: stay eager for good
+            cudaGetLastError();
+            m->graphs_enabled = false;
+            sl.graph = nullptr;
+            m->sorted_pending = false; m->wide_on_side = false;
+            if ((rc = train_eager(m))) return rc;
+        } else {
+            sl.graph_view = m->dbatch;
+            sl.graph_launches = m->launches - l0;
+            m->launches = l0;
+            m->sorted_pending = false; m->wide_on_side = false; m->grads_pending = false;
+            WD_CUDA(cudaGraphLaunch(sl.graph, m->stream));
+            m->launches += sl.graph_launches;
+        }
+    } else {
+        if ((rc = train_eager(m))) return rc;
+        sl.eager_steps++;
+    }
     if (loss_out) return finish_step(m, loss_out, nullptr);
     return WD_OK;
 }

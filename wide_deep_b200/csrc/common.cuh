@@ -133,6 +133,11 @@ struct BatchSlot {           // one device-resident batch (ring used by benchmar
     float *dense = nullptr, *label = nullptr, *weight = nullptr;
     DevBatch view{};
     bool has_label = false, filled = false;
+    // CUDA graph of one whole train step on this slot (captured after a few eager steps; keyed by the batch view)
+    cudaGraphExec_t graph = nullptr;
+    DevBatch graph_view{};
+    int64_t graph_launches = 0;
+    int eager_steps = 0;
 };
 
 }  // namespace wd
@@ -248,6 +253,8 @@ struct WdModel {
     int64_t eval_batches = 0;
 
     int64_t launches = 0;
+    int cur_slot = 0;
+    bool graphs_enabled = true;              // WD_NO_GRAPH=1 disables step graphs
     int cur_layer = 0;                       // layer being launched (names the profiling marks)
     wd::PhaseTimer timer;
     std::vector<wd::BatchSlot> slots;        // slot 0 aliases the d_cat_* buffers above

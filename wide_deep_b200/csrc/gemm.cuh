@@ -53,7 +53,6 @@ struct Epi {
     int n_logical, act, bn;
     int m_valid;                       // rows >= m_valid are written as zero (transposed padding)
     int64_t split_stride;              // WGRAD: floats between split partials
-    int dbg;                           // timing experiments only (WD_EPI_DBG): 1 skip HT, 2 skip A_out, 4 skip param loads
 };
 
 

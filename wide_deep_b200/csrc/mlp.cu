@@ -493,7 +493,6 @@ int mlp_forward(WdModel* m, bool train) {
             ep.gamma = L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr;
             ep.beta = L.t_beta >= 0 ? m->d_P + m->dense[L.t_beta].off : nullptr;
             ep.n_logical = L.N; ep.act = m->activation; ep.bn = m->batch_norm; ep.m_valid = B;
-            { static const int dbg = getenv("WD_EPI_DBG") ? atoi(getenv("WD_EPI_DBG")) : 0; ep.dbg = dbg; }
             const int64_t wo = m->dense[L.t_kernel].wt_off;
             const float* Wt = m->d_Wt + wo;
             int rc = run_gemm(m, EPI_FWD, A, Wt, L.K_phys, B, L.N_phys, ep, 1, 0, m->d_Wsplit + 2 * m->wt_count + wo, m->d_Wsplit + 3 * m->wt_count + wo);
