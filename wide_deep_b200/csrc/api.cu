@@ -107,6 +107,8 @@ extern "C" int wd_model_destroy(WdModel* m) {
     if (m->ev_sorted) cudaEventDestroy(m->ev_sorted);
     if (m->ev_head) cudaEventDestroy(m->ev_head);
     if (m->ev_wide) cudaEventDestroy(m->ev_wide);
+    if (m->ev_dx0) cudaEventDestroy(m->ev_dx0);
+    if (m->ev_sparse) cudaEventDestroy(m->ev_sparse);
     if (m->stream) cudaStreamDestroy(m->stream);
     for (size_t i = 0; i < g_extra.size(); ++i)
         if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
@@ -429,6 +431,8 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sorted, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_dx0, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sparse, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
     m->graphs_enabled = getenv("WD_NO_GRAPH") == nullptr;
     int rc = build_model(d, m, x);
@@ -705,30 +709,49 @@ static int forward_core(WdModel* m, bool train) {
     return WD_OK;
 }
 
+// run `fn` on the side stream with the side scratch set
+template <typename F>
+static int on_side(WdModel* m, F fn) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->stream2; m->scratch_sel = 1;
+    int rc = fn();
+    m->stream = main_stream; m->scratch_sel = 0;
+    return rc;
+}
+
+// Backward.  Main stream: towers (dgrad before wgrad per layer), dense gradient reduction.  Side stream (when the
+// grouping already lives there): wide gradient sums as soon as dlogit exists, embedding gradient sums as soon as dX0
+// exists — i.e. under the remaining weight-gradient GEMMs.
 static int backward_core(WdModel* m) {
     int rc;
-    m->wide_on_side = false;
-    if (m->sorted_pending && m->use_wide) {
-        // the wide gradient sums need only dlogit: run them on the side stream under the towers' backward
+    m->wide_on_side = m->emb_on_side = false;
+    const bool side = m->sorted_pending;
+    const bool has_emb = m->use_deep && !m->tables.empty();
+    if (side && m->use_wide) {
         WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_head, 0));
-        cudaStream_t main_stream = m->stream;
-        m->stream = m->stream2; m->scratch_sel = 1;
-        rc = sparse_reduce_wide(m);
-        m->stream = main_stream; m->scratch_sel = 0;
-        if (rc) return rc;
+        if ((rc = on_side(m, [&] { return sparse_reduce_wide(m); }))) return rc;
         WD_CUDA(cudaEventRecord(m->ev_wide, m->stream2));
         m->wide_on_side = true;
     }
+    m->record_dx0 = side && has_emb;
+    m->dx0_recorded = false;
     if ((rc = mlp_backward(m))) return rc;
+    m->record_dx0 = false;
     mark(m, "mlp_other");
+    if (side && has_emb && m->dx0_recorded) {
+        WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_dx0, 0));
+        if ((rc = on_side(m, [&] { return sparse_reduce_emb(m); }))) return rc;
+        WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
+        m->emb_on_side = true;
+    }
     if ((rc = wide_bias_grad(m))) return rc;
     if ((rc = dense_reduce_grads(m))) return rc;
     mark(m, "dense_reduce");
-    if (m->sorted_pending) {
-        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sorted, 0));
+    if (side) {
+        if (!m->emb_on_side) WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sorted, 0));
         m->sorted_pending = false;
     } else if ((rc = sparse_group(m))) return rc;
-    if ((rc = sparse_reduce_emb(m))) return rc;
+    if (!m->emb_on_side && (rc = sparse_reduce_emb(m))) return rc;
     if (!m->wide_on_side && (rc = sparse_reduce_wide(m))) return rc;
     m->grads_pending = true;
     return WD_OK;
@@ -736,9 +759,26 @@ static int backward_core(WdModel* m) {
 
 static int apply_core(WdModel* m) {
     int rc;
-    if (m->wide_on_side) {                                  // wide list (and, in data-parallel runs, its merge) was produced on the side stream
-        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_wide, 0));
-        m->wide_on_side = false;
+    if (m->emb_on_side || m->wide_on_side) {
+        // every sparse list that lives on the side stream is applied there (after its merge in data-parallel runs);
+        // the dense optimizer runs on the main stream meanwhile and the streams join at the end of the step
+        if (!m->emb_on_side) WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_sorted, 0));
+        if (m->emb_on_side != (m->use_deep && !m->tables.empty()) || m->wide_on_side != m->use_wide) {
+            // mixed placement: bring everything to the main stream
+            WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
+            WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sparse, 0));
+            if ((rc = sparse_apply(m))) return rc;
+        } else {
+            if ((rc = on_side(m, [&] { return sparse_apply(m); }))) return rc;
+            WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
+        }
+        mark(m, "sparse_apply");
+        if ((rc = dense_apply(m))) return rc;
+        mark(m, "dense_apply");
+        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sparse, 0));
+        m->emb_on_side = m->wide_on_side = false;
+        m->grads_pending = false;
+        return WD_OK;
     }
     if ((rc = sparse_apply(m))) return rc;
     mark(m, "sparse_apply");
@@ -787,13 +827,13 @@ static int train_current(WdModel* m, float* loss_out) {
             cudaGetLastError();
             m->graphs_enabled = false;
             sl.graph = nullptr;
-            m->sorted_pending = false; m->wide_on_side = false;
+            m->sorted_pending = false; m->wide_on_side = m->emb_on_side = false;
             if ((rc = train_eager(m))) return rc;
         } else {
             sl.graph_view = m->dbatch;
             sl.graph_launches = m->launches - l0;
             m->launches = l0;
-            m->sorted_pending = false; m->wide_on_side = false; m->grads_pending = false;
+            m->sorted_pending = false; m->wide_on_side = m->emb_on_side = false; m->grads_pending = false;
             WD_CUDA(cudaGraphLaunch(sl.graph, m->stream));
             m->launches += sl.graph_launches;
         }
@@ -903,15 +943,8 @@ extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const 
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    if (which == 1 && m->wide_on_side) {
-        cudaStream_t main_stream = m->stream;
-        m->stream = m->stream2; m->scratch_sel = 1;
-        rc = merge_sparse(m, which, rows_dev, grads_dev, n);
-        m->stream = main_stream; m->scratch_sel = 0;
-        if (rc) return rc;
-        WD_CUDA(cudaEventRecord(m->ev_wide, m->stream2));
-        return WD_OK;
-    }
+    if ((which == 1 && m->wide_on_side) || (which == 0 && m->emb_on_side))
+        return on_side(m, [&] { return merge_sparse(m, which, rows_dev, grads_dev, n); });
     return merge_sparse(m, which, rows_dev, grads_dev, n);
 }
 
@@ -998,7 +1031,7 @@ extern "C" int wd_set_profile(WdModel* m, int enable) {
 extern "C" void* wd_stream(WdModel* m) { return m ? (void*)m->stream : nullptr; }
 extern "C" void* wd_stream_sparse(WdModel* m, int which) {
     if (!m) return nullptr;
-    return (which == 1 && m->wide_on_side) ? (void*)m->stream2 : (void*)m->stream;
+    return ((which == 1 && m->wide_on_side) || (which == 0 && m->emb_on_side)) ? (void*)m->stream2 : (void*)m->stream;
 }
 extern "C" int wd_sync(WdModel* m) {
     int rc = check_ready(m);

@@ -161,7 +161,9 @@ struct WdModel {
 
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // side stream: the id-only part of the sparse backward overlaps the towers
-    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr, ev_head = nullptr, ev_wide = nullptr;
+    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr, ev_head = nullptr, ev_wide = nullptr, ev_dx0 = nullptr, ev_sparse = nullptr;
+    bool record_dx0 = false, dx0_recorded = false;
+    bool emb_on_side = false;                // embedding gradient list (and its merge / apply) lives on the side stream
     bool sorted_pending = false;             // side stream holds this step's row grouping
     bool wide_on_side = false;               // wide gradient list (and its merge) lives on the side stream until apply
     wd::DevPlan dplan{};

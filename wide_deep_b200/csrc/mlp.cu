@@ -577,6 +577,26 @@ int mlp_backward(WdModel* m) {
                                                        L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
                                                        m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride);
             m->launches++;
+            // data gradients first: the deep-input gradient dX0 is what the embedding backward waits for, so it is
+            // produced before this layer's weight gradients (which then overlap the sparse backward on the side stream)
+            for (int s = 0; s < L.n_in_segs; ++s) {
+                const Seg& sg = L.segs[s];
+                if (sg.src < 0 && !need_dx0) continue;
+                float* dst; int dld, acc;
+                grad_dst(sg.src, &dst, &dld, &acc);
+                GemmA A2{};
+                A2.n = 1; A2.ptr[0] = L.dZ; A2.ld[0] = L.N_phys; A2.k[0] = L.N_phys;
+                Epi e2{};
+                e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
+                const int64_t woff = tkn.wt_off + (int64_t)sg.k_off * L.N_phys;
+                int rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
+                                  m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff);
+                if (rc) return rc;
+            }
+            if (l == 0 && &tw == &m->towers.back() && need_dx0 && m->ev_dx0 && m->record_dx0) {
+                WD_CUDA(cudaEventRecord(m->ev_dx0, m->stream));        // dX0 is complete from here on
+                m->dx0_recorded = true;
+            }
             for (int s = 0; s < L.n_in_segs; ++s) {
                 const Seg& sg = L.segs[s];
                 // weight gradient of the rows fed by this segment: [width_phys, N] = srcT * dZT^T, split over the batch
@@ -586,18 +606,6 @@ int mlp_backward(WdModel* m) {
                 ep.C = m->d_gpart + tkn.gpart_off + (int64_t)sg.k_off * L.N_phys; ep.ldc = L.N_phys; ep.split_stride = tkn.gstride;
                 int ks = ((Bk + L.wgrad_splits - 1) / L.wgrad_splits + 31) / 32 * 32;
                 int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, m->ldt, sg.width_phys, L.N_phys, ep, L.wgrad_splits, ks);
-                if (rc) return rc;
-                // data gradient into the source
-                if (sg.src < 0 && !need_dx0) continue;
-                float* dst; int dld, acc;
-                grad_dst(sg.src, &dst, &dld, &acc);
-                GemmA A2{};
-                A2.n = 1; A2.ptr[0] = L.dZ; A2.ld[0] = L.N_phys; A2.k[0] = L.N_phys;
-                Epi e2{};
-                e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
-                const int64_t woff = tkn.wt_off + (int64_t)sg.k_off * L.N_phys;
-                rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
-                              m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff);
                 if (rc) return rc;
             }
         }
