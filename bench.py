@@ -44,13 +44,35 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    A step is ~1 ms, so `nvidia-smi -lms` (>= 100 ms per sample) would miss short runs: NVML is polled in-process every 2 ms from a
+    thread (same counters nvidia-smi reads); nvidia-smi is the fallback when the NVML binding is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()]
+        if ids and self.index < len(ids) and ids[self.index].strip().isdigit():
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = [float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))]
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -59,13 +81,35 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
-            if len(f) >= 8 and f[0] == str(self.index):
+            if len(f) >= 8 and f[0] == str(self._physical_index()):
                 self.rows.append(f)
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "power_w": float(np.median(self.power)) if self.power else None, "source": "nvml, 2 ms poll during both timed regions"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -78,7 +122,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvidia-smi -lms 100"}
 
 
 def workload(n_gpus, per_gpu_batch):
@@ -100,7 +144,7 @@ def config_dict(n_gpus, per_gpu_batch):
 
 
 # ------------------------------------------------------------------------------------------- reference arm
-def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32):
+def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32, budget_s=None):
     """Time the CPU restatement (oracle) on the same workload; returns (examples/s, seconds per step)."""
     import torch
     torch.set_num_threads(threads)
@@ -122,8 +166,10 @@ def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32):
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
+            if budget_s is not None and sum(times) > budget_s:
+                break
     sec = float(np.mean(times))
-    return batch_rows / sec, sec
+    return batch_rows / sec, sec, len(times)
 
 
 def run_reference(args):
@@ -132,9 +178,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     rows = 2048                     # bounded sample of the same workload (same tables, smaller batch)
-    steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
-    v, sec = oracle_examples_per_sec(rows, steps, warm, threads)
+    v, sec, steps = oracle_examples_per_sec(rows, max(1, args.steps), warm, threads, budget_s=90.0)   # K steps or 90 s of CPU work
     sample = "%d steps of %d examples (same tables/config), %d threads" % (steps, rows, threads)
     out = {"impl": "reference", "metric": "CTR examples/sec (train step)", "value": v, "unit": "examples/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -150,8 +195,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="examples per GPU per step")
     ap.add_argument("--engine", default=os.environ.get("WD_GEMM_ENGINE", "auto"))
@@ -285,7 +330,7 @@ def main():
                               "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            v, sec = oracle_examples_per_sec(2048, 3, 1, threads)
+            v, sec, _ = oracle_examples_per_sec(2048, 3, 1, threads)
             out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
                                    "sample": "3 steps of 2048 examples, same tables/config (oracle, fp32 accumulate)"}
         print(json.dumps(out))

@@ -41,7 +41,8 @@ enum { WD_ACT_RELU = 0, WD_ACT_RELU6, WD_ACT_SIGMOID, WD_ACT_TANH, WD_ACT_LEAKY_
 enum { WD_MODE_SIMPLE = 0, WD_MODE_FIRST_DENSE, WD_MODE_LAST_DENSE, WD_MODE_DENSE, WD_MODE_RESNET };
 /* GEMM engine for the MLP */
 enum { WD_GEMM_AUTO = 0, WD_GEMM_FFMA = 1, WD_GEMM_TC3X = 2 /* tcgen05 kind::tf32, 3-pass split */,
-       WD_GEMM_TC1X = 3 /* tcgen05 kind::tf32 single pass: fast, NOT within the 1e-4 parity bar */ };
+       WD_GEMM_TC1X = 3 /* tcgen05 kind::tf32 single pass: fast, NOT within the 1e-4 parity bar */,
+       WD_GEMM_BF16X3 = 4 /* tcgen05 kind::f16 on bf16 hi/lo copies written by the producing kernels, 3 passes */ };
 
 typedef struct WdOptimizer {
     int32_t kind;        /* WD_OPT_* */

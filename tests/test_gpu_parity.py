@@ -214,11 +214,13 @@ def _engine_pair(engine, hidden, mode, B, seed):
     return fc, om, plan, pm
 
 
+@pytest.mark.parametrize("engine", ["tc3x", "bf16x3"])
 @pytest.mark.parametrize("mode", ["simple", "dense", "first_dense"])
-def test_tc3x_engine_train_parity(mode):
-    """tcgen05 kind::tf32 with the 3-pass hi/lo split must meet the same 1e-4 bar as the fp32 FFMA engine."""
+def test_tc3x_engine_train_parity(mode, engine):
+    """tcgen05 with the 3-pass hi/lo split (kind::tf32 in-kernel split, or kind::f16 on bf16 hi/lo copies written by the
+    producing kernels) must meet the same 1e-4 bar as the fp32 FFMA engine."""
     B = 300
-    fc, om, plan, pm = _engine_pair("tc3x", (128, 96, 64), mode, B, seed=41)
+    fc, om, plan, pm = _engine_pair(engine, (128, 96, 64), mode, B, seed=41)
     rng = np.random.default_rng(43)
     for step in range(3):
         raw = random_raw_batch(fc, B, rng)
@@ -251,10 +253,11 @@ def test_tc1x_engine_is_close_but_not_parity_grade():
     assert err.max() < 2e-2
 
 
-def test_tc3x_wide_tiles_and_presplit_weights():
+@pytest.mark.parametrize("engine", ["tc3x", "bf16x3"])
+def test_tc3x_wide_tiles_and_presplit_weights(engine):
     """Hidden widths that are multiples of 256 take the 128x256-tile path with pre-split (hi/lo) weights."""
     B = 700
-    fc, om, plan, pm = _engine_pair("tc3x", (512, 256), "simple", B, seed=53)
+    fc, om, plan, pm = _engine_pair(engine, (512, 256), "simple", B, seed=53)
     rng = np.random.default_rng(59)
     for step in range(2):
         raw = random_raw_batch(fc, B, rng)

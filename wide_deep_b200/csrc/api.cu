@@ -300,6 +300,10 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_X0, actn))) return rc;
         if ((rc = dev_alloc(m, &m->d_X0T, actn))) return rc;
         if ((rc = dev_alloc(m, &m->d_dX0, actn))) return rc;
+        if (m->gemm_engine == WD_GEMM_BF16X3)
+            for (int part = 0; part < 2; ++part) {
+                if ((rc = dev_alloc(m, &m->d_X0s[part], actn))) return rc;
+            }
 
         // towers
         int hu_off = 0, did = 0;
@@ -329,12 +333,16 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                 L.N = hidden ? hu[l] : 1;
                 L.N_phys = hidden ? pad_to(hu[l], 32) : 1;
                 L.t_gamma = L.t_beta = -1;
+                L.h_fp32 = false;
+                for (int src : srcs[tw.n_hidden]) if (src == l) L.h_fp32 = true;      // read by the logits layer
                 std::vector<int> idx(4, -1);
                 if (hidden) {
                     // split-K factor of the weight gradient: enough (tile x split) work items to fill one wave of SMs,
                     // each split still at least 512 batch rows long
                     {
-                        const int tiles = ((L.K_phys + 127) / 128) * ((L.N_phys + 127) / 128);
+                        // (the 3xBF16 engine covers N in 256-wide tiles when N allows it)
+                        const int tn = (m->gemm_engine == WD_GEMM_BF16X3 && L.N_phys % 256 == 0) ? 256 : 128;
+                        const int tiles = ((L.K_phys + 127) / 128) * ((L.N_phys + tn - 1) / tn);
                         int sp = m->wgrad_splits;
                         while (sp < 32 && tiles * sp * 2 <= 148 && m->max_batch_pad / (sp * 2) >= 512) sp *= 2;   // double only while one wave still holds it
                         L.wgrad_splits = sp;
@@ -352,6 +360,11 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                     if ((rc = dev_alloc(m, &L.dH, n))) return rc;
                     if ((rc = dev_alloc(m, &L.dZ, n))) return rc;
                     if ((rc = dev_alloc(m, &L.dZT, n))) return rc;
+                    if (m->gemm_engine == WD_GEMM_BF16X3)
+                        for (int part = 0; part < 2; ++part) {
+                            if ((rc = dev_alloc(m, &L.Hs[part], n))) return rc;
+                            if ((rc = dev_alloc(m, &L.dZs[part], n))) return rc;
+                        }
                 } else {
                     L.t_kernel = add_dense(L.K_phys, 1, m->row_tiles, 1, L.K_phys, false);
                     L.t_bias = add_dense(1, 1, m->row_tiles, 1, 4, false);
@@ -1008,6 +1021,10 @@ extern "C" int wd_debug_hidden(WdModel* m, int tower, int layer, float* out, int
     Layer& L = m->towers[tower].layers[layer];
     int64_t n = (int64_t)m->dbatch.B * L.N_phys;
     if (cap < n) { set_error("buffer too small"); return WD_EINVAL; }
+    if (m->gemm_engine == WD_GEMM_BF16X3 && !L.h_fp32) {
+        set_error("hidden layer %d is not materialised in fp32 by the bf16x3 engine (use gemm_engine ffma / tc3x to inspect it)", layer);
+        return WD_EUNSUPPORTED;
+    }
     WD_CUDA(cudaStreamSynchronize(m->stream));
     WD_CUDA(cudaMemcpy(out, L.H, n * 4, cudaMemcpyDeviceToHost));
     return L.N_phys;

@@ -1,5 +1,6 @@
 // Shared declarations of libwd_b200: host-side model object, device plan tables, launch helpers.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -108,6 +109,9 @@ struct Layer {
     float* dH;               // gradient w.r.t. H (accumulated over consumers)
     float* dZ;               // gradient w.r.t. pre-activation
     float* dZT;              // transposed [N_phys, ldt]
+    // 3xBF16 engine: bf16 hi / lo copies of H and dZ (what the tensor-core GEMMs read; no transposed copies)
+    __nv_bfloat16 *Hs[2], *dZs[2];
+    bool h_fp32;             // 3xBF16 engine: H is also stored in fp32 (only layers the logits layer reads)
     float* colpart;          // [3][row_tiles][N_phys] partial column sums: dbias, dgamma, dbeta
 };
 
@@ -211,6 +215,7 @@ struct WdModel {
     int32_t *d_tab_dim = nullptr, *d_tab_stride = nullptr, *d_tab_x0 = nullptr, *d_tab_col = nullptr;
     int64_t* d_tab_row_base = nullptr;
     float *d_X0 = nullptr, *d_X0T = nullptr, *d_dX0 = nullptr;
+    __nv_bfloat16* d_X0s[2] = {nullptr, nullptr};   // bf16 hi / lo copy of X0 (3xBF16 engine)
     int ldt = 0;                             // leading dim of transposed activations (= max_batch_pad)
     std::vector<wd::Tower> towers;
 

@@ -1,6 +1,8 @@
 // Shared GEMM interface of the MLP engines (FFMA in mlp.cu, tcgen05 in gemm_tc.cu): operand descriptions,
 // epilogue description and the activation functions (reference python/lib/utils/model_util.py:28-59).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace wd {
@@ -42,6 +44,8 @@ struct GemmA {                         // A operand: up to kMaxSegs K-contiguous
     const float* ptr[kMaxSegs];
     int ld[kMaxSegs];
     int k[kMaxSegs];                   // multiple of 16
+    const __nv_bfloat16* hi[kMaxSegs]; // 3xBF16 engine: the same segments pre-split into bf16 hi / lo copies (same ld)
+    const __nv_bfloat16* lo[kMaxSegs];
 };
 enum { EPI_FWD = 0, EPI_STORE = 1, EPI_WGRAD = 2 };
 struct Epi {
@@ -53,7 +57,16 @@ struct Epi {
     int n_logical, act, bn;
     int m_valid;                       // rows >= m_valid are written as zero (transposed padding)
     int64_t split_stride;              // WGRAD: floats between split partials
+    // 3xBF16 engine, FWD: the layer output also leaves as bf16 hi / lo copies, row-major [M, ldh] and transposed [N, ldt]
+    __nv_bfloat16 *Hs_hi, *Hs_lo, *HTs_hi, *HTs_lo;
 };
+
+// hi = bf16(x) (round to nearest), lo = bf16(x - hi): x = hi + lo up to 2^-17 relative; the product a*b is rebuilt as
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi on the bf16 tensor pipe with fp32 accumulation (dropped term ~2^-18)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
 
 
 }  // namespace wd

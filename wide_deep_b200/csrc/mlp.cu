@@ -161,15 +161,23 @@ static void launch_gemm(WdModel* m, int mode, const GemmA& A, const float* B, in
 // tcgen05 engine (gemm_tc.cu); returns WD_EUNSUPPORTED when the shape is not covered
 int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len,
             const float* B_hi, const float* B_lo);
+// 3xBF16 tcgen05 engine (gemm_bf16.cu): operands are the bf16 hi / lo copies (GemmA::hi/lo, Bq_hi/Bq_lo)
+int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, int M, int N,
+                 const Epi& ep, int splits, int ksplit_len);
 
 static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits = 1, int ksplit_len = 0,
-                    const float* B_hi = nullptr, const float* B_lo = nullptr) {
+                    const float* B_hi = nullptr, const float* B_lo = nullptr, const __nv_bfloat16* Bq_hi = nullptr, const __nv_bfloat16* Bq_lo = nullptr) {
     static const char* kNamesL[3][4] = {{"gemm_fwd_l0", "gemm_fwd_l1", "gemm_fwd_l2", "gemm_fwd_l3+"},
                                         {"gemm_dgrad_l0", "gemm_dgrad_l1", "gemm_dgrad_l2", "gemm_dgrad_l3+"},
                                         {"gemm_wgrad_l0", "gemm_wgrad_l1", "gemm_wgrad_l2", "gemm_wgrad_l3+"}};
     const char* kNames[3] = {kNamesL[0][m->cur_layer < 3 ? m->cur_layer : 3], kNamesL[1][m->cur_layer < 3 ? m->cur_layer : 3],
                              kNamesL[2][m->cur_layer < 3 ? m->cur_layer : 3]};
     mark(m, "mlp_other");
+    if (m->gemm_engine == WD_GEMM_BF16X3) {
+        int rc = tc_gemm_bf16(m, mode, A, Bq_hi, Bq_lo, ldb, M, N, ep, splits, ksplit_len);
+        mark(m, kNames[mode]);
+        return rc;
+    }
     if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
         int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len, B_hi, B_lo);
         if (rc != WD_EUNSUPPORTED) { mark(m, kNames[mode]); return rc; }
@@ -192,6 +200,22 @@ __global__ void transpose_kernel(const float* __restrict__ in, int ld_in, int M,
     for (int i = threadIdx.y; i < 32; i += 8) {
         int nn = n0 + i, mm = m0 + threadIdx.x;
         if (nn < N && mm < Mpad) out[(int64_t)nn * ld_out + mm] = t[threadIdx.x][i];
+    }
+}
+
+// 3xBF16 engine: bf16 hi / lo copies of the deep input [M, ld] (the only form the tensor-core GEMMs read)
+__global__ void x0_split_kernel(const float* __restrict__ in, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(in)[i];
+        __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+        split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1); split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
+        uint2 ph, pl;
+        ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+        pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+        reinterpret_cast<uint2*>(hi)[i] = ph;
+        reinterpret_cast<uint2*>(lo)[i] = pl;
     }
 }
 
@@ -305,7 +329,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
                                                         int ld, const float* __restrict__ gamma, int act, int bn,
                                                         float* __restrict__ dZ, float* __restrict__ dZT, int ldt,
                                                         float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
-                                                        int64_t pstride) {
+                                                        int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo) {
     __shared__ float tile[32][33];
     __shared__ float red[3][8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
@@ -324,9 +348,16 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
                 dz = dh * gsc * act_bwd(act, a);
                 sb += dz; sg += dh * a * inv; sbe += dh;
             }
-            if (mm < B && n < N) dZ[(int64_t)mm * ld + n] = dz;
+            if (q_hi) {                                           // 3xBF16 engine: the GEMMs read bf16 hi / lo copies only
+                if (mm < B && n < N) {
+                    __nv_bfloat16 h, l;
+                    split_bf16(dz, h, l);
+                    q_hi[(int64_t)mm * ld + n] = h; q_lo[(int64_t)mm * ld + n] = l;
+                }
+            } else if (mm < B && n < N) dZ[(int64_t)mm * ld + n] = dz;
             tile[ty * 4 + i][tx] = dz;
         }
+        if (q_hi) continue;                                       // (uniform) the 3xBF16 engine needs no transposed copy
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -408,9 +439,17 @@ __device__ __forceinline__ void store_split(float* __restrict__ Wsplit, int64_t 
     Wsplit[2 * wt_count + wt_off + et] = hi;       // Wt [N, K] hi
     Wsplit[3 * wt_count + wt_off + et] = lo;       // Wt [N, K] lo
 }
+// 3xBF16 engine: W [K, N] as bf16 hi / lo (the first two quarter-size arrays of the buffer); no transposed copy is needed
+__device__ __forceinline__ void store_split_bf16(float* __restrict__ Wsplit, int64_t wt_count, int64_t wt_off, int64_t e, float w) {
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(Wsplit);
+    __nv_bfloat16 hi, lo;
+    split_bf16(w, hi, lo);
+    q[wt_off + e] = hi;
+    q[wt_count + wt_off + e] = lo;
+}
 __global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ G,
                                    float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ Wt,
-                                   float* __restrict__ Wsplit, int64_t wt_count, OptParamsD dnn, OptParamsD lin, int lin_tensor) {
+                                   float* __restrict__ Wsplit, int64_t wt_count, OptParamsD dnn, OptParamsD lin, int lin_tensor, int bf16) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nt - 1;
         while (lo < hi) {
@@ -425,14 +464,17 @@ __global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, in
         if (t.wt_off >= 0) {
             int64_t e = i - t.off;
             int k = (int)(e / t.cols), n = (int)(e % t.cols);
-            Wt[t.wt_off + (int64_t)n * t.rows + k] = w;
-            store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, w);
+            if (bf16) store_split_bf16(Wsplit, wt_count, t.wt_off, e, w);
+            else {
+                Wt[t.wt_off + (int64_t)n * t.rows + k] = w;
+                store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, w);
+            }
         }
     }
 }
 // Wt refresh only (after init / tensor upload)
 __global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ P, float* __restrict__ Wt,
-                                       float* __restrict__ Wsplit, int64_t wt_count) {
+                                       float* __restrict__ Wsplit, int64_t wt_count, int bf16) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nt - 1;
         while (lo < hi) {
@@ -444,13 +486,14 @@ __global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt
             int64_t e = i - t.off;
             int k = (int)(e / t.cols), n = (int)(e % t.cols);
             Wt[t.wt_off + (int64_t)n * t.rows + k] = P[i];
-            store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, P[i]);
+            if (bf16) store_split_bf16(Wsplit, wt_count, t.wt_off, e, P[i]);
+            else store_split(Wsplit, wt_count, t.wt_off, e, (int64_t)n * t.rows + k, P[i]);
         }
     }
 }
 int dense_refresh_transposes(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
-    dense_transpose_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_P, m->d_Wt, m->d_Wsplit, m->wt_count);
+    dense_transpose_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_P, m->d_Wt, m->d_Wsplit, m->wt_count, m->gemm_engine == WD_GEMM_BF16X3);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
@@ -461,6 +504,9 @@ static const float* src_ptr(WdModel* m, Tower& tw, int src, bool transposed) {
     if (src < 0) return transposed ? m->d_X0T : m->d_X0;
     return transposed ? tw.layers[src].HT : tw.layers[src].H;
 }
+static const __nv_bfloat16* src_split(WdModel* m, Tower& tw, int src, int part) {
+    return src < 0 ? m->d_X0s[part] : tw.layers[src].Hs[part];
+}
 static int src_ld(WdModel* m, Tower& tw, int src, bool transposed) {
     if (transposed) return m->ldt;
     return src < 0 ? m->d0_phys : tw.layers[src].N_phys;
@@ -469,7 +515,13 @@ static int src_ld(WdModel* m, Tower& tw, int src, bool transposed) {
 int mlp_forward(WdModel* m, bool train) {
     const int B = m->dbatch.B;
     if (!m->use_deep) return WD_OK;
-    if (train) {                                       // X0T for the first layer's weight gradient
+    const bool q = m->gemm_engine == WD_GEMM_BF16X3;
+    const __nv_bfloat16* Wq = reinterpret_cast<const __nv_bfloat16*>(m->d_Wsplit);
+    if (q) {                                           // bf16 hi / lo copies of X0
+        const int64_t n4 = (int64_t)B * m->d0_phys / 4;
+        x0_split_kernel<<<grid_for(n4, 256), 256, 0, m->stream>>>(m->d_X0, n4, m->d_X0s[0], m->d_X0s[1]);
+        m->launches++;
+    } else if (train) {                                // X0T for the first layer's weight gradient
         int Bp = (B + 127) / 128 * 128;
         dim3 g((m->d0_phys + 31) / 32, (Bp + 31) / 32);
         transpose_kernel<<<g, dim3(32, 8), 0, m->stream>>>(m->d_X0, m->d0_phys, B, Bp, m->d0_phys, m->d_X0T, m->ldt);
@@ -485,17 +537,24 @@ int mlp_forward(WdModel* m, bool train) {
                 A.ptr[s] = src_ptr(m, tw, L.segs[s].src, false);
                 A.ld[s] = src_ld(m, tw, L.segs[s].src, false);
                 A.k[s] = L.segs[s].width_phys;
+                if (q) { A.hi[s] = src_split(m, tw, L.segs[s].src, 0); A.lo[s] = src_split(m, tw, L.segs[s].src, 1); }
             }
             Epi ep{};
             ep.A_out = L.A; ep.H_out = L.H; ep.ldh = L.N_phys;
-            ep.HT = train ? L.HT : nullptr; ep.ldt = m->ldt;
+            ep.HT = (train && !q) ? L.HT : nullptr; ep.ldt = m->ldt;
+            if (q) {                                   // fp32 H only where the logits layer reads it
+                ep.Hs_hi = L.Hs[0]; ep.Hs_lo = L.Hs[1];
+                if (!L.h_fp32) ep.H_out = nullptr;
+            }
             ep.bias = m->d_P + m->dense[L.t_bias].off;
             ep.gamma = L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr;
             ep.beta = L.t_beta >= 0 ? m->d_P + m->dense[L.t_beta].off : nullptr;
             ep.n_logical = L.N; ep.act = m->activation; ep.bn = m->batch_norm; ep.m_valid = B;
             const int64_t wo = m->dense[L.t_kernel].wt_off;
             const float* Wt = m->d_Wt + wo;
-            int rc = run_gemm(m, EPI_FWD, A, Wt, L.K_phys, B, L.N_phys, ep, 1, 0, m->d_Wsplit + 2 * m->wt_count + wo, m->d_Wsplit + 3 * m->wt_count + wo);
+            // (3xBF16: B = W [K, N] itself, N-contiguous, leading dimension N_phys)
+            int rc = run_gemm(m, EPI_FWD, A, Wt, q ? L.N_phys : L.K_phys, B, L.N_phys, ep, 1, 0, m->d_Wsplit + 2 * m->wt_count + wo,
+                              m->d_Wsplit + 3 * m->wt_count + wo, Wq + wo, Wq + m->wt_count + wo);
             if (rc) return rc;
         }
         Layer& LL = tw.layers[tw.n_hidden];
@@ -536,6 +595,8 @@ int mlp_backward(WdModel* m) {
     const int Bk = (B + 15) / 16 * 16;                                // reduction length of wgrad
     bool dx0_written = false;
     const bool need_dx0 = !m->tables.empty();
+    const bool q = m->gemm_engine == WD_GEMM_BF16X3;
+    const __nv_bfloat16* Wq = reinterpret_cast<const __nv_bfloat16*>(m->d_Wsplit);
     for (auto& tw : m->towers) {
         std::vector<char> written(tw.n_hidden, 0);
         auto grad_dst = [&](int src, float** p, int* ld, int* acc) {
@@ -575,7 +636,8 @@ int mlp_backward(WdModel* m) {
             dim3 g((L.N_phys + 31) / 32, rts);
             act_bn_bwd_kernel<<<g, 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                                                        L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
-                                                       m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride);
+                                                       m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride,
+                                                       q ? L.dZs[0] : nullptr, q ? L.dZs[1] : nullptr);
             m->launches++;
             // data gradients first: the deep-input gradient dX0 is what the embedding backward waits for, so it is
             // produced before this layer's weight gradients (which then overlap the sparse backward on the side stream)
@@ -586,11 +648,12 @@ int mlp_backward(WdModel* m) {
                 grad_dst(sg.src, &dst, &dld, &acc);
                 GemmA A2{};
                 A2.n = 1; A2.ptr[0] = L.dZ; A2.ld[0] = L.N_phys; A2.k[0] = L.N_phys;
+                A2.hi[0] = L.dZs[0]; A2.lo[0] = L.dZs[1];
                 Epi e2{};
                 e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
                 const int64_t woff = tkn.wt_off + (int64_t)sg.k_off * L.N_phys;
                 int rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
-                                  m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff);
+                                  m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff, Wq + woff, Wq + m->wt_count + woff);
                 if (rc) return rc;
             }
             if (l == 0 && &tw == &m->towers.back() && need_dx0 && m->ev_dx0 && m->record_dx0) {
@@ -602,10 +665,16 @@ int mlp_backward(WdModel* m) {
                 // weight gradient of the rows fed by this segment: [width_phys, N] = srcT * dZT^T, split over the batch
                 GemmA A{};
                 A.n = 1; A.ptr[0] = src_ptr(m, tw, sg.src, true); A.ld[0] = m->ldt; A.k[0] = Bk;
+                if (q) {                               // row-major [B, width] copies; the batch is the reduction dimension
+                    A.hi[0] = src_split(m, tw, sg.src, 0); A.lo[0] = src_split(m, tw, sg.src, 1);
+                    A.ld[0] = src_ld(m, tw, sg.src, false); A.k[0] = B;
+                }
                 Epi ep{};
                 ep.C = m->d_gpart + tkn.gpart_off + (int64_t)sg.k_off * L.N_phys; ep.ldc = L.N_phys; ep.split_stride = tkn.gstride;
                 int ks = ((Bk + L.wgrad_splits - 1) / L.wgrad_splits + 31) / 32 * 32;
-                int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, m->ldt, sg.width_phys, L.N_phys, ep, L.wgrad_splits, ks);
+                if (q) ks = (ks + 63) / 64 * 64;
+                int rc = run_gemm(m, EPI_WGRAD, A, L.dZT, q ? L.N_phys : m->ldt, sg.width_phys, L.N_phys, ep, L.wgrad_splits, ks, nullptr, nullptr,
+                                  L.dZs[0], L.dZs[1]);
                 if (rc) return rc;
             }
         }
@@ -630,7 +699,7 @@ int dense_apply(WdModel* m) {
     OptParamsD l{m->lin_opt.kind, m->lin_opt.lr, m->lin_opt.l1, m->lin_opt.l2};
     int lin_tensor = m->use_wide ? 0 : -1;                       // tensor 0 is the wide bias when the wide part exists
     dense_apply_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_G,
-                                                                            m->d_P, m->d_S1, m->d_S2, m->d_Wt, m->d_Wsplit, m->wt_count, d, l, lin_tensor);
+                                                                            m->d_P, m->d_S1, m->d_S2, m->d_Wt, m->d_Wsplit, m->wt_count, d, l, lin_tensor, m->gemm_engine == WD_GEMM_BF16X3);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;

@@ -530,15 +530,17 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
 }
 
 // ugrad[u] = sum of the row's chunk partials (multi-chunk rows only).  Each lane checks one unique row; the (rare)
-// multi-chunk rows of a warp are combined by the whole warp: lane l adds chunks l, l+32, ... and a fixed-order shuffle
-// tree adds the 32 lane sums, so the result does not depend on scheduling.
+// multi-chunk rows of a warp are combined by the whole warp: lane groups add chunks g, g+NG, ... and a fixed-order shuffle
+// tree adds the group sums, so the result does not depend on scheduling.  Hot rows are neighbours in row order (they are the
+// rows of the small tables), so a warp takes every NW-th group of rows (lane l of warp w checks row (it * 32 + l) * NW + w):
+// neighbouring hot rows land in different warps and their long chunk lists are walked concurrently, not one after the other.
 __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ choff,
                                                             const float* __restrict__ cpart, float* __restrict__ ugrad, int width) {
     const int nu = *d_nuniq;
     const int lane = threadIdx.x & 31;
     const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = w0 * 32; base < nu; base += nw * 32) {
-        const int64_t u = base + lane;
+    for (int64_t it = 0; it * 32 * nw < nu; ++it) {
+        const int64_t u = (it * 32 + lane) * nw + w0;
         int c0 = 0, c1 = 0;
         if (u < nu) { c0 = choff[u]; c1 = choff[u + 1]; }
         unsigned multi = __ballot_sync(0xffffffffu, c1 > c0);
@@ -546,12 +548,25 @@ __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __res
             const int src = __ffs(multi) - 1;
             multi &= multi - 1;
             const int b0 = __shfl_sync(0xffffffffu, c0, src), b1 = __shfl_sync(0xffffffffu, c1, src);
+            const int64_t urow = (it * 32 + src) * nw + w0;
             const int G = width >> 2;
             if (width >= 4 && (G & (G - 1)) == 0 && G <= 32) {
-                // G lanes cover one chunk's row (float4 each), 32/G chunks in flight; fixed-order tree over the chunk groups
+                // G lanes cover one chunk's row (float4 each), 32/G chunks in flight per step, 4 steps unrolled;
+                // fixed-order tree over the chunk groups
                 const int lq = lane % G, cg = lane / G, NG = 32 / G;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int c = b0 + cg; c < b1; c += NG) {
+                int c = b0 + cg;
+                for (; c + 3 * NG < b1; c += 4 * NG) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(cpart + (int64_t)c * width + lq * 4);
+                    const float4 v1 = *reinterpret_cast<const float4*>(cpart + (int64_t)(c + NG) * width + lq * 4);
+                    const float4 v2 = *reinterpret_cast<const float4*>(cpart + (int64_t)(c + 2 * NG) * width + lq * 4);
+                    const float4 v3 = *reinterpret_cast<const float4*>(cpart + (int64_t)(c + 3 * NG) * width + lq * 4);
+                    acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                    acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+                    acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+                    acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+                }
+                for (; c < b1; c += NG) {
                     const float4 v = *reinterpret_cast<const float4*>(cpart + (int64_t)c * width + lq * 4);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
@@ -559,14 +574,14 @@ __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __res
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
                     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
                 }
-                if (cg == 0) *reinterpret_cast<float4*>(ugrad + (base + src) * width + lq * 4) = acc;
+                if (cg == 0) *reinterpret_cast<float4*>(ugrad + urow * width + lq * 4) = acc;
             } else {
                 for (int q = 0; q < width; ++q) {
                     float acc = 0.f;
                     for (int c = b0 + lane; c < b1; c += 32) acc += cpart[(int64_t)c * width + q];
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                    if (lane == 0) ugrad[(base + src) * width + q] = acc;
+                    if (lane == 0) ugrad[urow * width + q] = acc;
                 }
             }
         }

@@ -35,7 +35,7 @@ ACTS = ["relu", "relu6", "sigmoid", "tanh", "leaky_relu", "elu", "selu", "softpl
 MODES = ["simple", "first_dense", "last_dense", "dense", "resnet"]
 T_WIDE_COL, T_EMB_TABLE, T_DENSE, T_WIDE_BIAS = range(4)
 D_KERNEL, D_BIAS, D_GAMMA, D_BETA = range(4)
-GEMM = {"auto": 0, "ffma": 1, "tc3x": 2, "tc1x": 3}
+GEMM = {"auto": 0, "ffma": 1, "tc3x": 2, "tc1x": 3, "bf16x3": 4}
 
 
 def embedding_dim(n):
