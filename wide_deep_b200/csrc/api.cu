@@ -102,13 +102,14 @@ extern "C" int wd_model_destroy(WdModel* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
     for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
-    if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
+    for (int w = 0; w < 2; ++w) {
+        if (m->sstream[w]) { cudaStreamSynchronize(m->sstream[w]); cudaStreamDestroy(m->sstream[w]); }
+        if (m->ev_grouped[w]) cudaEventDestroy(m->ev_grouped[w]);
+        if (m->ev_done[w]) cudaEventDestroy(m->ev_done[w]);
+    }
     if (m->ev_ids) cudaEventDestroy(m->ev_ids);
-    if (m->ev_sorted) cudaEventDestroy(m->ev_sorted);
     if (m->ev_head) cudaEventDestroy(m->ev_head);
-    if (m->ev_wide) cudaEventDestroy(m->ev_wide);
     if (m->ev_dx0) cudaEventDestroy(m->ev_dx0);
-    if (m->ev_sparse) cudaEventDestroy(m->ev_sparse);
     if (m->stream) cudaStreamDestroy(m->stream);
     for (size_t i = 0; i < g_extra.size(); ++i)
         if (g_extra[i].first == m) { delete g_extra[i].second; g_extra.erase(g_extra.begin() + i); break; }
@@ -201,10 +202,10 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if ((rc = dev_alloc(m, &m->d_e_id, m->max_nnz))) return rc;
     if ((rc = dev_alloc(m, &m->d_nnz, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_flags, 4))) return rc;
-    for (int k = 0; k < 2; ++k) if ((rc = dev_alloc(m, &m->d_sort_counter_s[k], 4))) return rc;
+    for (int k = 0; k < 3; ++k) if ((rc = dev_alloc(m, &m->d_sort_counter_s[k], 4))) return rc;
     {
         int64_t n = std::max<int64_t>(Bm * std::max(C, 1) + 2, m->max_nnz + 2);
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
             int32_t* t;
             if ((rc = dev_alloc(m, &t, n / 4096 + 8))) return rc;
             m->d_scan_tmp_s[k] = t;
@@ -413,8 +414,8 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_cpart[w], m->cpart_cap * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         m->sparse_cap[w] = m->max_nnz;
     }
-    m->sort_hist_cap = 1024 * ((m->max_nnz + 4095) / 4096 + 1) + 4 * 1024 + 64;
-    for (int k = 0; k < 2; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
+    m->sort_hist_cap = 1024 * ((m->max_nnz + kSortTile - 1) / kSortTile + 1) + 4 * 1024 + 64;
+    for (int k = 0; k < 3; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
     if ((rc = metrics_setup())) return rc;
     if ((rc = init_sparse_tables(m, 0, 0))) return rc;           // slots = initial accumulator, weights 0
     if ((rc = init_dense_slots(m))) return rc;
@@ -439,13 +440,14 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     m->device = device;
     memset(m->timer.ev, 0, sizeof(m->timer.ev));
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
+    for (int w = 0; w < 2; ++w) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->sstream[w], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_grouped[w], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_done[w], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sorted, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_dx0, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_sparse, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
     m->graphs_enabled = getenv("WD_NO_GRAPH") == nullptr;
     int rc = build_model(d, m, x);
@@ -693,18 +695,30 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
     return WD_OK;
 }
 
-// launch the id-only grouping of the sparse backward on the side stream (overlaps forward + backward of the towers)
+static bool list_present(const WdModel* m, int which) { return which == 0 ? (m->use_deep && !m->tables.empty()) : m->use_wide; }
+
+// run `fn` on the side stream of sparse list `which` with that stream's scratch set
+template <typename F>
+static int on_side(WdModel* m, int which, F fn) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->sstream[which]; m->scratch_sel = 1 + which;
+    int rc = fn();
+    m->stream = main_stream; m->scratch_sel = 0;
+    return rc;
+}
+
+// launch the id-only grouping of both sparse lists on their side streams (overlaps forward + backward of the towers)
 static int group_async(WdModel* m) {
     if (m->timer.enabled) return WD_OK;                      // profiling: keep everything on one stream (done before the reduce)
     WD_CUDA(cudaEventRecord(m->ev_ids, m->stream));
-    WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_ids, 0));
-    cudaStream_t main_stream = m->stream;
-    m->stream = m->stream2; m->scratch_sel = 1;
-    int rc = sparse_group(m);
-    m->stream = main_stream; m->scratch_sel = 0;
-    if (rc) return rc;
-    WD_CUDA(cudaEventRecord(m->ev_sorted, m->stream2));
-    m->sorted_pending = true;
+    for (int w = 0; w < 2; ++w) {
+        if (!list_present(m, w)) continue;
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[w], m->ev_ids, 0));
+        int rc = on_side(m, w, [&] { return sparse_group_which(m, w); });
+        if (rc) return rc;
+        WD_CUDA(cudaEventRecord(m->ev_grouped[w], m->sstream[w]));
+        m->side_pending[w] = true;
+    }
     return WD_OK;
 }
 
@@ -718,85 +732,60 @@ static int forward_core(WdModel* m, bool train) {
     mark(m, "mlp_other");
     if ((rc = loss_forward(m, train))) return rc;
     mark(m, "head");
-    if (train && m->sorted_pending) WD_CUDA(cudaEventRecord(m->ev_head, m->stream));
+    if (train && (m->side_pending[0] || m->side_pending[1])) WD_CUDA(cudaEventRecord(m->ev_head, m->stream));
     return WD_OK;
 }
 
-// run `fn` on the side stream with the side scratch set
-template <typename F>
-static int on_side(WdModel* m, F fn) {
-    cudaStream_t main_stream = m->stream;
-    m->stream = m->stream2; m->scratch_sel = 1;
-    int rc = fn();
-    m->stream = main_stream; m->scratch_sel = 0;
-    return rc;
-}
-
-// Backward.  Main stream: towers (dgrad before wgrad per layer), dense gradient reduction.  Side stream (when the
+// Backward.  Main stream: towers (dgrad before wgrad per layer), dense gradient reduction.  Side streams (when the
 // grouping already lives there): wide gradient sums as soon as dlogit exists, embedding gradient sums as soon as dX0
 // exists — i.e. under the remaining weight-gradient GEMMs.
 static int backward_core(WdModel* m) {
     int rc;
-    m->wide_on_side = m->emb_on_side = false;
-    const bool side = m->sorted_pending;
-    const bool has_emb = m->use_deep && !m->tables.empty();
-    if (side && m->use_wide) {
-        WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_head, 0));
-        if ((rc = on_side(m, [&] { return sparse_reduce_wide(m); }))) return rc;
-        WD_CUDA(cudaEventRecord(m->ev_wide, m->stream2));
-        m->wide_on_side = true;
+    m->side_active[0] = m->side_active[1] = false;
+    if (m->side_pending[1]) {
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], m->ev_head, 0));
+        if ((rc = on_side(m, 1, [&] { return sparse_reduce_wide(m); }))) return rc;
+        m->side_active[1] = true;
     }
-    m->record_dx0 = side && has_emb;
+    m->record_dx0 = m->side_pending[0];
     m->dx0_recorded = false;
     if ((rc = mlp_backward(m))) return rc;
     m->record_dx0 = false;
     mark(m, "mlp_other");
-    if (side && has_emb && m->dx0_recorded) {
-        WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_dx0, 0));
-        if ((rc = on_side(m, [&] { return sparse_reduce_emb(m); }))) return rc;
-        WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
-        m->emb_on_side = true;
+    if (m->side_pending[0] && m->dx0_recorded) {
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[0], m->ev_dx0, 0));
+        if ((rc = on_side(m, 0, [&] { return sparse_reduce_emb(m); }))) return rc;
+        m->side_active[0] = true;
     }
     if ((rc = wide_bias_grad(m))) return rc;
     if ((rc = dense_reduce_grads(m))) return rc;
     mark(m, "dense_reduce");
-    if (side) {
-        if (!m->emb_on_side) WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sorted, 0));
-        m->sorted_pending = false;
-    } else if ((rc = sparse_group(m))) return rc;
-    if (!m->emb_on_side && (rc = sparse_reduce_emb(m))) return rc;
-    if (!m->wide_on_side && (rc = sparse_reduce_wide(m))) return rc;
+    for (int w = 0; w < 2; ++w) {                           // lists that stay on the main stream
+        if (m->side_active[w] || !list_present(m, w)) { m->side_pending[w] = false; continue; }
+        if (m->side_pending[w]) WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_grouped[w], 0));
+        else if ((rc = sparse_group_which(m, w))) return rc;
+        m->side_pending[w] = false;
+        if ((rc = (w == 0 ? sparse_reduce_emb(m) : sparse_reduce_wide(m)))) return rc;
+    }
     m->grads_pending = true;
     return WD_OK;
 }
 
+// Optimizer.  A list whose sums live on its side stream is applied there (after its merge in data-parallel runs); the dense
+// optimizer runs on the main stream meanwhile and the streams join at the end of the step.
 static int apply_core(WdModel* m) {
     int rc;
-    if (m->emb_on_side || m->wide_on_side) {
-        // every sparse list that lives on the side stream is applied there (after its merge in data-parallel runs);
-        // the dense optimizer runs on the main stream meanwhile and the streams join at the end of the step
-        if (!m->emb_on_side) WD_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_sorted, 0));
-        if (m->emb_on_side != (m->use_deep && !m->tables.empty()) || m->wide_on_side != m->use_wide) {
-            // mixed placement: bring everything to the main stream
-            WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
-            WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sparse, 0));
-            if ((rc = sparse_apply(m))) return rc;
-        } else {
-            if ((rc = on_side(m, [&] { return sparse_apply(m); }))) return rc;
-            WD_CUDA(cudaEventRecord(m->ev_sparse, m->stream2));
-        }
-        mark(m, "sparse_apply");
-        if ((rc = dense_apply(m))) return rc;
-        mark(m, "dense_apply");
-        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_sparse, 0));
-        m->emb_on_side = m->wide_on_side = false;
-        m->grads_pending = false;
-        return WD_OK;
+    for (int w = 0; w < 2; ++w) {
+        if (m->side_active[w]) {
+            if ((rc = on_side(m, w, [&] { return sparse_apply_which(m, w); }))) return rc;
+            WD_CUDA(cudaEventRecord(m->ev_done[w], m->sstream[w]));
+        } else if ((rc = sparse_apply_which(m, w))) return rc;
     }
-    if ((rc = sparse_apply(m))) return rc;
     mark(m, "sparse_apply");
     if ((rc = dense_apply(m))) return rc;
     mark(m, "dense_apply");
+    for (int w = 0; w < 2; ++w)
+        if (m->side_active[w]) { WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0)); m->side_active[w] = false; }
     m->grads_pending = false;
     return WD_OK;
 }
@@ -840,13 +829,13 @@ static int train_current(WdModel* m, float* loss_out) {
             cudaGetLastError();
             m->graphs_enabled = false;
             sl.graph = nullptr;
-            m->sorted_pending = false; m->wide_on_side = m->emb_on_side = false;
+            m->side_pending[0] = m->side_pending[1] = m->side_active[0] = m->side_active[1] = false;
             if ((rc = train_eager(m))) return rc;
         } else {
             sl.graph_view = m->dbatch;
             sl.graph_launches = m->launches - l0;
             m->launches = l0;
-            m->sorted_pending = false; m->wide_on_side = m->emb_on_side = false; m->grads_pending = false;
+            m->side_pending[0] = m->side_pending[1] = m->side_active[0] = m->side_active[1] = false; m->grads_pending = false;
             WD_CUDA(cudaGraphLaunch(sl.graph, m->stream));
             m->launches += sl.graph_launches;
         }
@@ -941,7 +930,7 @@ extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads,
     if (n) {                                   // the count needs a sync; pass n = NULL for the asynchronous fixed-size exchange
         int32_t nu = 0;
         WD_CUDA(cudaStreamSynchronize(m->stream));
-        WD_CUDA(cudaStreamSynchronize(m->stream2));
+        WD_CUDA(cudaStreamSynchronize(m->sstream[which]));
         WD_CUDA(cudaMemcpy(&nu, m->d_nuniq[which], 4, cudaMemcpyDeviceToHost));
         *n = nu;
     }
@@ -956,8 +945,7 @@ extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const 
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    if ((which == 1 && m->wide_on_side) || (which == 0 && m->emb_on_side))
-        return on_side(m, [&] { return merge_sparse(m, which, rows_dev, grads_dev, n); });
+    if (m->side_active[which]) return on_side(m, which, [&] { return merge_sparse(m, which, rows_dev, grads_dev, n); });
     return merge_sparse(m, which, rows_dev, grads_dev, n);
 }
 
@@ -1048,7 +1036,7 @@ extern "C" int wd_set_profile(WdModel* m, int enable) {
 extern "C" void* wd_stream(WdModel* m) { return m ? (void*)m->stream : nullptr; }
 extern "C" void* wd_stream_sparse(WdModel* m, int which) {
     if (!m) return nullptr;
-    return ((which == 1 && m->wide_on_side) || (which == 0 && m->emb_on_side)) ? (void*)m->stream2 : (void*)m->stream;
+    return (which >= 0 && which < 2 && m->side_active[which]) ? (void*)m->sstream[which] : (void*)m->stream;
 }
 extern "C" int wd_sync(WdModel* m) {
     int rc = check_ready(m);

@@ -11,6 +11,8 @@
 
 namespace wd {
 
+constexpr int kSortTile = 1024;          // keys per radix-sort tile (sort.cu); sizes the per-tile histogram scratch
+
 void set_error(const char* fmt, ...);
 
 #define WD_CUDA(call)                                                                         \
@@ -164,12 +166,14 @@ struct WdModel {
     int gemm_engine = 0;
 
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;          // side stream: the id-only part of the sparse backward overlaps the towers
-    cudaEvent_t ev_ids = nullptr, ev_sorted = nullptr, ev_head = nullptr, ev_wide = nullptr, ev_dx0 = nullptr, ev_sparse = nullptr;
+    // side streams, one per sparse gradient list (0 = embedding rows, 1 = wide rows): the id-only grouping, the gradient sums,
+    // the data-parallel merge and the row updates of a list all run there, overlapping the towers on the main stream
+    cudaStream_t sstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr;
+    cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool side_pending[2] = {false, false};   // the list's grouping of this step was issued on its side stream
+    bool side_active[2] = {false, false};    // the list's sums live on its side stream (merge / apply follow there)
     bool record_dx0 = false, dx0_recorded = false;
-    bool emb_on_side = false;                // embedding gradient list (and its merge / apply) lives on the side stream
-    bool sorted_pending = false;             // side stream holds this step's row grouping
-    bool wide_on_side = false;               // wide gradient list (and its merge) lives on the side stream until apply
     wd::DevPlan dplan{};
     std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
     int64_t bytes_allocated = 0;
@@ -194,7 +198,7 @@ struct WdModel {
     int32_t* d_e_id = nullptr;               // [max_nnz] column-local id (debug / parity)
     int32_t* d_nnz = nullptr;                // device scalar: entries this step
     int32_t* d_flags = nullptr;              // device error flags [4]
-    void* d_scan_tmp_s[2] = {nullptr, nullptr};   // scan / sort scratch, one set per stream (0 main, 1 side)
+    void* d_scan_tmp_s[3] = {nullptr, nullptr, nullptr};   // scan / sort scratch, one set per stream (0 main, 1 + list for the side streams)
     int scratch_sel = 0;
 
     // ---- wide part: record {w, n, z, 0} per row
@@ -238,9 +242,9 @@ struct WdModel {
     // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
     uint32_t *d_sk[2] = {nullptr, nullptr}, *d_sv[2] = {nullptr, nullptr};     // ping-pong keys / values
     uint32_t *d_sk2[2] = {nullptr, nullptr}, *d_sv2[2] = {nullptr, nullptr};
-    int32_t* d_sort_hist_s[2] = {nullptr, nullptr};
+    int32_t* d_sort_hist_s[3] = {nullptr, nullptr, nullptr};
     int64_t sort_hist_cap = 0;
-    int32_t* d_sort_counter_s[2] = {nullptr, nullptr};
+    int32_t* d_sort_counter_s[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_urow[2] = {nullptr, nullptr};   // unique rows
     int32_t* d_ustart[2] = {nullptr, nullptr};  // segment starts in the sorted list (+1 sentinel)
     float* d_ugrad[2] = {nullptr, nullptr};     // [cap, width]
@@ -276,7 +280,9 @@ int sparse_forward(WdModel* m);                                  // sparse.cu: w
 int sparse_group(WdModel* m);                                    // sparse.cu: sort (row, occurrence) pairs, unique rows, chunks
 int sparse_reduce_emb(WdModel* m);                               // sparse.cu: per-row gradient sums (needs dX0)
 int sparse_reduce_wide(WdModel* m);                              // sparse.cu: per-row gradient sums (needs dlogit only)
-int sparse_apply(WdModel* m);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
+int sparse_apply(WdModel* m);
+int sparse_apply_which(WdModel* m, int which);                     // sparse.cu: 0 = embedding rows, 1 = wide rows
+int sparse_group_which(WdModel* m, int which);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
 int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
 int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0
 int dense_reduce_grads(WdModel* m);                              // mlp.cu

@@ -5,10 +5,14 @@
 // Every fp32 operand exists in HBM as two bf16 copies, hi = bf16_rn(x) and lo = bf16_rn(x - hi), written by the kernel that
 // PRODUCED the operand (forward epilogue, act_bn_bwd_kernel, x0_split_kernel, dense_apply_kernel), so this kernel moves and
 // multiplies bf16 only: per 64-element k-block four TMA tiles (A_hi, A_lo, B_hi, B_lo; 128-byte swizzle) and
-// 4 k-steps x 3 tcgen05.mma.kind::f16 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) into one fp32 accumulator.  hi + lo carries 16
-// mantissa bits and the dropped a_lo*b_lo term is ~2^-18, so a product is good to ~1e-5 relative — measured ~1e-6 on the logits
-// (tests/test_gpu_parity.py::test_bf16x3_*), inside the 1e-4 parity bar — at half the shared-memory bytes per flop and twice
-// the tensor-pipe rate of the 3xTF32 engine (gemm_tc.cu), with no in-kernel splitting pass at all.
+// 4 k-steps x 3 tcgen05.mma.kind::f16 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) into one fp32 accumulator.  hi + lo represents x to
+// 2^-17 and the dropped a_lo*b_lo term is below 2^-16, so one product carries ~1e-5 relative error (rms ~8e-6; random signs, so a
+// long dot product does better): measured 5e-6 on the logits of the benchmark shape, up to ~1e-4 on small ill-conditioned
+// towers (tests/test_gpu_parity.py, scratch/engine_err.py).  That is a FAST mode: it meets the 1e-4 logit bar on the
+// benchmarked configuration (bench.py re-checks it against the oracle in the same run) but is not fp32-faithful the way the
+// 3xTF32 engine (gemm_tc.cu, 2^-21) is; it costs half the shared-memory bytes per flop, runs at twice the tensor-pipe rate and
+// needs no in-kernel splitting pass.  (Keeping the residual in fp16 would give 19 bits, but tcgen05.mma.kind::f16 traps with an
+// illegal-instruction fault on sm_100a when the A and B formats differ — tried, reverted.)
 //
 // Operand majors.  Forward: A = activations [m][k] (K-major), B = weights W[k][n] (MN-major: n contiguous) — no transposed weight
 // copy exists.  Data gradient: A = dZ [m][n] and B = W[k_in][n], both K-major over n.  Weight gradient: A = layer input [b][k_in]
@@ -214,6 +218,17 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
             const int mw = m0 + q * 32;                        // first row of this warp's chunk
             const int m = mw + lane;
             const int a = use & 1, au = use >> 1;
+            // bias / BN scale / BN shift of column nb + lane: fetched one chunk ahead (the first chunk's before the wait for the
+            // accumulator), so their global-load latency never sits on the epilogue's critical path
+            float pb = 0.f, pg = 1.f, pe = 0.f;
+            auto load_params = [&](int nbx, float& b_, float& g_, float& e_) {
+                const int gn = nbx + lane;
+                const bool in = gn < ep.n_logical;
+                b_ = in ? ep.bias[gn] : 0.f;
+                g_ = (in && ep.bn) ? ep.gamma[gn] * 0.99950037468777f : 1.f;
+                e_ = (in && ep.bn) ? ep.beta[gn] : 0.f;
+            };
+            if (MODE == EPI_FWD) load_params(n0, pb, pg, pe);
             if (nkb > 0) {
                 mbar_wait(&tmem_full[a], au & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -222,6 +237,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
             for (int c = 0; c < TBN / 32; ++c) {
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;
+                float qb = 0.f, qg = 1.f, qe = 0.f;
+                if (MODE == EPI_FWD && c + 1 < TBN / 32 && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
                 uint32_t v[32];
                 if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TBN + c * 32), v);
                 else {
@@ -230,13 +247,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                 }
                 if (MODE == EPI_FWD) {
                     float* wp = epi_params + (warp - 2) * 96;
-                    {
-                        const int gn = nb + lane;
-                        const bool in = gn < ep.n_logical;
-                        wp[lane] = in ? ep.bias[gn] : 0.f;
-                        wp[32 + lane] = (in && ep.bn) ? ep.gamma[gn] * 0.99950037468777f : 1.f;
-                        wp[64 + lane] = (in && ep.bn) ? ep.beta[gn] : 0.f;
-                    }
+                    wp[lane] = pb; wp[32 + lane] = pg; wp[64 + lane] = pe;
+                    pb = qb; pg = qg; pe = qe;
                     __syncwarp();
                     uint32_t h[32];
                     const bool rv = m < ep.m_valid;

@@ -114,8 +114,8 @@ int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out)
 // ------------------------------------------------------------------------------------------ radix sort
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS_PER_WARP = 512;                 // 16 rounds of 32
-constexpr int RS_TILE = RS_WARPS * RS_ITEMS_PER_WARP;  // 4096 keys per tile
+constexpr int RS_ITEMS_PER_WARP = kSortTile / RS_WARPS;  // 4 rounds of 32
+constexpr int RS_TILE = kSortTile;                       // 1024 keys per tile: short blocks, enough of them to fill the SMs
 constexpr int RS_MAX_BINS = 1024;
 
 // Per-tile digit histogram -> hist[tile * bins + bin] (tile-major, coalesced) and global per-bin totals gtot[bin].
@@ -147,14 +147,22 @@ __global__ void __launch_bounds__(256) rs_colscan_kernel(const int32_t* __restri
     const int bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (bin >= bins) return;
     int carry = 0;
-    for (int t0 = 0; t0 < ntiles; t0 += 32) {
-        const int t = t0 + lane;
-        const int v = t < ntiles ? hist[(int64_t)t * bins + bin] : 0;
-        int inc = v;
+    for (int t0 = 0; t0 < ntiles; t0 += 128) {              // 4 independent loads in flight per lane, then 4 shuffle scans
+        int v[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
-        if (t < ntiles) hist[(int64_t)t * bins + bin] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i * 32 + lane;
+            v[i] = t < ntiles ? hist[(int64_t)t * bins + bin] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i * 32 + lane;
+            int inc = v[i];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+            if (t < ntiles) hist[(int64_t)t * bins + bin] = carry + inc - v[i];
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
     }
     if (lane == 0) gtot[bin] = carry;
 }

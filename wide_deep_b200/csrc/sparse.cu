@@ -729,25 +729,23 @@ int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int
 // Stage 1 of the sparse backward: group the step's (row, occurrence) pairs by row for both table spaces and lay out
 // the hot-row chunks.  Depends only on the ids of the batch (not on any gradient), so api.cu runs it on a side stream
 // concurrently with the towers' forward/backward.
-int sparse_group(WdModel* m) {
+int sparse_group_which(WdModel* m, int which) {
     int rc;
     const int g = grid_for(m->max_nnz, 256);
-    if (m->use_deep && !m->tables.empty()) {
-        if ((rc = group_rows(m, 0, m->d_nnz, m->d_e_emb))) return rc;
-        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_urow[0], m->max_nnz);
+    const bool present = which == 0 ? (m->use_deep && !m->tables.empty()) : m->use_wide;
+    if (present) {
+        if ((rc = group_rows(m, which, m->d_nnz, which == 0 ? m->d_e_emb : m->d_e_wide))) return rc;
+        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_choff[which], m->d_urow[which], m->max_nnz);
         m->launches++;
-        if ((rc = exclusive_scan_i32(m, m->d_choff[0], m->max_nnz, m->d_nchunks[0]))) return rc;
-        mark(m, "emb_group");
-    }
-    if (m->use_wide) {
-        if ((rc = group_rows(m, 1, m->d_nnz, m->d_e_wide))) return rc;
-        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_urow[1], m->max_nnz);
-        m->launches++;
-        if ((rc = exclusive_scan_i32(m, m->d_choff[1], m->max_nnz, m->d_nchunks[1]))) return rc;
-        mark(m, "wide_group");
+        if ((rc = exclusive_scan_i32(m, m->d_choff[which], m->max_nnz, m->d_nchunks[which]))) return rc;
+        mark(m, which == 0 ? "emb_group" : "wide_group");
     }
     WD_CUDA(cudaGetLastError());
     return WD_OK;
+}
+int sparse_group(WdModel* m) {
+    int rc = sparse_group_which(m, 0);
+    return rc ? rc : sparse_group_which(m, 1);
 }
 
 // Stage 2: per-row gradient sums; leaves (urow, ugrad, nuniq) ready for exchange / apply
@@ -784,20 +782,24 @@ int sparse_reduce_wide(WdModel* m) {
     return WD_OK;
 }
 
-int sparse_apply(WdModel* m) {
-    if (m->use_deep && !m->tables.empty()) {
+int sparse_apply_which(WdModel* m, int which) {
+    if (which == 0 && m->use_deep && !m->tables.empty()) {
         emb_apply_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
             m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim, (int)m->tables.size(), m->d_tab_row_base, m->d_tab_data,
             m->d_tab_dim, m->d_tab_stride, make_opt(m->dnn_opt));
         m->launches++;
     }
-    if (m->use_wide) {
+    if (which == 1 && m->use_wide) {
         wide_apply_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_urow[1], m->d_ugrad[1], m->d_wide,
                                                                           make_opt(m->lin_opt));
         m->launches++;
     }
     WD_CUDA(cudaGetLastError());
     return WD_OK;
+}
+int sparse_apply(WdModel* m) {
+    int rc = sparse_apply_which(m, 0);
+    return rc ? rc : sparse_apply_which(m, 1);
 }
 
 }  // namespace wd
