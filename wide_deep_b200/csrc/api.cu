@@ -94,10 +94,13 @@ extern "C" int wd_device_count(void) {
 extern "C" uint64_t wd_fingerprint64(const uint8_t* bytes, size_t n) { return wd::fingerprint64(bytes, n); }
 extern "C" uint64_t wd_fingerprint_cat64(uint64_t a, uint64_t b) { return wd::fingerprint_cat64(a, b); }
 
+namespace wd { void tc_map_cache_clear(); }
+
 extern "C" int wd_model_destroy(WdModel* m) {
     if (!m) return WD_OK;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    tc_map_cache_clear();
     for (auto& sl : m->slots) if (sl.graph) cudaGraphExecDestroy(sl.graph);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);

@@ -20,10 +20,11 @@
 // and TMA zero-fills the batch tail.  An MN-major operand is fetched as 64-column boxes (64 k-rows x 128 B, 128-byte swizzle);
 // its UMMA descriptor uses LBO = one box (8 KB) between 64-wide column groups and SBO = 1 KB between 8-row k groups.
 //
-// One persistent CTA per SM, six warps: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2-5 = epilogue (TMEM lane quarter
-// = warp % 4).  The TMEM accumulator is double buffered (2 x TBN columns) so the epilogue's global stores of tile i overlap the
-// MMAs of tile i+1.  Forward epilogue = bias + activation + BN-affine, stores the fp32 outputs and the bf16 hi/lo copies (row
-// major and transposed) that the next layer / the weight gradient will read.
+// One persistent CTA per SM, ten warps: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2-9 = epilogue (TMEM lane quarter
+// = warp % 4, two warps per quarter splitting the columns).  The TMEM accumulator is double buffered (2 x TBN columns) so the epilogue's global stores of tile i overlap the
+// MMAs of tile i+1.  Forward epilogue = bias + activation + BN-affine; it stores the post-activation values (fp32, for the
+// backward), the layer output as bf16 hi/lo copies (what the next layer and the weight gradient read) and, only for layers the
+// logits layer reads, the fp32 layer output.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -34,26 +35,27 @@
 namespace wd {
 
 int tc_make_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows);   // gemm_tc.cu
-int tc_make_map_out(CUtensorMap* map, const void* ptr, int esize, int rows, int cols, int64_t ld, int nz, int64_t zstride,
-                    int box_cols, int box_rows, int swizzle);                                        // gemm_tc.cu
 
 namespace {
 
 constexpr int QBM = 128;         // UMMA M
 constexpr int QBK = 64;          // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int Q_THREADS = 192;
+constexpr int Q_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 struct QMaps {
     CUtensorMap a_hi[kMaxSegs], a_lo[kMaxSegs];
     CUtensorMap b_hi, b_lo;
-    // TMA-store targets: STORE / WGRAD output C; FWD outputs A (post-activation), H (optional), bf16 hi / lo copies of H
-    CUtensorMap o_c, o_a, o_h, o_hs_hi, o_hs_lo;
 };
 struct QSegs { int n; int k[kMaxSegs]; int koff[kMaxSegs]; };
 
+// optional timeline probe of CTA 0 (WD_GEMM_PROBE=1): globaltimer stamps per launch slot, read back by wd_debug_gemm_probe
+__device__ unsigned long long g_probe[32 * 8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROBE(i) do { if (probe >= 0 && blockIdx.x == 0 && lane == 0) g_probe[probe * 8 + (i)] = gtime(); } while (0)
+
 template <int TBN, int MODE>
 __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid_constant__ QMaps maps, const QSegs segs, int M, int N, int ktot,
-                                                                   int ksplit_len, int nsplit, Epi ep) {
+                                                                   int ksplit_len, int nsplit, Epi ep, int probe) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr bool A_MN = MODE == EPI_WGRAD;                       // operand stored with its M / N index contiguous
@@ -65,12 +67,12 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
     auto a_lo = [&](int s) { return base + s * STAGE_BYTES + A_BYTES; };
     auto b_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_BYTES; };
     auto b_lo = [&](int s) { return base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
-    uint8_t* stage_out = base + NST * STAGE_BYTES;                 // 4 epilogue warps x 2 x 4 KB store staging (1024-byte aligned)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 32768);
+    uint8_t* stage_out = base + NST * STAGE_BYTES;                 // 8 epilogue warps x 2 KB store staging (1024-byte aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 16384);
     uint64_t* full = bars; uint64_t* empty = bars + NST;
     uint64_t* tmem_full = bars + 2 * NST; uint64_t* tmem_empty = bars + 2 * NST + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
-    float* epi_params = reinterpret_cast<float*>(bars + 16);      // [4 epilogue warps][bias | scale | shift][32]
+    float* epi_params = reinterpret_cast<float*>(bars + 16);      // [8 epilogue warps][bias | scale | shift][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + QBM - 1) / QBM;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) PROBE(0);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                 const int s = g % NST, it = g / NST;
                 mbar_wait(&full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (g == 0) PROBE(1);
                 if (lane == 0) {
                     const uint32_t sa_hi = smem_u32(a_hi(s)), sb_hi = smem_u32(b_hi(s));
                     const uint32_t sa_lo = smem_u32(a_lo(s)), sb_lo = smem_u32(b_lo(s));
@@ -185,39 +189,56 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                 }
                 __syncwarp();
             }
+            PROBE(use == 0 ? 2 : 3);
             ++use;
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-        // A thread owns one accumulator row (tcgen05.ld 32x32b), so direct global stores would touch 32 different lines per
-        // instruction.  Each warp instead stages its 32 x 32 chunk in shared memory (swizzled, conflict-free) and one lane hands
-        // it to the TMA store unit; two 4 KB staging buffers per warp alternate so a store drains while the next chunk is built.
-        const int q = warp & 3;
-        uint8_t* stg = stage_out + (warp - 2) * 8192;
-        int nuse = 0, use = 0;
-        auto acquire = [&]() -> uint8_t* {
-            if (lane == 0) bulk_wait_read<1>();                   // the store issued two uses ago has finished reading its buffer
-            __syncwarp();
-            uint8_t* p = stg + (nuse & 1) * 4096;
-            ++nuse;
-            return p;
-        };
-        auto put_f32 = [&](uint8_t* p, const uint32_t (&x)[32]) {     // [32 rows][32 floats], 128-byte swizzle, lane = row
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(p + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-        };
-        auto put_bf16 = [&](uint8_t* p, const uint32_t (&x)[16]) {    // [32 rows][32 bf16], 64-byte swizzle, lane = row
+        // ------------------------------------------------------------------ epilogue: warps 2..9
+        // TMEM lane quarter = warp % 4 (hardware rule), so two warps share a quarter and split the tile's columns in halves.
+        // A thread owns one accumulator row (tcgen05.ld 32x32b); storing straight from registers would touch 32 different
+        // 128-byte lines per instruction, so every 32-row x 64-byte piece goes through a 2 KB swizzled (conflict-free) staging
+        // tile: lane = row writes it, then 4 lanes x 16 B cover a row and one store instruction writes 8 rows — whole sectors,
+        // fire-and-forget.  (A TMA-store epilogue was measured no faster; the epilogue is bound by its instruction count, hence
+        // eight warps, packed bf16 conversions and a predicate-free relu path.)
+        const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+        uint8_t* stg = stage_out + ew * 2048;
+        int use = 0;
+        auto put64 = [&](const uint32_t* x) {                         // 16 words per lane -> [32 rows][64 B], 64-byte swizzle
+            __syncwarp();                                             // earlier readers of the staging tile are done
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(p + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            __syncwarp();
+        };
+        // rows [mw, mw + 32) of a row-major matrix, 64 bytes per row starting at dst (byte pointer of row mw); accumulate: fp32 +=
+        auto flush64 = [&](uint8_t* __restrict__ dst, int64_t ld_bytes, int mw, bool accumulate) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + (lane >> 2), c = lane & 3;
+                uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                if (mw + r < M) {
+                    uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
+                    if (accumulate) {
+                        const uint4 p = *g;
+                        v4.x = __float_as_uint(__uint_as_float(v4.x) + __uint_as_float(p.x)); v4.y = __float_as_uint(__uint_as_float(v4.y) + __uint_as_float(p.y));
+                        v4.z = __float_as_uint(__uint_as_float(v4.z) + __uint_as_float(p.z)); v4.w = __float_as_uint(__uint_as_float(v4.w) + __uint_as_float(p.w));
+                    }
+                    *g = v4;
+                }
+            }
+        };
+        auto store_f32 = [&](float* __restrict__ dst, int64_t ld, int mw, int nb, const uint32_t* x, bool accumulate) {   // 32 x 32 fp32
+            uint8_t* d = reinterpret_cast<uint8_t*>(dst + (int64_t)mw * ld + nb);
+            put64(x); flush64(d, ld * 4, mw, accumulate);
+            put64(x + 16); flush64(d + 64, ld * 4, mw, accumulate);
         };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int m0, n0, z, kbeg, nkb;
             tile_range(tile, m0, n0, z, kbeg, nkb);
-            const int mw = m0 + q * 32;                        // first row of this warp's chunk
+            const int mw = m0 + q * 32;                        // first row of this warp's chunks
             const int m = mw + lane;
             const int a = use & 1, au = use >> 1;
+            const int c_beg = half * (TBN / 64), c_end = c_beg + TBN / 64;
             // bias / BN scale / BN shift of column nb + lane: fetched one chunk ahead (the first chunk's before the wait for the
             // accumulator), so their global-load latency never sits on the epilogue's critical path
             float pb = 0.f, pg = 1.f, pe = 0.f;
@@ -228,17 +249,18 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                 g_ = (in && ep.bn) ? ep.gamma[gn] * 0.99950037468777f : 1.f;
                 e_ = (in && ep.bn) ? ep.beta[gn] : 0.f;
             };
-            if (MODE == EPI_FWD) load_params(n0, pb, pg, pe);
+            if (MODE == EPI_FWD && n0 + c_beg * 32 < N) load_params(n0 + c_beg * 32, pb, pg, pe);
             if (nkb > 0) {
                 mbar_wait(&tmem_full[a], au & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+            if (ew == 0) PROBE(use == 0 ? 4 : 6);
 #pragma unroll 1
-            for (int c = 0; c < TBN / 32; ++c) {
+            for (int c = c_beg; c < c_end; ++c) {
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;
                 float qb = 0.f, qg = 1.f, qe = 0.f;
-                if (MODE == EPI_FWD && c + 1 < TBN / 32 && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
+                if (MODE == EPI_FWD && c + 1 < c_end && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
                 uint32_t v[32];
                 if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TBN + c * 32), v);
                 else {
@@ -246,90 +268,83 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
                 if (MODE == EPI_FWD) {
-                    float* wp = epi_params + (warp - 2) * 96;
+                    float* wp = epi_params + ew * 96;
+                    __syncwarp();
                     wp[lane] = pb; wp[32 + lane] = pg; wp[64 + lane] = pe;
                     pb = qb; pg = qg; pe = qe;
                     __syncwarp();
                     uint32_t h[32];
                     const bool rv = m < ep.m_valid;
-                    if (ep.act == WD_ACT_RELU) {                      // warp-uniform fast path
+                    if (ep.act == WD_ACT_RELU) {
+                        // warp-uniform fast path, no per-column predicate: padded columns have zero weights, bias 0, scale 1,
+                        // shift 0, and relu(0) = 0 keeps them zero
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const bool ok = rv && (nb + j) < ep.n_logical;
-                            const float av = ok ? fmaxf(__uint_as_float(v[j]) + wp[j], 0.f) : 0.f;
-                            v[j] = __float_as_uint(av);
-                            h[j] = __float_as_uint(ok ? fmaf(av, wp[32 + j], wp[64 + j]) : 0.f);
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(wp + 4 * j4);
+                            const float4 g4 = *reinterpret_cast<const float4*>(wp + 32 + 4 * j4);
+                            const float4 e4 = *reinterpret_cast<const float4*>(wp + 64 + 4 * j4);
+                            const float a0 = fmaxf(__uint_as_float(v[4 * j4]) + b4.x, 0.f), a1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b4.y, 0.f);
+                            const float a2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f), a3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
+                            v[4 * j4] = __float_as_uint(a0); v[4 * j4 + 1] = __float_as_uint(a1); v[4 * j4 + 2] = __float_as_uint(a2); v[4 * j4 + 3] = __float_as_uint(a3);
+                            h[4 * j4] = __float_as_uint(fmaf(a0, g4.x, e4.x)); h[4 * j4 + 1] = __float_as_uint(fmaf(a1, g4.y, e4.y));
+                            h[4 * j4 + 2] = __float_as_uint(fmaf(a2, g4.z, e4.z)); h[4 * j4 + 3] = __float_as_uint(fmaf(a3, g4.w, e4.w));
+                        }
+                        if (nb + 32 > ep.n_logical) {                 // chunk straddling the logical width: BN shift must not leak into padding
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nb + j >= ep.n_logical) { v[j] = 0u; h[j] = 0u; }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const bool ok = rv && (nb + j) < ep.n_logical;
+                            const bool ok = (nb + j) < ep.n_logical;
                             const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + wp[j]) : 0.f;
                             v[j] = __float_as_uint(av);
                             h[j] = __float_as_uint(ok ? fmaf(av, wp[32 + j], wp[64 + j]) : 0.f);
                         }
                     }
-                    __syncwarp();
-                    if (ep.A_out != ep.H_out) {
-                        uint8_t* p = acquire();
-                        put_f32(p, v);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) { tma_store_3d(&maps.o_a, p, nb, mw, 0); bulk_commit(); }
+                    if (!rv) {                                        // rows past the batch: zeros (only in the last row tile)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = 0u; h[j] = 0u; }
                     }
-                    if (ep.H_out) {                                    // fp32 copy only where something reads it (logits layer)
-                        uint8_t* p = acquire();
-                        put_f32(p, h);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) { tma_store_3d(&maps.o_h, p, nb, mw, 0); bulk_commit(); }
-                    }
+                    if (ep.A_out != ep.H_out) store_f32(ep.A_out, ep.ldh, mw, nb, v, false);
+                    if (ep.H_out) store_f32(ep.H_out, ep.ldh, mw, nb, h, false);      // fp32 copy only where something reads it
                     uint32_t hh[16], hl[16];                           // packed bf16 pairs of the hi / lo copies
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(__uint_as_float(h[2 * j]), h0, l0);
-                        split_bf16(__uint_as_float(h[2 * j + 1]), h1, l1);
-                        hh[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        hl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        const float x0 = __uint_as_float(h[2 * j]), x1 = __uint_as_float(h[2 * j + 1]);
+                        const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+                        const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xFFFF0000u));
+                        hh[j] = hb;
+                        hl[j] = *reinterpret_cast<const uint32_t*>(&lp);
                     }
-                    {
-                        uint8_t* p = acquire();
-                        put_bf16(p, hh);
-                        put_bf16(p + 2048, hl);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) { tma_store_3d(&maps.o_hs_hi, p, nb, mw, 0); tma_store_3d(&maps.o_hs_lo, p + 2048, nb, mw, 0); bulk_commit(); }
-                    }
+                    uint8_t* dh = reinterpret_cast<uint8_t*>(ep.Hs_hi + (int64_t)mw * ep.ldh + nb);
+                    uint8_t* dl = reinterpret_cast<uint8_t*>(ep.Hs_lo + (int64_t)mw * ep.ldh + nb);
+                    put64(hh); flush64(dh, (int64_t)ep.ldh * 2, mw, false);
+                    put64(hl); flush64(dl, (int64_t)ep.ldh * 2, mw, false);
                 } else {
-                    uint8_t* p = acquire();
-                    put_f32(p, v);
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (MODE == EPI_STORE && ep.accumulate) tma_reduce_add_3d(&maps.o_c, p, nb, mw, 0);
-                        else tma_store_3d(&maps.o_c, p, nb, mw, MODE == EPI_WGRAD ? z : 0);
-                        bulk_commit();
-                    }
+                    store_f32(ep.C + (MODE == EPI_WGRAD ? (int64_t)z * ep.split_stride : 0), ep.ldc, mw, nb, v, MODE == EPI_STORE && ep.accumulate);
                 }
             }
             if (nkb > 0) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&tmem_empty[a]);                   // accumulator buffer a may be overwritten
+                if (ew == 0) PROBE(use == 0 ? 5 : 7);
                 ++use;
             }
         }
-        if (lane == 0) bulk_wait_all();                        // every store has landed before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * TBN)));
 }
 
+int g_probe_slot = 0;
+
 template <int TBN, int MODE>
 int launch_q(WdModel* m, const QMaps& maps, const QSegs& segs, int M, int N, int ktot, int splits, int ksplit_len, const Epi& ep) {
     constexpr int NST = TBN == 256 ? 2 : 3;
-    constexpr int smem = NST * 2 * (QBM * 128 + TBN * 128) + 32768 + 1024 + 128 + 1536;
+    constexpr int smem = NST * 2 * (QBM * 128 + TBN * 128) + 16384 + 1024 + 128 + 3072;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
@@ -339,13 +354,23 @@ int launch_q(WdModel* m, const QMaps& maps, const QSegs& segs, int M, int N, int
     }
     const int nsplit = MODE == EPI_WGRAD ? splits : 1;
     const int ntiles = ((N + TBN - 1) / TBN) * ((M + QBM - 1) / QBM) * nsplit;
-    tc_gemm_bf16_kernel<TBN, MODE><<<ntiles < num_sms ? ntiles : num_sms, Q_THREADS, smem, m->stream>>>(maps, segs, M, N, ktot, ksplit_len, nsplit, ep);
+    static const bool probe_on = getenv("WD_GEMM_PROBE") != nullptr;
+    const int probe = probe_on ? (g_probe_slot++ & 31) : -1;
+    tc_gemm_bf16_kernel<TBN, MODE><<<ntiles < num_sms ? ntiles : num_sms, Q_THREADS, smem, m->stream>>>(maps, segs, M, N, ktot, ksplit_len, nsplit, ep, probe);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
 
 }  // namespace
+
+// debugging aid (not part of the public header): copies the probe stamps of the last 32 launches, resets the slot counter
+extern "C" int wd_debug_gemm_probe(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_probe, sizeof(unsigned long long) * 32 * 8);
+    g_probe_slot = 0;
+    return e == cudaSuccess ? 0 : -1;
+}
 
 // whether the engine uses 128 x 256 output tiles for this problem (also consulted when the split-K factor is chosen)
 bool tc_bf16_wide_tile(int mode, int M, int N, int splits, int num_sms) {
@@ -392,19 +417,7 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
         if ((rc = tc_make_map_bf16(&maps.b_lo, B_lo, ktot, N, ldb, 64))) return rc;
     }
     if (mode == EPI_WGRAD) ksplit_len = (ksplit_len + QBK - 1) / QBK * QBK;
-    if (mode == EPI_FWD) {
-        if (!ep.Hs_hi || !ep.Hs_lo) { set_error("bf16 GEMM engine: forward without hi/lo outputs"); return WD_EINVAL; }
-        if ((rc = tc_make_map_out(&maps.o_hs_hi, ep.Hs_hi, 2, M, N, ep.ldh, 1, 0, 32, 32, 1))) return rc;
-        if ((rc = tc_make_map_out(&maps.o_hs_lo, ep.Hs_lo, 2, M, N, ep.ldh, 1, 0, 32, 32, 1))) return rc;
-        if (ep.H_out) { if ((rc = tc_make_map_out(&maps.o_h, ep.H_out, 4, M, N, ep.ldh, 1, 0, 32, 32, 2))) return rc; }
-        else maps.o_h = maps.o_hs_hi;
-        if (ep.A_out != ep.H_out) { if ((rc = tc_make_map_out(&maps.o_a, ep.A_out, 4, M, N, ep.ldh, 1, 0, 32, 32, 2))) return rc; }
-        else maps.o_a = maps.o_h;
-        maps.o_c = maps.o_hs_hi;
-    } else {
-        if ((rc = tc_make_map_out(&maps.o_c, ep.C, 4, M, N, ep.ldc, mode == EPI_WGRAD ? splits : 1, ep.split_stride, 32, 32, 2))) return rc;
-        maps.o_a = maps.o_h = maps.o_hs_hi = maps.o_hs_lo = maps.o_c;
-    }
+    if (mode == EPI_FWD && (!ep.Hs_hi || !ep.Hs_lo)) { set_error("bf16 GEMM engine: forward without hi/lo outputs"); return WD_EINVAL; }
 #define WD_Q_LAUNCH(MODE_) \
     return wide ? launch_q<256, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep) : launch_q<128, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep)
     if (mode == EPI_FWD) { WD_Q_LAUNCH(EPI_FWD); }

@@ -21,6 +21,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
@@ -483,8 +486,45 @@ static int get_encode() {
     return WD_OK;
 }
 
+// Encoded tensor maps are cached by (base, shape, pitch, box, element size): a train step re-creates the same ~100 maps every
+// time, and cuTensorMapEncodeTiled costs about a microsecond each on the launching thread — which matters wherever steps are
+// launched eagerly (data-parallel steps, profiling), not replayed from a CUDA graph.
+struct MapKey {
+    const void* p; int rows, cols, ld, box_rows, esize;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && esize == o.esize; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.p * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)(uint32_t)k.rows << 32 | (uint32_t)k.cols) * 0xC2B2AE3D27D4EB4Full;
+        h ^= ((uint64_t)(uint32_t)k.ld << 20 | (uint64_t)(uint32_t)k.box_rows << 4 | (uint32_t)k.esize) * 0x165667B19E3779F9ull;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+static bool map_cache_get(const MapKey& k, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(k);
+    if (it == g_map_cache.end()) return false;
+    *out = it->second;
+    return true;
+}
+static void map_cache_put(const MapKey& k, const CUtensorMap& v) {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    if (g_map_cache.size() > 4096) g_map_cache.clear();          // models come and go (tests): keep the table bounded
+    g_map_cache[k] = v;
+}
+// a freed model's buffers may be handed out again with another shape: drop every cached map when a model dies
+void tc_map_cache_clear() {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    g_map_cache.clear();
+}
+
 // row-major fp32 matrix [rows, cols] with leading dimension ld (floats); box = 32 floats x box_rows, 128B swizzle
 static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+    const MapKey key{ptr, rows, cols, ld, box_rows, 4};
+    if (map_cache_get(key, map)) return WD_OK;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
@@ -493,6 +533,7 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return WD_ECUDA; }
+    map_cache_put(key, *map);
     return WD_OK;
 }
 
@@ -500,6 +541,8 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
 int tc_make_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
     int rc = get_encode();
     if (rc) return rc;
+    const MapKey key{ptr, rows, cols, ld, box_rows, 2};
+    if (map_cache_get(key, map)) return WD_OK;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
@@ -508,28 +551,7 @@ int tc_make_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int 
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(bf16) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return WD_ECUDA; }
-    return WD_OK;
-}
-
-// output tile map for the TMA-store epilogue: [nz][rows][cols] elements of `esize` bytes, row pitch ld, plane pitch zstride
-// (elements); box = box_cols x box_rows x 1; swizzle: 0 none, 1 = 64 B, 2 = 128 B
-int tc_make_map_out(CUtensorMap* map, const void* ptr, int esize, int rows, int cols, int64_t ld, int nz, int64_t zstride,
-                    int box_cols, int box_rows, int swizzle) {
-    int rc = get_encode();
-    if (rc) return rc;
-    if (((uintptr_t)ptr & 15) || (ld * esize) % 16 || (nz > 1 && (zstride * esize) % 16)) {
-        set_error("output tile map: base / pitch not 16-byte aligned (ld=%lld zstride=%lld)", (long long)ld, (long long)zstride);
-        return WD_EINVAL;
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(nz > 0 ? nz : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)(nz > 1 ? zstride : (int64_t)ld * rows) * esize};
-    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims,
-                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%d cols=%d ld=%lld", (int)r, rows, cols, (long long)ld); return WD_ECUDA; }
+    map_cache_put(key, *map);
     return WD_OK;
 }
 
