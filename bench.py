@@ -140,6 +140,9 @@ def config_dict(n_gpus, per_gpu_batch):
             "global_batch": per_gpu_batch * n_gpus, "per_gpu_batch": per_gpu_batch,
             "parallelism": "dp%d" % n_gpus if n_gpus > 1 else "single",
             "tables": "replicated", "ids": "uniform",
+            "exchange": ("dense all-reduce of MLP/wide-bias gradients + gradient blocks of tables <= %s rows; all-gather + on-device "
+                         "re-reduction of (row, gradient) lists for the larger tables" % os.environ.get("WD_DENSE_EXCHANGE_ROWS", "16384"))
+            if n_gpus > 1 else "none",
             "l2": "ring of %d distinct resident batches; touched rows per step ~60 MB, tables 8.6 GB >> 126 MB L2" % RING}
 
 
@@ -259,14 +262,17 @@ def main():
     B = args.batch
     fc, cross, model_conf, emb, n_cat, n_dense, P = workload(world, B)
     n_cols = n_cat + n_dense + len(cross)
+    # data-parallel runs: tables / wide columns of <= 16384 rows (18 of the 26 embedding tables, 31 of the 47 wide columns) are
+    # exchanged as a dense gradient block inside the dense all-reduce; only the large tables' touched rows travel as lists
+    dense_rows = int(os.environ.get("WD_DENSE_EXCHANGE_ROWS", "16384")) if world > 1 else 0
     plan = Plan(fc, cross, model_conf, "wide_deep", max_batch=B, embedding_dim_override=emb, gemm_engine=args.engine,
-                max_nnz=B * n_cols * (world if world > 1 else 1), max_keys=B * n_cat)
+                max_nnz=B * n_cols * (world if world > 1 else 1), max_keys=B * n_cat, dense_exchange_max_rows=dense_rows)
     model = WideDeepModel(plan, device=local)
     model.init(seed=0x5EED0005)          # identical replicas on every rank
     trainer = None
     if world > 1:
         from wide_deep_b200.parallel import DataParallelTrainer
-        trainer = DataParallelTrainer(model, fixed_rows=(B * n_cat, B * n_cols))
+        trainer = DataParallelTrainer(model, fixed_rows=plan.exchange_rows(B))
 
     # distinct batches per (rank, ring slot) in pinned host memory
     host = []
@@ -327,6 +333,14 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
+
+    if trainer and os.environ.get("WD_DP_PROFILE") and rank == 0:
+        for i in range(3):
+            prof = trainer.profile_step(i % RING)
+        sys.stderr.write("dp phases (ms from step start): %s\n" % json.dumps({k: round(v, 3) for k, v in prof.items()}))
+    elif trainer and os.environ.get("WD_DP_PROFILE"):
+        for i in range(3):
+            trainer.profile_step(i % RING)
 
     # per-kernel timings (CUDA events between stages on the model stream), a few profiled steps
     phases = {}

@@ -96,6 +96,14 @@ typedef struct WdPlanDesc {
     int64_t max_nnz;                /* upper bound on categorical-column ids per step (0: derive) */
     int64_t max_keys;               /* upper bound on batch keys per step (0: derive) */
     int32_t gemm_engine;            /* WD_GEMM_* */
+    /* Data-parallel exchange format.  Embedding tables / wide columns with at most this many rows ("small") are laid out after
+     * the large ones in the global row space and their per-step gradient leaves as a DENSE block appended to the dense gradient
+     * arena (wd_dense_grad_ptr / wd_dense_grad_count: one all-reduce covers it), not as (row, gradient) list entries; only the
+     * large tables' touched rows go through wd_sparse_grads / wd_sparse_set.  0 = every table uses the list (default).
+     * wide_small_base = first wide row of the small wide columns (= wide_rows when there is none); the plan orders the wide
+     * columns large-first. */
+    int64_t dense_exchange_max_rows;
+    int64_t wide_small_base;
 } WdPlanDesc;
 
 /* One batch in HOST memory (pinned for async copies).  Replaces the feature dict produced by input_fn
@@ -165,6 +173,12 @@ void *wd_dense_grad_ptr(WdModel *m);          /* device pointer */
 int wd_sparse_grads(WdModel *m, int which, void **rows, void **grads, int64_t *n, int32_t *width, int64_t *capacity);
 /* Replace the sparse gradient list by a merged one (rows need not be unique or sorted). */
 int wd_sparse_set(WdModel *m, int which, const void *rows_dev, const void *grads_dev, int64_t n);
+/* Same, for the concatenation of n_lists lists of list_len rows each that are individually sorted ascending, duplicate-free
+ * and padded with 0xFFFFFFFF — exactly what a fixed-size all-gather of wd_sparse_grads' buffers yields.  Merged without a
+ * sort (one binary search per list and element); duplicates across lists are summed in list order.  With the same buffers
+ * every step the merge is replayed from a CUDA graph.  (Replaces the push of sparse updates to the parameter servers,
+ * reference python/train.py:197-217.) */
+int wd_sparse_set_sorted(WdModel *m, int which, const void *rows_dev, const void *grads_dev, int32_t n_lists, int64_t list_len);
 
 /* Streaming eval metrics (binary head, reference joint.py:402-406): accumulate per batch, then finish.
  * out[0..9] = accuracy, accuracy_baseline, auc, auc_precision_recall, average_loss, label/mean, loss,

@@ -25,23 +25,32 @@ def main():
     fc, cross, model = small_conf(hidden=(64, 32))
     B = 96 * world
     om = OM.OracleModel(fc, cross, model, "wide_deep").init(5)
-    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64 * world, max_keys=B * 64)
+    # WD_DP_DENSE: tables / wide columns of <= 1000 rows travel as a dense block inside the dense all-reduce, the rest as lists
+    dense_rows = 1000 if os.environ.get("WD_DP_DENSE") else 0
+    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64 * world, max_keys=B * 64, dense_exchange_max_rows=dense_rows)
+    plan_list = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64 * world, max_keys=B * 64)
     pm = WideDeepModel(plan, device=local)
     copy_params_to_product(om, pm)
     fixed = (96 * 64, 96 * 64) if os.environ.get("WD_DP_FIXED") else None
     trainer = DataParallelTrainer(pm, fixed_rows=fixed)
     single = None
     if rank == 0:
-        single = WideDeepModel(plan, device=local)
+        single = WideDeepModel(plan_list, device=local)     # reference: one GPU, whole batch, plain list path
         copy_params_to_product(om, single)
+    use_slot = bool(os.environ.get("WD_DP_SLOT"))           # resident-slot steps: forward+backward replayed from a CUDA graph
     rng = np.random.default_rng(77)
-    for step in range(3):
+    for step in range(6 if use_slot else 3):
         raw = random_raw_batch(fc, B, rng)
         label = (rng.random(B) < 0.3).astype(np.float32)
         lo, hi = shard_rows(B, rank, world)
-        trainer.step(to_product_batch(plan, slice_raw(raw, lo, hi), label[lo:hi]))
+        shard = to_product_batch(plan, slice_raw(raw, lo, hi), label[lo:hi])
+        if use_slot:
+            pm.upload_slot(0, shard)
+            trainer.step_slot(0)
+        else:
+            trainer.step(shard)
         if single is not None:
-            single.train_step(to_product_batch(plan, raw, label))
+            single.train_step(to_product_batch(plan_list, raw, label))
     pm.sync()
     ok = True
     if rank == 0:

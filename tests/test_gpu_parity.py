@@ -40,10 +40,11 @@ def small_conf(hidden=(64, 32), mode="simple", act="relu", bn=1, dnn_opt="Adagra
     return fc, cross, model
 
 
-def build_pair(fc, cross, model, model_type="wide_deep", B=96, seed=0, tf_compat_pad=False, emb_dim=None, max_batch=None):
+def build_pair(fc, cross, model, model_type="wide_deep", B=96, seed=0, tf_compat_pad=False, emb_dim=None, max_batch=None, dense_rows=0):
     om = OM.OracleModel(fc, cross, model, model_type, embedding_dim_override=emb_dim, tf_compat_pad=tf_compat_pad).init(seed)
     plan = Plan(fc, cross, model, model_type, max_batch=max_batch or B, embedding_dim_override=emb_dim,
-                tf_compat_pad=tf_compat_pad, max_nnz=(max_batch or B) * 64, max_keys=(max_batch or B) * 64, gemm_engine="ffma")
+                tf_compat_pad=tf_compat_pad, max_nnz=(max_batch or B) * 64, max_keys=(max_batch or B) * 64, gemm_engine="ffma",
+                dense_exchange_max_rows=dense_rows)
     pm = WideDeepModel(plan)
     copy_params_to_product(om, pm)
     return om, plan, pm
@@ -142,9 +143,9 @@ def test_weighted_examples_and_ragged_batch():
     _train_compare(fc, cross, model, "wide_deep", steps=2, seed=17, weighted=True, B=77, max_batch=128)
 
 
-def _train_compare(fc, cross, model, model_type, steps, seed, weighted=False, B=160, max_batch=None):
+def _train_compare(fc, cross, model, model_type, steps, seed, weighted=False, B=160, max_batch=None, dense_rows=0):
     rng = np.random.default_rng(seed)
-    om, plan, pm = build_pair(fc, cross, model, model_type, B=B, seed=seed, max_batch=max_batch)
+    om, plan, pm = build_pair(fc, cross, model, model_type, B=B, seed=seed, max_batch=max_batch, dense_rows=dense_rows)
     for step in range(steps):
         raw = random_raw_batch(fc, B, rng)
         label = (rng.random(B) < 0.3).astype(np.float32)
@@ -167,6 +168,15 @@ def _train_compare(fc, cross, model, model_type, steps, seed, weighted=False, B=
     logits, _ = pm.forward(to_product_batch(plan, raw, label))
     _, cache = om.forward(raw)
     np.testing.assert_array_less(np.abs(logits - cache["logits"]), 5 * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+
+
+@pytest.mark.parametrize("model_type,dense_rows", [("wide_deep", 1000), ("wide_deep", 10 ** 9), ("wide", 500), ("deep", 1000)])
+def test_dense_exchange_of_small_tables(model_type, dense_rows):
+    """dense_exchange_max_rows: tables / wide columns up to that size live at the end of the row space; their summed gradients
+    leave the (row, gradient) lists for a dense block (what data-parallel runs all-reduce) and are applied from it.  Same results
+    as the list path, checked against the oracle on one GPU (10**9: every table takes the dense route)."""
+    fc, cross, model = small_conf()
+    _train_compare(fc, cross, model, model_type, steps=3, seed=29, dense_rows=dense_rows)
 
 
 def test_run_to_run_bit_reproducible():

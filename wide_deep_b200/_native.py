@@ -56,6 +56,7 @@ SYMBOLS = {
     "wd_sparse_grads": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_i64),
                                        ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
     "wd_sparse_set": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _i64]),
+    "wd_sparse_set_sorted": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int32, _i64]),
     "wd_eval_reset": (ctypes.c_int, [_vp]),
     "wd_eval_accumulate": (ctypes.c_int, [_vp, _vp]),
     "wd_eval_finish": (ctypes.c_int, [_vp, _vp]),

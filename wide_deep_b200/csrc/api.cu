@@ -101,7 +101,9 @@ extern "C" int wd_model_destroy(WdModel* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     tc_map_cache_clear();
-    for (auto& sl : m->slots) if (sl.graph) cudaGraphExecDestroy(sl.graph);
+    for (auto& sl : m->slots) { if (sl.graph) cudaGraphExecDestroy(sl.graph); if (sl.graph_bwd) cudaGraphExecDestroy(sl.graph_bwd); }
+    for (auto& g : m->merge_graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (m->ev_bwd_done) cudaEventDestroy(m->ev_bwd_done);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
     for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
@@ -155,6 +157,8 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     m->ldt = m->max_batch_pad;
     m->row_tiles = m->max_batch_pad / 128;
     m->gemm_engine = d->gemm_engine == WD_GEMM_AUTO ? WD_GEMM_TC3X : d->gemm_engine;
+    m->dense_exchange_max_rows = d->dense_exchange_max_rows > 0 ? d->dense_exchange_max_rows : 0;
+    m->small_base[1] = (m->dense_exchange_max_rows > 0 && d->wide_small_base >= 0 && d->wide_small_base <= d->wide_rows) ? d->wide_small_base : d->wide_rows;
     m->max_nnz = d->max_nnz > 0 ? d->max_nnz : (int64_t)d->max_batch * std::max(C, 1) * 2;
     m->keys_cap = d->max_keys > 0 ? d->max_keys : (int64_t)d->max_batch * std::max(d->n_cat_fields, 1) * 4;
     if (m->lin_opt.kind == WD_OPT_FTRL && m->lin_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
@@ -250,16 +254,47 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             tb.rows = d->table_rows[t]; tb.dim = d->table_dim[t]; tb.x0_off = d->table_x0_off[t];
             tb.dim_logical = d->table_dim_logical[t];
             if (tb.dim_logical < 1 || tb.dim_logical > tb.dim) { set_error("table %d: bad logical width", t); return WD_EINVAL; }
-            tb.row_base = row_base; tb.stride = tb.dim * (1 + nslots); tb.col = -1;
+            tb.row_base = 0; tb.stride = tb.dim * (1 + nslots); tb.col = -1;
             if (tb.dim % 4 || tb.x0_off % 4) { set_error("table %d: dim and deep-input offset must be multiples of 4", t); return WD_EINVAL; }
             for (int c = 0; c < C; ++c) if (d->col_emb_table[c] == t) tb.col = c;
             if (tb.col < 0) { set_error("table %d has no producing column", t); return WD_EINVAL; }
             if ((rc = dev_alloc(m, &tb.data, tb.rows * tb.stride, true))) return rc;
             for (int i = 0; i < tb.dim_logical; ++i) x->x0_real[tb.x0_off + i] = 1;
-            h_row_base.push_back(row_base);
-            row_base += tb.rows;
             m->emb_max_dim = std::max(m->emb_max_dim, tb.dim);
             m->tables.push_back(tb);
+        }
+        // global row space: large tables first, then the small (dense-exchanged) ones, each group in table order
+        std::vector<int> row_order;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) m->small_base[0] = row_base;
+            for (int t = 0; t < d->n_tables; ++t) {
+                const bool small = m->dense_exchange_max_rows > 0 && m->tables[t].rows <= m->dense_exchange_max_rows;
+                if (small != (pass == 1)) continue;
+                if (small) m->n_small_tab++;
+                m->tables[t].row_base = row_base;
+                row_base += m->tables[t].rows;
+                row_order.push_back(t);
+            }
+        }
+        for (int t = 0; t < d->n_tables; ++t) h_row_base.push_back(m->tables[t].row_base);
+        {
+            std::vector<int64_t> rb, go; std::vector<float*> dt; std::vector<int32_t> dm, st;
+            int64_t off = 0;
+            for (int t : row_order) {
+                const EmbTable& tb = m->tables[t];
+                const bool small = m->dense_exchange_max_rows > 0 && tb.rows <= m->dense_exchange_max_rows;
+                rb.push_back(tb.row_base); dt.push_back(tb.data); dm.push_back(tb.dim); st.push_back(tb.stride);
+                go.push_back(small ? off : -1);
+                if (small) off += tb.rows * tb.dim;
+            }
+            m->gs_emb_floats = off;
+            m->n_rtab = (int)row_order.size();
+            { const int64_t* t_; if ((rc = upload_vec(m, rb.data(), m->n_rtab, &t_))) return rc; m->d_rtab_row_base = (int64_t*)t_; }
+            { const int64_t* t_; if ((rc = upload_vec(m, go.data(), m->n_rtab, &t_))) return rc; m->d_rtab_gs_off = (int64_t*)t_; }
+            { float* const* t_; if ((rc = upload_vec<float*>(m, dt.data(), m->n_rtab, (float* const**)&t_))) return rc; m->d_rtab_data = (float**)t_; }
+            { const int32_t* t_;
+              if ((rc = upload_vec(m, dm.data(), m->n_rtab, &t_))) return rc; m->d_rtab_dim = (int32_t*)t_;
+              if ((rc = upload_vec(m, st.data(), m->n_rtab, &t_))) return rc; m->d_rtab_stride = (int32_t*)t_; }
         }
         m->emb_total_rows = row_base;
         if (row_base >= (1ll << 31)) { set_error("more than 2^31 embedding rows on one device"); return WD_EUNSUPPORTED; }
@@ -383,11 +418,12 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             m->towers.push_back(tw);
         }
     }
+    m->gs_count = m->gs_emb_floats + (m->use_wide ? m->wide_rows - m->small_base[1] : 0);
     if (m->dense_count > 0) {
         if ((rc = dev_alloc(m, &m->d_P, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_S1, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_S2, m->dense_count))) return rc;
-        if ((rc = dev_alloc(m, &m->d_G, m->dense_count))) return rc;
+        if ((rc = dev_alloc(m, &m->d_G, m->dense_count + m->gs_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_gpart, m->gpart_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_Wt, std::max<int64_t>(m->wt_count, 1)))) return rc;
         if ((rc = dev_alloc(m, &m->d_Wsplit, std::max<int64_t>(4 * m->wt_count, 1)))) return rc;
@@ -410,6 +446,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_ustart[w], m->max_nnz + 8))) return rc;
         if ((rc = dev_alloc(m, &m->d_ugrad[w], (m->max_nnz + 8) * (w == 0 ? std::max(m->emb_max_dim, 4) : 1)))) return rc;
         if ((rc = dev_alloc(m, &m->d_nuniq[w], 4))) return rc;
+        if ((rc = dev_alloc(m, &m->d_nubig[w], 4))) return rc;
         if ((rc = dev_alloc(m, &m->d_nvalid[w], 4))) return rc;
         m->cpart_cap = 2 * (m->max_nnz / 16) + 64;        // kChunk = 16 (sparse.cu)
         if ((rc = dev_alloc(m, &m->d_choff[w], m->max_nnz + 8))) return rc;
@@ -451,6 +488,7 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_dx0, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_bwd_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); wd_model_destroy(m); return WD_ECUDA; }
     m->graphs_enabled = getenv("WD_NO_GRAPH") == nullptr;
     int rc = build_model(d, m, x);
@@ -745,9 +783,11 @@ static int forward_core(WdModel* m, bool train) {
 static int backward_core(WdModel* m) {
     int rc;
     m->side_active[0] = m->side_active[1] = false;
+    if (m->gs_count > 0) WD_CUDA(cudaMemsetAsync(m->d_G + m->dense_count, 0, (size_t)m->gs_count * sizeof(float), m->stream));
     if (m->side_pending[1]) {
+        if (m->gs_count > 0) { WD_CUDA(cudaEventRecord(m->ev_head, m->stream)); }     // (re-recorded: also orders the memset above)
         WD_CUDA(cudaStreamWaitEvent(m->sstream[1], m->ev_head, 0));
-        if ((rc = on_side(m, 1, [&] { return sparse_reduce_wide(m); }))) return rc;
+        if ((rc = on_side(m, 1, [&] { int r = sparse_reduce_wide(m); return r ? r : small_scatter(m, 1); }))) return rc;
         m->side_active[1] = true;
     }
     m->record_dx0 = m->side_pending[0];
@@ -757,7 +797,7 @@ static int backward_core(WdModel* m) {
     mark(m, "mlp_other");
     if (m->side_pending[0] && m->dx0_recorded) {
         WD_CUDA(cudaStreamWaitEvent(m->sstream[0], m->ev_dx0, 0));
-        if ((rc = on_side(m, 0, [&] { return sparse_reduce_emb(m); }))) return rc;
+        if ((rc = on_side(m, 0, [&] { int r = sparse_reduce_emb(m); return r ? r : small_scatter(m, 0); }))) return rc;
         m->side_active[0] = true;
     }
     if ((rc = wide_bias_grad(m))) return rc;
@@ -769,7 +809,14 @@ static int backward_core(WdModel* m) {
         else if ((rc = sparse_group_which(m, w))) return rc;
         m->side_pending[w] = false;
         if ((rc = (w == 0 ? sparse_reduce_emb(m) : sparse_reduce_wide(m)))) return rc;
+        if ((rc = small_scatter(m, w))) return rc;
     }
+    if (m->gs_count > 0)                                    // the dense block is read (all-reduced) on the main stream
+        for (int w = 0; w < 2; ++w)
+            if (m->side_active[w]) {
+                WD_CUDA(cudaEventRecord(m->ev_done[w], m->sstream[w]));
+                WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0));
+            }
     m->grads_pending = true;
     return WD_OK;
 }
@@ -786,6 +833,7 @@ static int apply_core(WdModel* m) {
     }
     mark(m, "sparse_apply");
     if ((rc = dense_apply(m))) return rc;
+    if ((rc = small_apply(m))) return rc;
     mark(m, "dense_apply");
     for (int w = 0; w < 2; ++w)
         if (m->side_active[w]) { WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0)); m->side_active[w] = false; }
@@ -892,6 +940,24 @@ extern "C" int wd_forward(WdModel* m, const WdBatch* b, float* logits_out, float
 }
 
 
+// forward + backward of the current batch; `join` brings the side streams back into the main stream (needed to end a capture)
+static int backward_eager(WdModel* m, bool join) {
+    int rc;
+    if ((rc = forward_core(m, true))) return rc;
+    if ((rc = backward_core(m))) return rc;
+    if (join)
+        for (int w = 0; w < 2; ++w)
+            if (m->side_active[w]) {
+                WD_CUDA(cudaEventRecord(m->ev_done[w], m->sstream[w]));
+                WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0));
+            }
+    return WD_OK;
+}
+
+// Data-parallel steps run forward + backward, then the exchange (NCCL, outside the library), then merge + apply.  The first part
+// is ~65 launches on three streams: like the full step it is captured per batch slot after two eager runs and replayed.  Inside
+// the graph the streams overlap as in the eager schedule; after it the sparse lists continue on their side streams, which wait for
+// the graph through ev_bwd_done.
 extern "C" int wd_step_backward_slot(WdModel* m, int slot, float* loss_out) {
     int rc = check_ready(m);
     if (rc) return rc;
@@ -899,8 +965,51 @@ extern "C" int wd_step_backward_slot(WdModel* m, int slot, float* loss_out) {
     if (!m->slots[slot].filled) { set_error("batch slot %d was never uploaded", slot); return WD_ESTATE; }
     if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
     timer_begin(m);
-    if ((rc = forward_core(m, true))) return rc;
-    if ((rc = backward_core(m))) return rc;
+    BatchSlot& sl = m->slots[slot];
+    const bool can_graph = m->graphs_enabled && !m->timer.enabled;
+    auto after_graph = [&]() -> int {
+        WD_CUDA(cudaGraphLaunch(sl.graph_bwd, m->stream));
+        m->launches += sl.graph_bwd_launches;
+        WD_CUDA(cudaEventRecord(m->ev_bwd_done, m->stream));
+        for (int w = 0; w < 2; ++w) {
+            m->side_pending[w] = false;
+            m->side_active[w] = sl.bwd_side_active[w];
+            if (m->side_active[w]) WD_CUDA(cudaStreamWaitEvent(m->sstream[w], m->ev_bwd_done, 0));
+        }
+        m->grads_pending = true;
+        return WD_OK;
+    };
+    if (can_graph && sl.graph_bwd && same_view(sl.graph_bwd_view, m->dbatch)) {
+        if ((rc = after_graph())) return rc;
+    } else if (can_graph && sl.bwd_eager_steps >= 2) {
+        if (sl.graph_bwd) { cudaGraphExecDestroy(sl.graph_bwd); sl.graph_bwd = nullptr; }
+        const int64_t l0 = m->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = backward_eager(m, true);
+            cudaError_t e2 = cudaStreamEndCapture(m->stream, &g);
+            if (rc == WD_OK && e2 == cudaSuccess && g) e = cudaGraphInstantiate(&sl.graph_bwd, g, 0);
+            else e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
+            if (g) cudaGraphDestroy(g);
+        }
+        if (e != cudaSuccess || !sl.graph_bwd) {             // capture not possible here: stay eager for good
+            cudaGetLastError();
+            m->graphs_enabled = false;
+            sl.graph_bwd = nullptr;
+            m->side_pending[0] = m->side_pending[1] = m->side_active[0] = m->side_active[1] = false;
+            if ((rc = backward_eager(m, false))) return rc;
+        } else {
+            sl.graph_bwd_view = m->dbatch;
+            sl.graph_bwd_launches = m->launches - l0;
+            m->launches = l0;
+            sl.bwd_side_active[0] = m->side_active[0]; sl.bwd_side_active[1] = m->side_active[1];
+            if ((rc = after_graph())) return rc;
+        }
+    } else {
+        if ((rc = backward_eager(m, false))) return rc;
+        sl.bwd_eager_steps++;
+    }
     if (loss_out) return finish_step(m, loss_out, nullptr);
     return WD_OK;
 }
@@ -923,7 +1032,7 @@ extern "C" int wd_step_apply(WdModel* m) {
     return apply_core(m);
 }
 
-extern "C" int64_t wd_dense_grad_count(WdModel* m) { return m ? m->dense_count : 0; }
+extern "C" int64_t wd_dense_grad_count(WdModel* m) { return m ? m->dense_count + m->gs_count : 0; }
 extern "C" void* wd_dense_grad_ptr(WdModel* m) { return m ? m->d_G : nullptr; }
 
 extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads, int64_t* n, int32_t* width, int64_t* capacity) {
@@ -944,12 +1053,63 @@ extern "C" int wd_sparse_grads(WdModel* m, int which, void** rows, void** grads,
     return WD_OK;
 }
 
-extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int64_t n) {
+// n_lists = 0: general (unsorted) list of n rows; n_lists > 0: n_lists sorted, duplicate-free lists of n / n_lists rows each
+static int sparse_set_impl(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int64_t n, int n_lists) {
     int rc = check_ready(m);
     if (rc) return rc;
     if (which < 0 || which > 1 || !m->d_urow[which]) { set_error("no sparse gradient list %d", which); return WD_EINVAL; }
-    if (m->side_active[which]) return on_side(m, which, [&] { return merge_sparse(m, which, rows_dev, grads_dev, n); });
-    return merge_sparse(m, which, rows_dev, grads_dev, n);
+    const bool side = m->side_active[which];
+    auto merge = [&]() -> int {
+        return n_lists > 0 ? merge_sparse_sorted(m, which, rows_dev, grads_dev, n_lists, n / n_lists) : merge_sparse(m, which, rows_dev, grads_dev, n);
+    };
+    auto run = [&]() -> int {
+        if (side) return on_side(m, which, merge);
+        return merge();
+    };
+    // ~25 small launches on one stream; with a fixed-size exchange the arguments never change, so after two eager runs the merge
+    // is captured and replayed (the data-parallel tail is otherwise bound by the launching thread, not by the GPU)
+    WdModel::MergeGraph& g = m->merge_graph[which];
+    cudaStream_t st = side ? m->sstream[which] : m->stream;
+    const bool same = g.rows == rows_dev && g.grads == grads_dev && g.n == n && g.on_side == side && g.n_lists == n_lists;
+    if (!m->graphs_enabled || m->timer.enabled) return run();
+    if (g.exec && same) {
+        WD_CUDA(cudaGraphLaunch(g.exec, st));
+        m->launches += g.launches;
+        return WD_OK;
+    }
+    if (!same) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        g.rows = rows_dev; g.grads = grads_dev; g.n = n; g.on_side = side; g.n_lists = n_lists; g.eager = 0;
+    }
+    if (g.eager < 2) { g.eager++; return run(); }
+    const int64_t l0 = m->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rc = run();
+        cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+        if (rc == WD_OK && e2 == cudaSuccess && graph) e = cudaGraphInstantiate(&g.exec, graph, 0);
+        else e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (e != cudaSuccess || !g.exec) {                        // not capturable here: stay eager
+        cudaGetLastError();
+        g.exec = nullptr; g.eager = -1000000;
+        return run();
+    }
+    g.launches = m->launches - l0;
+    m->launches = l0;
+    WD_CUDA(cudaGraphLaunch(g.exec, st));
+    m->launches += g.launches;
+    return WD_OK;
+}
+
+extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int64_t n) {
+    return sparse_set_impl(m, which, rows_dev, grads_dev, n, 0);
+}
+extern "C" int wd_sparse_set_sorted(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int32_t n_lists, int64_t list_len) {
+    if (n_lists < 1 || list_len < 1) { set_error("wd_sparse_set_sorted: bad list shape"); return WD_EINVAL; }
+    return sparse_set_impl(m, which, rows_dev, grads_dev, (int64_t)n_lists * list_len, n_lists);
 }
 
 // ------------------------------------------------------------------------------------------------- eval

@@ -144,6 +144,12 @@ struct BatchSlot {           // one device-resident batch (ring used by benchmar
     DevBatch graph_view{};
     int64_t graph_launches = 0;
     int eager_steps = 0;
+    // CUDA graph of forward + backward only (data-parallel steps: wd_step_backward_slot), side streams joined at its end
+    cudaGraphExec_t graph_bwd = nullptr;
+    DevBatch graph_bwd_view{};
+    int64_t graph_bwd_launches = 0;
+    int bwd_eager_steps = 0;
+    bool bwd_side_active[2] = {false, false};
 };
 
 }  // namespace wd
@@ -169,11 +175,24 @@ struct WdModel {
     // side streams, one per sparse gradient list (0 = embedding rows, 1 = wide rows): the id-only grouping, the gradient sums,
     // the data-parallel merge and the row updates of a list all run there, overlapping the towers on the main stream
     cudaStream_t sstream[2] = {nullptr, nullptr};
-    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr;
+    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr;
     cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool side_pending[2] = {false, false};   // the list's grouping of this step was issued on its side stream
     bool side_active[2] = {false, false};    // the list's sums live on its side stream (merge / apply follow there)
     bool record_dx0 = false, dx0_recorded = false;
+    // CUDA graph of the data-parallel merge of list w (wd_sparse_set with the same buffers every step: fixed-size exchange)
+    struct MergeGraph { cudaGraphExec_t exec = nullptr; const void* rows = nullptr; const void* grads = nullptr; int64_t n = 0; int n_lists = 0;
+                        bool on_side = false; int eager = 0; int64_t launches = 0; } merge_graph[2];
+    // ---- dense exchange of small tables (WdPlanDesc::dense_exchange_max_rows)
+    int64_t dense_exchange_max_rows = 0;
+    int64_t small_base[2] = {0, 0};          // first global row of the small embedding tables / small wide columns
+    int64_t gs_count = 0, gs_emb_floats = 0; // floats of the small-table gradient block behind d_G[dense_count]; its embedding part
+    int n_rtab = 0, n_small_tab = 0;         // tables in row order (large first, then small); how many of them are small
+    int64_t* d_rtab_row_base = nullptr;      // [n_rtab] row base, ascending
+    float** d_rtab_data = nullptr;
+    int32_t *d_rtab_dim = nullptr, *d_rtab_stride = nullptr;
+    int64_t* d_rtab_gs_off = nullptr;        // [n_rtab] float offset inside the block (-1: large table)
+    int32_t* d_nubig[2] = {nullptr, nullptr};   // unique rows below small_base (what stays in the list)
     wd::DevPlan dplan{};
     std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
     int64_t bytes_allocated = 0;
@@ -282,7 +301,10 @@ int sparse_reduce_emb(WdModel* m);                               // sparse.cu: p
 int sparse_reduce_wide(WdModel* m);                              // sparse.cu: per-row gradient sums (needs dlogit only)
 int sparse_apply(WdModel* m);
 int sparse_apply_which(WdModel* m, int which);                     // sparse.cu: 0 = embedding rows, 1 = wide rows
-int sparse_group_which(WdModel* m, int which);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
+int sparse_group_which(WdModel* m, int which);
+int merge_sparse_sorted(WdModel* m, int which, const void* rows, const void* grads, int n_lists, int64_t list_len);   // sparse.cu
+int small_scatter(WdModel* m, int which);                         // sparse.cu: small-table rows of list `which` -> dense block
+int small_apply(WdModel* m);                                     // sparse.cu: optimizer over the dense block (after its all-reduce)                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
 int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
 int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0
 int dense_reduce_grads(WdModel* m);                              // mlp.cu

@@ -679,6 +679,7 @@ __global__ void wide_apply_kernel(const int32_t* __restrict__ d_nuniq, const uin
 static OptParams make_opt(const WdOptimizer& o) { return OptParams{o.kind, o.lr, o.l1, o.l2, o.init_acc}; }
 
 // sort (row, occurrence) pairs by row and find the unique rows; e_row: per-occurrence row ids (kInvalidRow = skip)
+static int group_tail(WdModel* m, int which, const int32_t* d_n);
 static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row) {
     const uint32_t invalid = 1u << m->sort_bits[which];
     int g = grid_for(m->max_nnz, 256);
@@ -686,6 +687,13 @@ static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t*
     m->launches++;
     int rc = radix_sort_pairs(m, which, m->sort_bits[which] + 1, d_n);
     if (rc) return rc;
+    return group_tail(m, which, d_n);
+}
+// unique rows + segment starts of the sorted (row, occurrence) pairs in d_sk / d_sv
+static int group_tail(WdModel* m, int which, const int32_t* d_n) {
+    const uint32_t invalid = 1u << m->sort_bits[which];
+    int g = grid_for(m->max_nnz, 256);
+    int rc;
     int32_t* flags = (int32_t*)m->d_sk2[which];               // ping-pong buffer is free after the sort
     seg_flag_kernel<<<g, 256, 0, m->stream>>>(d_n, m->d_sk[which], invalid, flags, m->max_nnz);
     m->launches++;
@@ -709,13 +717,66 @@ __global__ void merged_sum_kernel(const int32_t* __restrict__ d_nuniq, const int
     }
 }
 
+__global__ void set_count_kernel(int32_t* dst, int32_t v) { *dst = v; }
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
 // Replace the gradient list `which` by the row-wise sum of an external (rows, grads) list, e.g. the
 // all-gathered lists of every rank: keeps "sum duplicates, apply once" across data-parallel replicas.
 int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int64_t n) {
     if (n > m->max_nnz) { set_error("merged sparse list has %lld rows, capacity %lld", (long long)n, (long long)m->max_nnz); return WD_EINVAL; }
-    int32_t n32 = (int32_t)n;
-    WD_CUDA(cudaMemcpyAsync(m->d_nvalid[which], &n32, 4, cudaMemcpyHostToDevice, m->stream));
+    set_count_kernel<<<1, 1, 0, m->stream>>>(m->d_nvalid[which], (int32_t)n);     // (a kernel, not a memcpy: capturable into a graph)
+    m->launches++;
     int rc = group_rows(m, which, m->d_nvalid[which], (const uint32_t*)rows);
+    if (rc) return rc;
+    const int width = which == 0 ? m->emb_max_dim : 1;
+    merged_sum_kernel<<<grid_for(std::max<int64_t>(n, 1) * width, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_sv[which],
+                                                                                           (const float*)grads, m->d_ugrad[which], width);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// Merge of G lists that are each sorted ascending, duplicate-free and padded with kInvalidRow (what wd_sparse_grads hands out, so
+// what a fixed-size all-gather of it yields): no sort — every element finds its position in the stable merged order with one
+// binary search per list (own list: its index), one kernel; then the usual unique-row / segment pass and the ordered sums.
+__device__ __forceinline__ int upper_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256) merge_rank_kernel(const uint32_t* __restrict__ rows, int G, int K, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals, int32_t* __restrict__ d_nvalid) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int n = 0;
+        for (int r = 0; r < G; ++r) n += lower_bound_u32(rows + (int64_t)r * K, K, kInvalidRow);
+        *d_nvalid = n;
+    }
+    const int64_t total = (int64_t)G * K;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = rows[e];
+        if (x == kInvalidRow) continue;
+        const int r = (int)(e / K);
+        int pos = (int)(e - (int64_t)r * K);                        // earlier entries of the own list are all smaller
+        for (int q = 0; q < G; ++q) {
+            if (q == r) continue;
+            const uint32_t* lst = rows + (int64_t)q * K;
+            pos += q < r ? upper_bound_u32(lst, K, x) : lower_bound_u32(lst, K, x);   // ties: lower list index first (stable)
+        }
+        keys[pos] = x;
+        vals[pos] = (uint32_t)e;
+    }
+}
+int merge_sparse_sorted(WdModel* m, int which, const void* rows, const void* grads, int n_lists, int64_t list_len) {
+    const int64_t n = (int64_t)n_lists * list_len;
+    if (n_lists < 1 || list_len < 1 || list_len > 0x7fffffff) { set_error("merge: bad list shape"); return WD_EINVAL; }
+    if (n > m->max_nnz) { set_error("merged sparse list has %lld rows, capacity %lld", (long long)n, (long long)m->max_nnz); return WD_EINVAL; }
+    merge_rank_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>((const uint32_t*)rows, n_lists, (int)list_len, m->d_sk[which], m->d_sv[which], m->d_nvalid[which]);
+    m->launches++;
+    int rc = group_tail(m, which, m->d_nvalid[which]);
     if (rc) return rc;
     const int width = which == 0 ? m->emb_max_dim : 1;
     merged_sum_kernel<<<grid_for(std::max<int64_t>(n, 1) * width, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_sv[which],
@@ -782,11 +843,122 @@ int sparse_reduce_wide(WdModel* m) {
     return WD_OK;
 }
 
+// ------------------------------------------------------------------------- dense exchange of small tables
+// Rows of the small tables sit at the end of the global row space, so they are the tail of the sorted unique-row list.  Their summed
+// gradients move into the dense block behind the dense gradient arena (all-reduced with it in data-parallel runs) and leave the
+// list: the tail is overwritten with kInvalidRow and the list length becomes the number of large-table rows.
+__global__ void __launch_bounds__(256) small_scatter_emb_kernel(const int32_t* __restrict__ d_nuniq, uint32_t* __restrict__ urow,
+                                                                const float* __restrict__ ugrad, int width, uint32_t small_base, int ntab,
+                                                                const int64_t* __restrict__ rtab_row_base, const int32_t* __restrict__ rtab_dim,
+                                                                const int64_t* __restrict__ rtab_gs_off, float* __restrict__ Gs,
+                                                                int32_t* __restrict__ d_nubig) {
+    const int nu = *d_nuniq;
+    const int lb = lower_bound_u32(urow, nu, small_base);        // (a concurrently invalidated tail entry still compares >= small_base)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nubig = lb;
+    const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+    const int64_t gstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 4;
+    for (int64_t u = lb + g0; u < nu; u += gstep) {
+        const int64_t row = urow[u];
+        int lo = 0, hi = ntab - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rtab_row_base[mid] <= row) lo = mid; else hi = mid - 1; }
+        const int dim = rtab_dim[lo];
+        float* dst = Gs + rtab_gs_off[lo] + (row - rtab_row_base[lo]) * dim;
+        for (int q = lig; q * 4 < dim; q += 8)
+            *reinterpret_cast<float4*>(dst + q * 4) = *reinterpret_cast<const float4*>(ugrad + u * width + q * 4);
+        __syncwarp();
+        if (lig == 0) urow[u] = kInvalidRow;
+    }
+}
+__global__ void __launch_bounds__(256) small_scatter_wide_kernel(const int32_t* __restrict__ d_nuniq, uint32_t* __restrict__ urow,
+                                                                 const float* __restrict__ ugrad, uint32_t small_base, float* __restrict__ Gs,
+                                                                 int32_t* __restrict__ d_nubig) {
+    const int nu = *d_nuniq;
+    const int lb = lower_bound_u32(urow, nu, small_base);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nubig = lb;
+    for (int64_t u = lb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += (int64_t)gridDim.x * blockDim.x) {
+        Gs[urow[u] - small_base] = ugrad[u];
+        urow[u] = kInvalidRow;
+    }
+}
+__global__ void copy_count_kernel(int32_t* dst, const int32_t* src) { *dst = *src; }
+
+int small_scatter(WdModel* m, int which) {
+    if (m->gs_count == 0) return WD_OK;
+    float* block = m->d_G + m->dense_count;
+    if (which == 0) {
+        if (m->n_small_tab == 0 || !(m->use_deep && !m->tables.empty())) return WD_OK;
+        small_scatter_emb_kernel<<<grid_for(m->max_nnz * 8, 256, 148 * 8), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim,
+            (uint32_t)m->small_base[0], m->n_rtab, m->d_rtab_row_base, m->d_rtab_dim, m->d_rtab_gs_off, block, m->d_nubig[0]);
+    } else {
+        if (!m->use_wide || m->small_base[1] >= m->wide_rows) return WD_OK;
+        small_scatter_wide_kernel<<<grid_for(m->max_nnz, 256, 148 * 8), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_urow[1], m->d_ugrad[1],
+            (uint32_t)m->small_base[1], block + m->gs_emb_floats, m->d_nubig[1]);
+    }
+    copy_count_kernel<<<1, 1, 0, m->stream>>>(m->d_nuniq[which], m->d_nubig[which]);
+    m->launches += 2;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
+// optimizer over the dense block: one update per small-table row whose (all-reduced) gradient is not identically zero —
+// untouched rows have an exactly zero gradient and every optimizer here leaves a row unchanged for g = 0
+__global__ void __launch_bounds__(256) small_apply_emb_kernel(const float* __restrict__ Gs, int64_t n4, int ntab, int first_small,
+                                                              const int64_t* __restrict__ rtab_gs_off, float* const* __restrict__ rtab_data,
+                                                              const int32_t* __restrict__ rtab_dim, const int32_t* __restrict__ rtab_stride, OptParams o) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g = *reinterpret_cast<const float4*>(Gs + i * 4);
+        if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+        int lo = first_small, hi = ntab - 1;                       // small tables are the last entries, offsets ascending
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rtab_gs_off[mid] <= i * 4) lo = mid; else hi = mid - 1; }
+        const int dim = rtab_dim[lo], stride = rtab_stride[lo];
+        const int64_t local = i * 4 - rtab_gs_off[lo];
+        float* rec = rtab_data[lo] + (local / dim) * stride + (local % dim);
+        const int nslots = stride / dim - 1;
+        float4 w = *reinterpret_cast<float4*>(rec);
+        float4 s1 = nslots >= 1 ? *reinterpret_cast<float4*>(rec + dim) : make_float4(0, 0, 0, 0);
+        float4 s2 = nslots >= 2 ? *reinterpret_cast<float4*>(rec + 2 * dim) : make_float4(0, 0, 0, 0);
+        opt_update(o, g.x, w.x, s1.x, s2.x);
+        opt_update(o, g.y, w.y, s1.y, s2.y);
+        opt_update(o, g.z, w.z, s1.z, s2.z);
+        opt_update(o, g.w, w.w, s1.w, s2.w);
+        *reinterpret_cast<float4*>(rec) = w;
+        if (nslots >= 1) *reinterpret_cast<float4*>(rec + dim) = s1;
+        if (nslots >= 2) *reinterpret_cast<float4*>(rec + 2 * dim) = s2;
+    }
+}
+__global__ void __launch_bounds__(256) small_apply_wide_kernel(const float* __restrict__ Gs, int64_t n, float4* __restrict__ wide, OptParams o) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = Gs[i];
+        if (g == 0.f) continue;
+        float4 r = wide[i];
+        opt_update(o, g, r.x, r.y, r.z);
+        wide[i] = r;
+    }
+}
+int small_apply(WdModel* m) {
+    if (m->gs_count == 0) return WD_OK;
+    const float* block = m->d_G + m->dense_count;
+    if (m->gs_emb_floats > 0) {
+        small_apply_emb_kernel<<<grid_for(m->gs_emb_floats / 4, 256), 256, 0, m->stream>>>(block, m->gs_emb_floats / 4, m->n_rtab, m->n_rtab - m->n_small_tab,
+            m->d_rtab_gs_off, m->d_rtab_data, m->d_rtab_dim, m->d_rtab_stride, make_opt(m->dnn_opt));
+        m->launches++;
+    }
+    const int64_t nw = m->use_wide ? m->wide_rows - m->small_base[1] : 0;
+    if (nw > 0) {
+        small_apply_wide_kernel<<<grid_for(nw, 256), 256, 0, m->stream>>>(block + m->gs_emb_floats, nw,
+            reinterpret_cast<float4*>(m->d_wide) + m->small_base[1], make_opt(m->lin_opt));
+        m->launches++;
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int sparse_apply_which(WdModel* m, int which) {
     if (which == 0 && m->use_deep && !m->tables.empty()) {
         emb_apply_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
-            m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim, (int)m->tables.size(), m->d_tab_row_base, m->d_tab_data,
-            m->d_tab_dim, m->d_tab_stride, make_opt(m->dnn_opt));
+            m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim, m->n_rtab, m->d_rtab_row_base, m->d_rtab_data,
+            m->d_rtab_dim, m->d_rtab_stride, make_opt(m->dnn_opt));          // tables in row order (binary search by row)
         m->launches++;
     }
     if (which == 1 && m->use_wide) {

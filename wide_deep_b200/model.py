@@ -173,6 +173,10 @@ class WideDeepModel(object):
     def sparse_set(self, which, rows_ptr, grads_ptr, n):
         check(self._lib.wd_sparse_set(self._h, which, ctypes.c_void_p(rows_ptr), ctypes.c_void_p(grads_ptr), int(n)))
 
+    def sparse_set_sorted(self, which, rows_ptr, grads_ptr, n_lists, list_len):
+        """Merge n_lists sorted, duplicate-free, INVALID_ROW-padded lists of list_len rows (all-gathered wd_sparse_grads buffers)."""
+        check(self._lib.wd_sparse_set_sorted(self._h, which, ctypes.c_void_p(rows_ptr), ctypes.c_void_p(grads_ptr), int(n_lists), int(list_len)))
+
     # ------------------------------------------------------------------ eval
     def eval_reset(self):
         check(self._lib.wd_eval_reset(self._h))

@@ -113,6 +113,36 @@ class DataParallelTrainer(object):
                     all_r=torch.empty((self.world * K,), dtype=torch.int32, device=self.device),
                     all_g=torch.empty((self.world * K, width), dtype=torch.float32, device=self.device))
 
+    def profile_step(self, slot):
+        """One step with CUDA-event stamps around its phases (debugging aid): returns {phase: ms}.  Phases of different lists
+        overlap; every time is measured from the start of the step on the stream the phase runs on."""
+        m = self.model
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t0 = ev(); t0.record(self.stream)
+        m.step_backward_slot(slot, want_loss=False)
+        marks = {}
+        e = ev(); e.record(self.stream); marks["backward(main)"] = e
+        for which in sorted(self.lists, reverse=True):
+            f = self.fixed[which]
+            sptr = m.stream_sparse(which)
+            st = self._ext.setdefault(sptr, torch.cuda.ExternalStream(sptr, device=self.device))
+            with torch.cuda.stream(st):
+                e = ev(); e.record(st); marks["list%d ready" % which] = e
+                dist.all_gather_into_tensor(f["all_r"], f["rows"], group=self.group)
+                dist.all_gather_into_tensor(f["all_g"], f["grads"], group=self.group)
+                e = ev(); e.record(st); marks["list%d gathered" % which] = e
+                m.sparse_set_sorted(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), self.world, f["K"])
+                e = ev(); e.record(st); marks["list%d merged" % which] = e
+        with torch.cuda.stream(self.stream):
+            if self.dense_grad is not None:
+                dist.all_reduce(self.dense_grad, op=dist.ReduceOp.SUM, group=self.group)
+            e = ev(); e.record(self.stream); marks["dense allreduce"] = e
+        m.step_apply()
+        e = ev(); e.record(self.stream); marks["apply+join(main)"] = e
+        m.sync()
+        torch.cuda.synchronize()
+        return {k: t0.elapsed_time(v) for k, v in marks.items()}
+
     def _collectives(self):
         m = self.model
         if self.fixed is not None:
@@ -126,7 +156,7 @@ class DataParallelTrainer(object):
                 with torch.cuda.stream(self._ext[sptr]):
                     dist.all_gather_into_tensor(f["all_r"], f["rows"], group=self.group)
                     dist.all_gather_into_tensor(f["all_g"], f["grads"], group=self.group)
-                    m.sparse_set(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), f["all_r"].numel())
+                    m.sparse_set_sorted(which, f["all_r"].data_ptr(), f["all_g"].data_ptr(), self.world, f["K"])
             with torch.cuda.stream(self.stream):
                 if self.dense_grad is not None:
                     dist.all_reduce(self.dense_grad, op=dist.ReduceOp.SUM, group=self.group)

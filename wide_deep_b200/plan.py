@@ -105,6 +105,7 @@ class PlanDescC(ctypes.Structure):
         ("lin_opt", _OptC), ("dnn_opt", _OptC),
         ("max_batch", ctypes.c_int32), ("max_nnz", ctypes.c_int64), ("max_keys", ctypes.c_int64),
         ("gemm_engine", ctypes.c_int32),
+        ("dense_exchange_max_rows", ctypes.c_int64), ("wide_small_base", ctypes.c_int64),
     ]
 
 
@@ -130,12 +131,16 @@ class Plan(object):
     """
 
     def __init__(self, feature_conf, cross_conf, model_conf, model_type="wide_deep", max_batch=8192,
-                 embedding_dim_override=None, tf_compat_pad=False, gemm_engine="auto", max_nnz=0, max_keys=0):
+                 embedding_dim_override=None, tf_compat_pad=False, gemm_engine="auto", max_nnz=0, max_keys=0,
+                 dense_exchange_max_rows=0):
         if model_type not in ("wide", "deep", "wide_deep"):
             raise ValueError("Invalid model type: {}, must be one of `wide`, `deep`, `wide_deep`".format(model_type))
         self.model_type, self.max_batch, self.tf_compat_pad = model_type, int(max_batch), bool(tf_compat_pad)
         self.use_wide, self.use_deep = model_type != "deep", model_type != "wide"
         self.gemm_engine, self.max_nnz, self.max_keys = gemm_engine, int(max_nnz), int(max_keys)
+        # data-parallel exchange format: tables / wide columns with at most this many rows travel as a dense gradient block
+        # (all-reduced with the dense gradients) instead of (row, gradient) list entries; 0 = lists for everything
+        self.dense_exchange_max_rows = int(dense_exchange_max_rows)
         edim = (lambda n: int(embedding_dim_override)) if embedding_dim_override else embedding_dim
 
         # ---- input fields
@@ -233,12 +238,21 @@ class Plan(object):
         self._col_index = col_index
 
         # ---- wide table layout
+        # (row space: large columns first, then the small ones that are exchanged densely — see dense_exchange_max_rows)
         base = 0
         self.wide_columns = []
-        for c in order:
-            if c.wide_base == 0 and self.use_wide:
-                c.wide_base = base
-                base += c.buckets
+        is_wide = [c.wide_base == 0 and self.use_wide for c in order]
+        small = [w and 0 < self.dense_exchange_max_rows >= c.buckets for c, w in zip(order, is_wide)]
+        self.wide_small_base = None
+        for want_small in (False, True):
+            if want_small:
+                self.wide_small_base = base
+            for c, w, sm in zip(order, is_wide, small):
+                if w and sm == want_small:
+                    c.wide_base = base
+                    base += c.buckets
+        for c, w in zip(order, is_wide):
+            if w:
                 self.wide_columns.append(c)
             else:
                 c.wide_base = -1
@@ -347,6 +361,16 @@ class Plan(object):
         w = lambda s: self.d0 if s == "x" else hu[s]
         return [(sum(w(s) for s in srcs[l]), hu[l] if l < len(hu) else 1) for l in range(len(hu) + 1)]
 
+    def exchange_rows(self, rows_per_column):
+        """Upper bounds (K_emb, K_wide) on the touched rows per step that stay in the (row, gradient) lists, given the maximum
+        number of ids one column contributes per step (batch size for single-valued columns): columns whose table is exchanged
+        densely (dense_exchange_max_rows) contribute nothing."""
+        t = self.dense_exchange_max_rows
+        big = lambda n: not (0 < t >= n)
+        k_emb = sum(rows_per_column for tb in self.tables if big(tb["rows"]))
+        k_wide = sum(rows_per_column for c in self.wide_columns if big(c.buckets))
+        return k_emb, k_wide
+
     def summary(self):
         return dict(model_type=self.model_type, cat_fields=len(self.cat_fields), dense_fields=len(self.dense_fields),
                     columns=len(self.columns), wide_columns=len(self.wide_columns), wide_rows=self.wide_rows,
@@ -423,6 +447,8 @@ class Plan(object):
             dst.kind, dst.lr, dst.l1, dst.l2 = OPT[o["kind"]], o["lr"], o["l1"], o["l2"]
             dst.lr_power, dst.init_acc = o["lr_power"], o["init_acc"]
         d.max_batch, d.max_nnz, d.max_keys, d.gemm_engine = self.max_batch, self.max_nnz, self.max_keys, GEMM[self.gemm_engine]
+        d.dense_exchange_max_rows = self.dense_exchange_max_rows
+        d.wide_small_base = self.wide_small_base if self.wide_small_base is not None else self.wide_rows
         return d, keep
 
 
