@@ -370,7 +370,11 @@ def main():
             flops = 6.0 * B * P                                   # 2BP forward + 4BP backward
             ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
             out["roofline"] = {"kernel": "mlp gemm (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
-                               "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                               "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                               # dram__bytes_read.sum + dram__bytes_write.sum over the nine GEMM launches of one step, from the ncu
+                               # --set full capture in profiles/r1_full_summary.md (bf16x3, B = 8192); None for other settings
+                               "traffic": 363.0e6 if (args.engine == "bf16x3" and B == 8192) else None,
+                               "traffic_unit": "bytes per step (9 launches)",
                                "peak_source": peaks["source"] + " dense bf16 (sustained).  achieved = algorithmic fp32 FLOPs (6*B*P) / GEMM time; "
                                               "both split engines issue 3 tensor-core products per algorithmic one, so the fp32-"
                                               "equivalent ceiling is 1/3 of the bf16 peak for bf16x3 and 1/6 for tc3x",
