@@ -153,7 +153,14 @@ int wd_train_step_resident(WdModel *m, float *loss_out);
 /* Ring of device-resident batches (slot in [0, 64); buffers are allocated on first use): lets a caller
  * prefetch batch i+1 while step i runs, and lets the benchmark step through distinct resident batches. */
 int wd_batch_upload_slot(WdModel *m, int slot, const WdBatch *batch);
+/* Asynchronous refill — the counterpart of `dataset.prefetch(2 * batch_size)` in the reference's input_fn (python/lib/dataset.py:
+ * 181-184): the host->device copies run on the library's upload stream, after the last step that read the slot and concurrently
+ * with the step running on another slot; the next step on this slot waits for them on the device.  The (pinned) host buffers must
+ * stay untouched until that step has been issued and has returned. */
+int wd_batch_prefetch_slot(WdModel *m, int slot, const WdBatch *batch);
 int wd_train_step_slot(WdModel *m, int slot, float *loss_out);   /* loss_out NULL: enqueue only, no sync */
+/* Loss of the most recent forward / train step (device->host read, synchronises the model stream). */
+int wd_last_loss(WdModel *m, float *loss_out);
 int wd_forward_resident(WdModel *m, float *logits_out, float *loss_out);
 
 /* Split step for data-parallel training (multi-GPU): phase 1 computes gradients and leaves

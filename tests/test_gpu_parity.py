@@ -179,6 +179,35 @@ def test_dense_exchange_of_small_tables(model_type, dense_rows):
     _train_compare(fc, cross, model, model_type, steps=3, seed=29, dense_rows=dense_rows)
 
 
+def test_prefetched_slots_equal_direct_steps():
+    """wd_batch_prefetch_slot (refill on the upload stream, step waits on the device) + wd_train_step_slot + wd_last_loss give
+    exactly the losses of plain wd_train_step calls on the same batches, graphs included (8 steps over two alternating slots)."""
+    fc, cross, model = small_conf()
+    B = 128
+    om, plan, pa = build_pair(fc, cross, model, B=B, seed=3)
+    pb = WideDeepModel(plan)
+    copy_params_to_product(om, pb)
+    rng = np.random.default_rng(5)
+    batches = []
+    for _ in range(8):
+        raw = random_raw_batch(fc, B, rng)
+        batches.append(to_product_batch(plan, raw, (rng.random(B) < 0.3).astype(np.float32)))
+    direct = [pa.train_step(b) for b in batches]
+    pb.prefetch_slot(2, batches[0])
+    got = []
+    for i in range(8):
+        if i + 1 < 8:
+            pb.prefetch_slot(2 + (i + 1) % 2, batches[i + 1])
+        if i % 2:
+            got.append(pb.train_step_slot(2 + i % 2, want_loss=True))
+        else:
+            pb.train_step_slot(2 + i % 2, want_loss=False)
+            got.append(pb.last_loss())
+    assert got == direct, (got, direct)
+    for name in pa.tensor_names()[:8]:
+        np.testing.assert_array_equal(pa.get_tensor(name), pb.get_tensor(name))
+
+
 def test_run_to_run_bit_reproducible():
     fc, cross, model = small_conf()
     rng = np.random.default_rng(23)

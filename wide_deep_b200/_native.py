@@ -70,6 +70,8 @@ SYMBOLS = {
     "wd_last_timings": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "wd_timing_name": (ctypes.c_char_p, [_vp, ctypes.c_int]),
     "wd_batch_upload_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "wd_batch_prefetch_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "wd_last_loss": (ctypes.c_int, [_vp, _vp]),
     "wd_train_step_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "wd_set_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "wd_stream": (_vp, [_vp]),

@@ -101,7 +101,13 @@ extern "C" int wd_model_destroy(WdModel* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     tc_map_cache_clear();
-    for (auto& sl : m->slots) { if (sl.graph) cudaGraphExecDestroy(sl.graph); if (sl.graph_bwd) cudaGraphExecDestroy(sl.graph_bwd); }
+    for (auto& sl : m->slots) {
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+        if (sl.graph_bwd) cudaGraphExecDestroy(sl.graph_bwd);
+        if (sl.ev_up) cudaEventDestroy(sl.ev_up);
+        if (sl.ev_used) cudaEventDestroy(sl.ev_used);
+    }
+    if (m->stream_up) { cudaStreamSynchronize(m->stream_up); cudaStreamDestroy(m->stream_up); }
     for (auto& g : m->merge_graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (m->ev_bwd_done) cudaEventDestroy(m->ev_bwd_done);
     for (void* p : m->allocs) cudaFree(p);
@@ -480,6 +486,7 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     m->device = device;
     memset(m->timer.ev, 0, sizeof(m->timer.ev));
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream_up, cudaStreamNonBlocking);
     for (int w = 0; w < 2; ++w) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->sstream[w], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_grouped[w], cudaEventDisableTiming);
@@ -653,7 +660,7 @@ static void timer_begin(WdModel* m) {
 }
 
 // make batch slot `s` current (allocating its buffers on first use); slot 0 aliases the model's own buffers
-static int select_slot(WdModel* m, int s) {
+static int ensure_slot(WdModel* m, int s) {
     if (s < 0 || s >= 64) { set_error("batch slot %d out of range [0, 64)", s); return WD_EINVAL; }
     if (m->slots.empty()) {
         BatchSlot b0;
@@ -671,33 +678,78 @@ static int select_slot(WdModel* m, int s) {
         if ((rc = dev_alloc(m, &b.weight, Bm))) return rc;
         m->slots.push_back(b);
     }
+    return WD_OK;
+}
+static int select_slot(WdModel* m, int s) {
+    int rc = ensure_slot(m, s);
+    if (rc) return rc;
     BatchSlot& b = m->slots[s];
     m->cur_slot = s;
     m->d_cat_offsets = b.off; m->d_cat_keys = b.keys; m->d_dense = b.dense; m->d_label = b.label; m->d_weight = b.weight;
     if (b.filled) { m->dbatch = b.view; m->batch_has_label = b.has_label; }
+    if (b.up_pending) {                                     // a prefetch refilled this slot on the upload stream
+        WD_CUDA(cudaStreamWaitEvent(m->stream, b.ev_up, 0));
+        b.up_pending = false;
+    }
+    return WD_OK;
+}
+// the model stream has consumed the current slot up to here (a later prefetch into it must wait for this point)
+static int mark_slot_used(WdModel* m) {
+    if (m->slots.empty()) return WD_OK;
+    BatchSlot& b = m->slots[m->cur_slot];
+    if (!b.ev_used) WD_CUDA(cudaEventCreateWithFlags(&b.ev_used, cudaEventDisableTiming));
+    WD_CUDA(cudaEventRecord(b.ev_used, m->stream));
+    b.used_recorded = true;
     return WD_OK;
 }
 
-static int upload_current(WdModel* m, const WdBatch* b) {
+// copies a host batch into the buffers of slot `sl` on stream `st`; fills the device view of the batch
+static int upload_into(WdModel* m, BatchSlot& sl, const WdBatch* b, cudaStream_t st, DevBatch* view, bool* has_label) {
     if (!b || b->batch_size <= 0 || b->batch_size > m->max_batch) { set_error("batch_size %d outside (0, %d]", b ? b->batch_size : -1, m->max_batch); return WD_EINVAL; }
     const int B = b->batch_size, F = m->n_cat_fields, Nd = m->n_dense_fields;
     int64_t nnz = b->cat_offsets ? b->nnz : (int64_t)B * F;
     if (nnz > m->keys_cap) { set_error("batch has %lld keys, capacity %lld (raise max_keys)", (long long)nnz, (long long)m->keys_cap); return WD_EINVAL; }
     if (F > 0) {
-        if (b->cat_offsets) WD_CUDA(cudaMemcpyAsync(m->d_cat_offsets, b->cat_offsets, ((int64_t)B * F + 1) * 4, cudaMemcpyHostToDevice, m->stream));
-        if (nnz > 0) WD_CUDA(cudaMemcpyAsync(m->d_cat_keys, b->cat_keys, nnz * 8, cudaMemcpyHostToDevice, m->stream));
+        if (b->cat_offsets) WD_CUDA(cudaMemcpyAsync(sl.off, b->cat_offsets, ((int64_t)B * F + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (nnz > 0) WD_CUDA(cudaMemcpyAsync(sl.keys, b->cat_keys, nnz * 8, cudaMemcpyHostToDevice, st));
     }
-    if (Nd > 0) WD_CUDA(cudaMemcpyAsync(m->d_dense, b->dense, (int64_t)B * Nd * 4, cudaMemcpyHostToDevice, m->stream));
-    if (b->label) WD_CUDA(cudaMemcpyAsync(m->d_label, b->label, (int64_t)B * 4, cudaMemcpyHostToDevice, m->stream));
-    if (b->weight) WD_CUDA(cudaMemcpyAsync(m->d_weight, b->weight, (int64_t)B * 4, cudaMemcpyHostToDevice, m->stream));
-    m->dbatch.B = B;
-    m->dbatch.cat_offsets = (F > 0 && b->cat_offsets) ? m->d_cat_offsets : nullptr;
-    m->dbatch.cat_keys = m->d_cat_keys;
-    m->dbatch.dense = m->d_dense;
-    m->dbatch.label = b->label ? m->d_label : nullptr;
-    m->dbatch.weight = b->weight ? m->d_weight : nullptr;
-    m->batch_has_label = b->label != nullptr;
+    if (Nd > 0) WD_CUDA(cudaMemcpyAsync(sl.dense, b->dense, (int64_t)B * Nd * 4, cudaMemcpyHostToDevice, st));
+    if (b->label) WD_CUDA(cudaMemcpyAsync(sl.label, b->label, (int64_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (b->weight) WD_CUDA(cudaMemcpyAsync(sl.weight, b->weight, (int64_t)B * 4, cudaMemcpyHostToDevice, st));
+    view->B = B;
+    view->cat_offsets = (F > 0 && b->cat_offsets) ? sl.off : nullptr;
+    view->cat_keys = sl.keys;
+    view->dense = sl.dense;
+    view->label = b->label ? sl.label : nullptr;
+    view->weight = b->weight ? sl.weight : nullptr;
+    *has_label = b->label != nullptr;
+    return WD_OK;
+}
+
+static int upload_current(WdModel* m, const WdBatch* b) {
+    BatchSlot& sl = m->slots[m->cur_slot];
+    int rc = upload_into(m, sl, b, m->stream, &m->dbatch, &m->batch_has_label);
+    if (rc) return rc;
     mark(m, "h2d");
+    return WD_OK;
+}
+
+// Asynchronous refill of a batch slot: the copies run on the library's upload stream, behind the last step that read the slot
+// and concurrently with whatever the model stream is doing (normally: the step on another slot).  The next step on this slot
+// waits for them on the device.  Host buffers must stay untouched until that step has been issued and returned.
+extern "C" int wd_batch_prefetch_slot(WdModel* m, int slot, const WdBatch* b) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if ((rc = ensure_slot(m, slot))) return rc;
+    BatchSlot& sl = m->slots[slot];
+    if (!sl.ev_up) WD_CUDA(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
+    if (sl.used_recorded) WD_CUDA(cudaStreamWaitEvent(m->stream_up, sl.ev_used, 0));
+    DevBatch view{};
+    bool has_label = false;
+    if ((rc = upload_into(m, sl, b, m->stream_up, &view, &has_label))) return rc;
+    WD_CUDA(cudaEventRecord(sl.ev_up, m->stream_up));
+    sl.view = view; sl.has_label = has_label; sl.filled = true; sl.up_pending = true;
+    if (slot == m->cur_slot) { m->dbatch = view; m->batch_has_label = has_label; }
     return WD_OK;
 }
 
@@ -894,6 +946,7 @@ static int train_current(WdModel* m, float* loss_out) {
         if ((rc = train_eager(m))) return rc;
         sl.eager_steps++;
     }
+    if ((rc = mark_slot_used(m))) return rc;
     if (loss_out) return finish_step(m, loss_out, nullptr);
     return WD_OK;
 }
@@ -1010,8 +1063,17 @@ extern "C" int wd_step_backward_slot(WdModel* m, int slot, float* loss_out) {
         if ((rc = backward_eager(m, false))) return rc;
         sl.bwd_eager_steps++;
     }
+    if ((rc = mark_slot_used(m))) return rc;
     if (loss_out) return finish_step(m, loss_out, nullptr);
     return WD_OK;
+}
+
+// loss of the most recent forward / train step (synchronises the model stream)
+extern "C" int wd_last_loss(WdModel* m, float* loss_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!loss_out) { set_error("wd_last_loss: null output"); return WD_EINVAL; }
+    return finish_step(m, loss_out, nullptr);
 }
 
 extern "C" int wd_step_backward(WdModel* m, const WdBatch* b, float* loss_out) {

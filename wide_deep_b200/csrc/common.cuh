@@ -139,6 +139,10 @@ struct BatchSlot {           // one device-resident batch (ring used by benchmar
     float *dense = nullptr, *label = nullptr, *weight = nullptr;
     DevBatch view{};
     bool has_label = false, filled = false;
+    // asynchronous refill (wd_batch_prefetch_slot): copies run on the upload stream between these two events
+    cudaEvent_t ev_up = nullptr;             // recorded on the upload stream after the slot's copies
+    cudaEvent_t ev_used = nullptr;           // recorded on the model stream after the last step that read the slot
+    bool up_pending = false, used_recorded = false;
     // CUDA graph of one whole train step on this slot (captured after a few eager steps; keyed by the batch view)
     cudaGraphExec_t graph = nullptr;
     DevBatch graph_view{};
@@ -175,6 +179,7 @@ struct WdModel {
     // side streams, one per sparse gradient list (0 = embedding rows, 1 = wide rows): the id-only grouping, the gradient sums,
     // the data-parallel merge and the row updates of a list all run there, overlapping the towers on the main stream
     cudaStream_t sstream[2] = {nullptr, nullptr};
+    cudaStream_t stream_up = nullptr;        // host->device refills of batch slots (wd_batch_prefetch_slot), overlapping the running step
     cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr;
     cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool side_pending[2] = {false, false};   // the list's grouping of this step was issued on its side stream

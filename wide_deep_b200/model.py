@@ -235,6 +235,21 @@ class WideDeepModel(object):
         check(self._lib.wd_batch_upload_slot(self._h, int(slot), ctypes.byref(c)))
         self._rows_hint = batch.batch_size
 
+    def prefetch_slot(self, slot, batch: Batch):
+        """Asynchronous refill of a batch slot on the upload stream (overlaps the step running on another slot).  The batch's
+        host arrays (pinned for a truly asynchronous copy) are kept alive here until the slot is refilled again."""
+        c = batch.to_c()
+        check(self._lib.wd_batch_prefetch_slot(self._h, int(slot), ctypes.byref(c)))
+        if not hasattr(self, "_prefetched"):
+            self._prefetched = {}
+        self._prefetched[int(slot)] = (batch, c)
+        self._rows_hint = batch.batch_size
+
+    def last_loss(self):
+        loss = ctypes.c_float()
+        check(self._lib.wd_last_loss(self._h, ctypes.byref(loss)))
+        return loss.value
+
     def train_step_slot(self, slot, want_loss=True):
         loss = ctypes.c_float()
         check(self._lib.wd_train_step_slot(self._h, int(slot), ctypes.byref(loss) if want_loss else None))
