@@ -304,12 +304,12 @@ int sparse_forward(WdModel* m);                                  // sparse.cu: w
 int sparse_group(WdModel* m);                                    // sparse.cu: sort (row, occurrence) pairs, unique rows, chunks
 int sparse_reduce_emb(WdModel* m);                               // sparse.cu: per-row gradient sums (needs dX0)
 int sparse_reduce_wide(WdModel* m);                              // sparse.cu: per-row gradient sums (needs dlogit only)
-int sparse_apply(WdModel* m);
-int sparse_apply_which(WdModel* m, int which);                     // sparse.cu: 0 = embedding rows, 1 = wide rows
-int sparse_group_which(WdModel* m, int which);
+int sparse_apply(WdModel* m);                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows (both lists)
+int sparse_apply_which(WdModel* m, int which);                   // sparse.cu: one list (0 = embedding rows, 1 = wide rows)
+int sparse_group_which(WdModel* m, int which);                   // sparse.cu: grouping of one list
 int merge_sparse_sorted(WdModel* m, int which, const void* rows, const void* grads, int n_lists, int64_t list_len);   // sparse.cu
-int small_scatter(WdModel* m, int which);                         // sparse.cu: small-table rows of list `which` -> dense block
-int small_apply(WdModel* m);                                     // sparse.cu: optimizer over the dense block (after its all-reduce)                                    // sparse.cu: Adagrad / FTRL / SGD on touched rows
+int small_scatter(WdModel* m, int which);                        // sparse.cu: small-table rows of list `which` -> dense block
+int small_apply(WdModel* m);                                     // sparse.cu: optimizer over the dense block (after its all-reduce)
 int mlp_forward(WdModel* m, bool want_transposes);               // mlp.cu: towers -> logits, loss
 int mlp_backward(WdModel* m);                                    // mlp.cu: grads of dense params, dX0
 int dense_reduce_grads(WdModel* m);                              // mlp.cu

@@ -1,4 +1,4 @@
-// Shared GEMM interface of the MLP engines (FFMA in mlp.cu, tcgen05 in gemm_tc.cu): operand descriptions,
+// Shared GEMM interface of the MLP engines (FFMA in mlp.cu, tcgen05 in gemm_tc.cu and gemm_bf16.cu): operand descriptions,
 // epilogue description and the activation functions (reference python/lib/utils/model_util.py:28-59).
 #pragma once
 #include <cuda_bf16.h>
@@ -57,8 +57,8 @@ struct Epi {
     int n_logical, act, bn;
     int m_valid;                       // rows >= m_valid are written as zero (transposed padding)
     int64_t split_stride;              // WGRAD: floats between split partials
-    // 3xBF16 engine, FWD: the layer output also leaves as bf16 hi / lo copies, row-major [M, ldh] and transposed [N, ldt]
-    __nv_bfloat16 *Hs_hi, *Hs_lo, *HTs_hi, *HTs_lo;
+    // 3xBF16 engine, FWD: the layer output leaves as bf16 hi / lo copies, row-major [M, ldh] (H_out may then be NULL)
+    __nv_bfloat16 *Hs_hi, *Hs_lo;
 };
 
 // hi = bf16(x) (round to nearest), lo = bf16(x - hi): x = hi + lo up to 2^-17 relative; the product a*b is rebuilt as
