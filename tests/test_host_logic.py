@@ -127,3 +127,27 @@ def test_shard_rows_cover_batch():
             spans = [shard_rows(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_dense_exchange_layout_and_list_bounds():
+    """dense_exchange_max_rows: the plan orders the wide columns large-first (small ones at the end of the row space, from
+    wide_small_base on) without changing any column's size, and exchange_rows() counts only the large tables / columns."""
+    from wide_deep_b200 import synthetic
+    from wide_deep_b200.plan import Plan
+    fc, cross, model, emb = synthetic.criteo_conf()
+    p0 = Plan(fc, cross, model, "wide_deep", max_batch=512, embedding_dim_override=emb)
+    p1 = Plan(fc, cross, model, "wide_deep", max_batch=512, embedding_dim_override=emb, dense_exchange_max_rows=16384)
+    assert p0.wide_rows == p1.wide_rows and p0.wide_small_base == p0.wide_rows      # nothing is small without the option
+    assert [c.name for c in p0.wide_columns] == [c.name for c in p1.wide_columns]
+    spans = sorted((c.wide_base, c.wide_base + c.buckets, c.buckets) for c in p1.wide_columns)
+    assert spans[0][0] == 0 and spans[-1][1] == p1.wide_rows
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))                     # the columns tile the row space
+    for lo, hi, n in spans:
+        assert (n <= 16384) == (lo >= p1.wide_small_base)                          # small columns exactly behind the base
+    n_big_emb = sum(1 for t in p1.tables if t["rows"] > 16384)
+    n_big_wide = sum(1 for c in p1.wide_columns if c.buckets > 16384)
+    assert (n_big_emb, n_big_wide) == (8, 16)
+    assert p1.exchange_rows(512) == (512 * 8, 512 * 16)
+    assert p0.exchange_rows(512) == (512 * len(p0.tables), 512 * len(p0.wide_columns))
+    d, _keep = p1.to_c()
+    assert d.dense_exchange_max_rows == 16384 and d.wide_small_base == p1.wide_small_base

@@ -85,3 +85,45 @@ def test_merge_skips_invalid_rows():
     grads = torch.tensor([[1.0], [9.0], [2.0], [3.0], [9.0]])
     u, s = merge_sparse_host(rows, grads)
     assert u.tolist() == [2, 5] and s[:, 0].tolist() == [2.0, 4.0]
+
+
+def test_sorted_list_merge_positions_equal_stable_sort():
+    """Host restatement of merge_rank_kernel (csrc/sparse.cu): for G sorted, duplicate-free, INVALID-padded lists the merged
+    position of an element = its index in its own list + (elements <= it in lower-numbered lists) + (elements < it in
+    higher-numbered lists).  Must reproduce a stable sort of the concatenation, and the row-wise sums of merge_sparse_host."""
+    from wide_deep_b200.parallel import INVALID_ROW, merge_sparse_host
+    INV = 0xFFFFFFFF                                                      # the marker as the device sees it (uint32 maximum)
+    rng = np.random.default_rng(11)
+    G, K = 4, 64
+    rows = np.full((G, K), INV, dtype=np.int64)
+    for g in range(G):
+        n = int(rng.integers(0, K + 1))                                   # ragged, possibly empty, possibly full lists
+        rows[g, :n] = np.sort(rng.choice(200, size=n, replace=False))
+    grads = rng.standard_normal((G * K, 3)).astype(np.float32)
+    flat = rows.reshape(-1)
+    pos = np.full(G * K, -1, dtype=np.int64)
+    for e in range(G * K):
+        x = flat[e]
+        if x == INV:
+            continue
+        r = e // K
+        p = e - r * K
+        for q in range(G):
+            if q != r:
+                p += np.searchsorted(rows[q], x, side="right" if q < r else "left")
+        pos[e] = p
+    valid = flat != INV
+    nv = int(valid.sum())
+    assert sorted(pos[valid].tolist()) == list(range(nv))                 # a permutation of [0, n_valid)
+    order = np.empty(nv, dtype=np.int64)
+    order[pos[valid]] = np.nonzero(valid)[0]
+    ref = np.nonzero(valid)[0][np.argsort(flat[valid], kind="stable")]    # stable sort of the concatenation
+    np.testing.assert_array_equal(order, ref)
+    # unique rows + sums in merged order == the reference merge
+    keys = flat[order]
+    uniq, start = np.unique(keys, return_index=True)
+    sums = np.add.reduceat(grads[order].astype(np.float64), start, axis=0)
+    as_i32 = np.where(valid, flat, INVALID_ROW).astype(np.int32)           # what torch sees: int32 with -1 for the marker
+    u2, s2 = merge_sparse_host(torch.from_numpy(as_i32), torch.from_numpy(grads))
+    np.testing.assert_array_equal(uniq, u2.numpy())
+    np.testing.assert_allclose(sums, s2.numpy().astype(np.float64), rtol=0, atol=1e-5)
