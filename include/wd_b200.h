@@ -216,8 +216,9 @@ int wd_last_timings(WdModel *m, float *ms_out, int cap);
 const char *wd_timing_name(WdModel *m, int i);
 int wd_set_profile(WdModel *m, int enable);
 void *wd_stream(WdModel *m);
-/* Stream on which sparse gradient list `which` is produced and on which wd_sparse_set will merge it: the wide list
- * is finished on a side stream while the towers' backward still runs, so its exchange can overlap that work. */
+/* Stream on which sparse gradient list `which` is produced and on which wd_sparse_set(_sorted) will merge it and
+ * wd_step_apply will apply it: each list has its own side stream, so its exchange overlaps the other list's and the
+ * dense all-reduce on wd_stream. */
 void *wd_stream_sparse(WdModel *m, int which);
 int wd_sync(WdModel *m);
 
