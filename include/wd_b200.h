@@ -216,6 +216,10 @@ int wd_last_timings(WdModel *m, float *ms_out, int cap);
 const char *wd_timing_name(WdModel *m, int i);
 int wd_set_profile(WdModel *m, int enable);
 void *wd_stream(WdModel *m);
+/* Timeline probe of the 3xBF16 GEMM (set WD_GEMM_PROBE=1 before the first launch): globaltimer stamps of CTA 0 for the last 32
+ * launches, 8 per launch — kernel start, first operands landed, main loop of the first / last tile done, epilogue of the first tile
+ * start / end, epilogue of the last tile start / end; out: uint64[256].  tools/gemm_probe.py prints them per layer. */
+int wd_debug_gemm_probe(unsigned long long *out);
 /* Stream on which sparse gradient list `which` is produced and on which wd_sparse_set(_sorted) will merge it and
  * wd_step_apply will apply it: each list has its own side stream, so its exchange overlaps the other list's and the
  * dense all-reduce on wd_stream. */

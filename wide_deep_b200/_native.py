@@ -72,6 +72,7 @@ SYMBOLS = {
     "wd_batch_upload_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "wd_batch_prefetch_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "wd_last_loss": (ctypes.c_int, [_vp, _vp]),
+    "wd_debug_gemm_probe": (ctypes.c_int, [_vp]),
     "wd_train_step_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "wd_set_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "wd_stream": (_vp, [_vp]),

@@ -8,7 +8,7 @@
 // 4 k-steps x 3 tcgen05.mma.kind::f16 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) into one fp32 accumulator.  hi + lo represents x to
 // 2^-17 and the dropped a_lo*b_lo term is below 2^-16, so one product carries ~1e-5 relative error (rms ~8e-6; random signs, so a
 // long dot product does better): measured 5e-6 on the logits of the benchmark shape, up to ~1e-4 on small ill-conditioned
-// towers (tests/test_gpu_parity.py, scratch/engine_err.py).  That is a FAST mode: it meets the 1e-4 logit bar on the
+// towers (tests/test_gpu_parity.py, tests/engine_error_report.py).  That is a FAST mode: it meets the 1e-4 logit bar on the
 // benchmarked configuration (bench.py re-checks it against the oracle in the same run) but is not fp32-faithful the way the
 // 3xTF32 engine (gemm_tc.cu, 2^-21) is; it costs half the shared-memory bytes per flop, runs at twice the tensor-pipe rate and
 // needs no in-kernel splitting pass.  (Keeping the residual in fp16 would give 19 bits, but tcgen05.mma.kind::f16 traps with an
