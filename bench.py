@@ -12,11 +12,16 @@ Workload (config.workload): BASELINE.json configs[1] / [2] — synthetic Criteo 
 JSON keys beyond the base contract:
   value     examples/s with the step's inputs already resident in HBM (a ring of distinct batches, so the
             rows each step touches are not the ones left in L2 by the previous step)
-  e2e       the same metric through the public host-buffer call (wd_train_step): pinned-host -> device copy of
-            the batch and device -> host read of the loss inside the timed region, every step
-  roofline  dominant kernel (MLP GEMMs) as achieved TFLOP/s vs the measured dense-bf16 tensor peak, timed live
-            with CUDA events on the model stream; `kernels` carries the same for the embedding gather (HBM)
+  e2e       the same metric fed from pinned host memory the way estimator.train feeds it: wd_batch_prefetch_slot refills two
+            alternating slots on the upload stream (the copy of step i+1 overlaps step i, like dataset.prefetch in the reference),
+            wd_train_step_slot runs the step, and every step ends with a device -> host read of its loss — all timed
+  roofline  dominant kernel group (the nine MLP GEMM launches) as achieved fp32-equivalent TFLOP/s vs the measured dense-bf16
+            tensor peak, timed live with CUDA events on the model stream; `kernels` carries the same for the embedding gather (HBM)
+  gemm_engine   bf16x3 by default here (2^-16 products); `parity` re-checks it against the oracle in this run (bar 1e-4) and
+            `strict_engine` reports the same step on the fp32-faithful tc3x engine (the library default)
   cpu_baseline  the oracle (CPU restatement of the reference; TensorFlow itself cannot run here) on the host cores
+Multi-GPU (config.exchange): one all-reduce for dense gradients + small-table gradient blocks, all-gather + on-device merge of the
+large tables' (row, gradient) lists; WD_DP_PROFILE=1 prints the phase timeline of a data-parallel step to stderr.
 """
 import argparse
 import json
