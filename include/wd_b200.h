@@ -239,7 +239,8 @@ typedef struct WdTsvSpec {
     int32_t use_weight;
     int32_t has_label;
 } WdTsvSpec;
-/* Returns nnz, or negative error.  Two-call protocol: keys_cap==0 -> only counts (offsets filled). */
+/* Returns nnz, or negative error.  keys_cap == 0 (or keys_out NULL): only counts (offsets filled) — call again with a buffer of nnz
+ * keys; or call once with keys_cap >= an upper bound (without tf_compat_pad: n_lines * n_cat_fields + number of ',' in the text). */
 int64_t wd_tsv_parse(const WdTsvSpec *spec, const char *text, int64_t text_len, int32_t n_lines,
                      int32_t *offsets_out, uint64_t *keys_out, int64_t keys_cap,
                      float *dense_out, float *label_out, float *weight_out, int32_t n_threads);

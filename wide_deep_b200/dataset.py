@@ -76,23 +76,30 @@ class TsvReader(object):
         self._lib = _native.lib()
 
     def parse(self, lines):
-        """list of text lines (no trailing newline needed) -> Batch"""
-        text = ("\n".join(l.rstrip("\n") for l in lines)).encode("utf-8")
+        """list of text lines (str or bytes, no trailing newline needed) -> Batch"""
+        if lines and isinstance(lines[0], bytes):
+            text = b"\n".join(lines)                                  # input_fn's path: no decode / encode round trip
+        else:
+            text = ("\n".join(l.rstrip("\n") for l in lines)).encode("utf-8")
         n = len(lines)
         F, Nd = len(self.plan.cat_fields), len(self.plan.dense_fields)
         offsets = np.zeros(n * F + 1, dtype=np.int32)
         dense = np.zeros((n, max(Nd, 1)), dtype=np.float32)
         label = np.zeros(n, dtype=np.float32)
         weight = np.ones(n, dtype=np.float32)
-        # pass 1: counts (keys_cap = 0), pass 2: keys
-        nnz = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, offsets.ctypes.data, None, 0,
-                                     dense.ctypes.data, label.ctypes.data, weight.ctypes.data, self.n_threads)
+        if self.plan.tf_compat_pad:
+            # padded string fields (quirk Q2) can exceed the token count: ask for the size first (keys_cap = 0), then fill
+            nnz = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, offsets.ctypes.data, None, 0,
+                                         dense.ctypes.data, label.ctypes.data, weight.ctypes.data, self.n_threads)
+            if nnz < 0:
+                raise ValueError(self._lib.wd_last_error().decode())
+            cap = max(nnz, 1)
+        else:
+            cap = n * max(F, 1) + text.count(b",") + 1               # every field holds at most (commas + 1) tokens
+        keys = np.empty(cap, dtype=np.uint64)
+        nnz = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, offsets.ctypes.data, keys.ctypes.data,
+                                     keys.size, dense.ctypes.data, label.ctypes.data, weight.ctypes.data, self.n_threads)
         if nnz < 0:
-            raise ValueError(self._lib.wd_last_error().decode())
-        keys = np.zeros(max(nnz, 1), dtype=np.uint64)
-        nnz2 = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, offsets.ctypes.data, keys.ctypes.data,
-                                      keys.size, dense.ctypes.data, label.ctypes.data, weight.ctypes.data, self.n_threads)
-        if nnz2 != nnz:
             raise ValueError(self._lib.wd_last_error().decode())
         return Batch(n, keys[:nnz], offsets, dense[:, :Nd] if Nd else None, None if self.is_pred else label,
                      weight if (self.use_weight and not self.is_pred) else None)
@@ -108,8 +115,8 @@ def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=N
     reader = TsvReader(config, plan, is_pred=(mode == "pred"))
     lines = []
     for f in list_files(csv_data_file):
-        with open(f) as fh:
-            lines.extend(l for l in fh.read().split("\n") if l != "")
+        with open(f, "rb") as fh:
+            lines.extend(l for l in fh.read().split(b"\n") if l != b"")
     if world > 1:
         lines = lines[rank::world]
     if mode == "train":
