@@ -94,18 +94,19 @@ class WideAndDeepClassifier(object):
         m = self._ensure_model()
         n, t0, loss = 0, time.time(), float("nan")
         log_every = (self.config.runconfig or {}).get("log_step_count_steps") or 1000
-        # one batch of look-ahead, as the reference's input_fn prefetches (python/lib/dataset.py:181-184): batch i+1 is parsed and
-        # its host->device copy issued (wd_batch_prefetch_slot, two alternating slots) before step i is waited for
+        # one batch of look-ahead, as the reference's input_fn prefetches (python/lib/dataset.py:181-184): while step i runs on the
+        # GPU, batch i+1 is parsed and its host->device copy issued (wd_batch_prefetch_slot, two alternating slots)
         it = iter(input_fn())
         cur = next(it, None)
         slot = 0
         if cur is not None:
             m.prefetch_slot(slot, cur)
         while cur is not None:
-            nxt = next(it, None)
+            m.train_step_slot(slot, want_loss=False)         # enqueue step i ...
+            nxt = next(it, None)                             # ... parse batch i+1 on the host while it runs ...
             if nxt is not None:
-                m.prefetch_slot(1 - slot, nxt)
-            loss = m.train_step_slot(slot, want_loss=True)
+                m.prefetch_slot(1 - slot, nxt)               # ... start its copy on the upload stream ...
+            loss = m.last_loss()                             # ... and only then wait for step i's loss
             n += 1
             if n % log_every == 0:
                 print("INFO: global_step %d: loss = %.6g (%.1f steps/sec)" % (m.global_step, loss, n / (time.time() - t0)))
