@@ -97,6 +97,25 @@ def test_checkpoint_roundtrip(tmp_path):
     assert m1 == m2 and m2["global_step"] == 1
 
 
+def test_estimator_train_equals_direct_steps(tmp_path):
+    """estimator.train (step i enqueued, batch i+1 parsed and prefetched into the other slot meanwhile, then the loss of step i
+    read) must leave exactly the parameters that plain train_step calls over the same batches leave (same seed, same order)."""
+    from wide_deep_b200.config import Config
+    from wide_deep_b200.dataset import input_fn
+    from wide_deep_b200.estimator import build_custom_estimator
+    cfg = Config()
+    data = os.path.join(ROOT, "data", "eval", "eval1")                      # 256 rows -> four batches of 64
+    est_a = build_custom_estimator(str(tmp_path / "a"), "wide_deep", config=cfg, max_batch=64)
+    est_a.train(input_fn=lambda: input_fn(data, None, "train", 64, config=cfg, plan=est_a.plan))
+    est_b = build_custom_estimator(str(tmp_path / "b"), "wide_deep", config=cfg, max_batch=64)
+    mb = est_b._ensure_model()                                             # fresh model, same seed as est_a's
+    losses = [mb.train_step(b) for b in input_fn(data, None, "train", 64, config=cfg, plan=est_b.plan)]
+    ma = est_a._ensure_model()
+    assert ma.global_step == mb.global_step == 4 and np.isfinite(losses).all()
+    for name in ma.tensor_names()[:12]:
+        np.testing.assert_array_equal(ma.get_tensor(name), mb.get_tensor(name))
+
+
 def test_device_fingerprint64_bit_exact(native_lib):
     import random
     from oracle import hashing as H
