@@ -146,9 +146,11 @@ class DataParallelTrainer(object):
     def _collectives(self):
         m = self.model
         if self.fixed is not None:
-            # asynchronous path: each list is exchanged on the stream that produced it — the wide list is ready while
-            # the towers' backward still runs on the main stream, so its all-gather + merge hide behind that work
-            for which in sorted(self.lists, reverse=True):              # wide (1) first
+            # asynchronous path: each list is exchanged, merged and later applied on its own side stream.  With the forward +
+            # backward replayed from one CUDA graph both lists become ready together, and the collectives of one communicator
+            # run in issue order: the embedding list (larger, longest merge + apply chain) goes first, the wide list second,
+            # the dense all-reduce (shortest tail) last
+            for which in sorted(self.lists):                             # embedding rows (0), then wide rows (1)
                 f = self.fixed[which]
                 sptr = m.stream_sparse(which)
                 if sptr not in self._ext:
