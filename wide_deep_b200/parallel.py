@@ -122,7 +122,7 @@ class DataParallelTrainer(object):
         m.step_backward_slot(slot, want_loss=False)
         marks = {}
         e = ev(); e.record(self.stream); marks["backward(main)"] = e
-        for which in sorted(self.lists, reverse=True):
+        for which in sorted(self.lists):
             f = self.fixed[which]
             sptr = m.stream_sparse(which)
             st = self._ext.setdefault(sptr, torch.cuda.ExternalStream(sptr, device=self.device))
