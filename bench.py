@@ -185,7 +185,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = 2048                     # bounded sample of the same workload (same tables, smaller batch)
+    rows = PER_GPU_BATCH            # the same step as the GPU arm (same tables, same batch size), a bounded number of them
     warm = max(1, min(args.warmup, 2))
     v, sec, steps = oracle_examples_per_sec(rows, max(1, args.steps), warm, threads, budget_s=90.0)   # K steps or 90 s of CPU work
     sample = "%d steps of %d examples (same tables/config), %d threads" % (steps, rows, threads)
@@ -423,9 +423,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             out["parity"] = parity_check(args.engine)
             threads = os.cpu_count() or 1
-            v, sec, _ = oracle_examples_per_sec(2048, 3, 1, threads)
+            v, sec, _ = oracle_examples_per_sec(B, 3, 1, threads)
             out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
-                                   "sample": "3 steps of 2048 examples, same tables/config (oracle, fp32 accumulate)"}
+                                   "sample": "3 steps of %d examples, same tables/config (oracle, fp32 accumulate)" % B}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -243,7 +243,7 @@ class OracleModel(object):
             wl = np.full(B, self.params["linear/linear_model/bias_weights"][0], dtype=A)
             for c in self.wide_cols:
                 offs, cid = ids[c.name]
-                wl += _csr(offs, cid, c.num_buckets, dtype=A) @ self.params[self.wname(c)].astype(A)
+                wl += _csr(offs, cid, c.num_buckets, dtype=A) @ self.params[self.wname(c)].astype(A, copy=False)
             cache["wide_logit"] = wl
             logits += wl
         if self.use_deep:
@@ -259,7 +259,7 @@ class OracleModel(object):
                     offs, cid = ids[c.cat.name]
                     cnt = np.diff(offs)
                     w = np.repeat(1.0 / np.maximum(cnt, 1), cnt)
-                    X[:, o:o + c.dim] = _csr(offs, cid, c.cat.num_buckets, w, dtype=A) @ self.params[self.ename(c)].astype(A)
+                    X[:, o:o + c.dim] = _csr(offs, cid, c.cat.num_buckets, w, dtype=A) @ self.params[self.ename(c)].astype(A, copy=False)
             cache["X"] = X
             dl = np.zeros(B, dtype=A)
             cache["towers"] = []
@@ -281,17 +281,17 @@ class OracleModel(object):
         for l in range(len(hu)):
             scope = "dnn/dnn_%d/hiddenlayer_%d" % (t + 1, l)
             inp = np.concatenate([pick(s) for s in srcs[l]], axis=1)
-            z = inp @ self.params[scope + "/kernel"].astype(A) + self.params[scope + "/bias"].astype(A)
+            z = inp @ self.params[scope + "/kernel"].astype(A, copy=False) + self.params[scope + "/bias"].astype(A, copy=False)
             a = act_fwd(self.act, z)
             if self.bn:   # A.8: always inference mode, moving mean 0 / var 1 (quirk Q4)
-                h = a * (self.params[scope + "/batch_normalization/gamma"].astype(A) * inv) \
-                    + self.params[scope + "/batch_normalization/beta"].astype(A)
+                h = a * (self.params[scope + "/batch_normalization/gamma"].astype(A, copy=False) * inv) \
+                    + self.params[scope + "/batch_normalization/beta"].astype(A, copy=False)
             else:
                 h = a
             INP.append(inp); Z.append(z); Aact.append(a); H.append(h)
         scope = "dnn/dnn_%d/logits" % (t + 1)
         inp = np.concatenate([pick(s) for s in srcs[-1]], axis=1)
-        logit = (inp @ self.params[scope + "/kernel"].astype(A) + self.params[scope + "/bias"].astype(A))[:, 0]
+        logit = (inp @ self.params[scope + "/kernel"].astype(A, copy=False) + self.params[scope + "/bias"].astype(A, copy=False))[:, 0]
         INP.append(inp)
         return dict(H=H, Z=Z, A=Aact, INP=INP, logit=logit, srcs=srcs)
 
@@ -353,7 +353,7 @@ class OracleModel(object):
                 o += wd
 
         scope = "dnn/dnn_%d/logits" % (t + 1)
-        K = self.params[scope + "/kernel"].astype(A)
+        K = self.params[scope + "/kernel"].astype(A, copy=False)
         grads[scope + "/kernel"] = tc["INP"][L].T @ dlogit[:, None]
         grads[scope + "/bias"] = np.array([dlogit.sum()])
         scatter(dlogit[:, None] @ K.T, srcs[L])
@@ -361,7 +361,7 @@ class OracleModel(object):
             scope = "dnn/dnn_%d/hiddenlayer_%d" % (t + 1, l)
             dh = dH[l]
             if self.bn:
-                gam = self.params[scope + "/batch_normalization/gamma"].astype(A)
+                gam = self.params[scope + "/batch_normalization/gamma"].astype(A, copy=False)
                 grads[scope + "/batch_normalization/gamma"] = (dh * tc["A"][l]).sum(0) * inv
                 grads[scope + "/batch_normalization/beta"] = dh.sum(0)
                 da = dh * (gam * inv)
@@ -370,7 +370,7 @@ class OracleModel(object):
             dz = da * act_bwd(self.act, tc["Z"][l], tc["A"][l])
             grads[scope + "/kernel"] = tc["INP"][l].T @ dz
             grads[scope + "/bias"] = dz.sum(0)
-            scatter(dz @ self.params[scope + "/kernel"].astype(A).T, srcs[l])
+            scatter(dz @ self.params[scope + "/kernel"].astype(A, copy=False).T, srcs[l])
 
     # ---- optimizers (A.9)
     def apply(self, grads):
