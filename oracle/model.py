@@ -310,7 +310,8 @@ class OracleModel(object):
         A = self.acc
         x = cache["logits"].astype(np.float64)
         w = np.ones_like(x) if weights is None else weights.astype(np.float64)
-        dlogit = ((1.0 / (1.0 + np.exp(-x)) - labels.astype(np.float64)) * w).astype(A)
+        with np.errstate(over="ignore"):                 # exp(-x) -> inf for very negative logits: 1 / inf = 0 is the right sigmoid
+            dlogit = ((1.0 / (1.0 + np.exp(-x)) - labels.astype(np.float64)) * w).astype(A)
         grads, ids, B = {}, cache["ids"], cache["B"]
         if self.use_wide:
             grads["linear/linear_model/bias_weights"] = np.array([dlogit.sum()])
