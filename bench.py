@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 
 PER_GPU_BATCH = 8192
 RING = 8
+# arithmetic the MLP GEMMs run in (tables, optimizers, pooling and every reduction are fp32 in all engines)
+DTYPE_OF_ENGINE = {"bf16x3": "bf16x3 (fp32 operands split into bf16 hi+lo, 3 tensor-core products, fp32 accumulate; 2^-16)",
+                   "tc3x": "tf32x3 (fp32 operands split into tf32 hi+lo, 3 tensor-core products, fp32 accumulate; 2^-21)",
+                   "tc1x": "tf32", "ffma": "f32", "auto": "tf32x3 (library default)"}
 
 
 def load_peaks():
@@ -46,6 +50,22 @@ def load_peaks():
         d = json.load(open(p))
         return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def gemm_traffic_from_profile(engine, batch):
+    """DRAM bytes of the GEMM launches of one step, from the newest committed ncu capture that matches (engine, batch):
+    profiles/*_gemm_traffic.json = {"engine", "batch", "dram_bytes_per_step", "command", "source"} written by
+    tools/ncu_summary.py --traffic from the `ncu --set full` raw CSV.  (None, reason) when no capture matches — never a constant."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json"))):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        if d.get("engine") == engine and int(d.get("batch", -1)) == int(batch):
+            best = (float(d["dram_bytes_per_step"]), os.path.relpath(path, ROOT))
+    return best if best else (None, "no committed ncu capture for engine=%s batch=%d" % (engine, batch))
 
 
 class ClockSampler(object):
@@ -153,14 +173,17 @@ def config_dict(n_gpus, per_gpu_batch):
 
 # ------------------------------------------------------------------------------------------- reference arm
 def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32, budget_s=None):
-    """Time the CPU restatement (oracle) on the same workload; returns (examples/s, seconds per step)."""
+    """Time the OPTIMISED CPU restatement (oracle/fast.py: torch-CPU matmuls + embedding_bag + sparse row updates, C hashing;
+    checked against oracle/model.py by tests/test_oracle_fast.py) on the same workload with every host thread; returns
+    (examples/s, seconds per step, steps timed).  torch.distributed.run exports OMP_NUM_THREADS=1: overridden explicitly."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["MKL_NUM_THREADS"] = str(threads)
     import torch
     torch.set_num_threads(threads)
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    from oracle import model as OM
+    from oracle import fast as OF, model as OM
     from wide_deep_b200 import synthetic
     fc, cross, model, emb, n_cat, n_dense, _ = workload(1, batch_rows)
-    om = OM.OracleModel(fc, cross, model, "wide_deep", embedding_dim_override=emb, acc=acc).init(1)
+    om = OF.FastCpuModel(OM.OracleModel(fc, cross, model, "wide_deep", embedding_dim_override=emb, acc=acc).init(1), threads=threads)
     cats = [f for f, c in fc.items() if c["type"] == "category"]
     dense_names = [f for f, c in fc.items() if c["type"] == "continuous"]
     times = []
@@ -185,16 +208,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = PER_GPU_BATCH            # the same step as the GPU arm (same tables, same batch size), a bounded number of them
+    # the same step as the GPU arm: same tables, same GLOBAL batch (N x 8192: the CPU arm is the whole box's host cores, whatever N
+    # is), a bounded number of steps
+    rows = args.batch * max(1, args.gpus)
     warm = max(1, min(args.warmup, 2))
     v, sec, steps = oracle_examples_per_sec(rows, max(1, args.steps), warm, threads, budget_s=90.0)   # K steps or 90 s of CPU work
-    sample = "%d steps of %d examples (same tables/config), %d threads" % (steps, rows, threads)
+    sample = "%d steps of %d examples (same tables/config as the GPU arm at N=%d), %d threads" % (steps, rows, args.gpus, threads)
     out = {"impl": "reference", "metric": "CTR examples/sec (train step)", "value": v, "unit": "examples/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": config_dict(1, rows),
+           "config": config_dict(max(1, args.gpus), args.batch),
            "cpu_baseline": {"value": v, "unit": "examples/s", "cores": threads, "kind": "port", "sample": sample,
-                            "note": "CPU restatement of the reference step (numpy/scipy oracle); TensorFlow 1.x is not installable here"},
+                            "note": "optimised CPU restatement of the reference step (oracle/fast.py: torch-CPU sgemm + embedding_bag + "
+                                    "sparse row updates, C hashing); TensorFlow 1.x is not installable here"},
            "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -372,7 +398,8 @@ def main():
         e2e = gb * args.steps / (ms_e2e / 1e3)
         out = {"metric": "CTR examples/sec (train step)", "value": value, "unit": "examples/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, B),
+               "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF_ENGINE.get(args.engine, "f32"), "data": "synthetic",
+               "config": config_dict(world, B),
                "e2e": {"value": e2e, "unit": "examples/s", "ms_per_step": ms_e2e / args.steps,
                        "h2d_bytes_per_step": host[0][0].h2d_bytes(), "d2h_bytes_per_step": 8,
                        "input": "pinned host batches, wd_batch_prefetch_slot into two alternating slots (copy of step i+1 overlaps step i), loss read every step"},
@@ -382,13 +409,16 @@ def main():
             gemm_ms = sum(v for k, v in phases.items() if k.startswith("gemm_"))
             flops = 6.0 * B * P                                   # 2BP forward + 4BP backward
             ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+            traffic, traffic_src = gemm_traffic_from_profile(args.engine, B)
             out["roofline"] = {"kernel": "mlp gemm (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                               # dram__bytes_read.sum + dram__bytes_write.sum over the nine GEMM launches of one step, from the ncu
-                               # --set full capture in profiles/r1_full_summary.md (bf16x3, B = 8192); None for other settings
-                               "traffic": 363.0e6 if (args.engine == "bf16x3" and B == 8192) else None,
-                               "traffic_unit": "bytes per step (9 launches)",
-                               "peak_source": peaks["source"] + " dense bf16 (sustained).  achieved = algorithmic fp32 FLOPs (6*B*P) / GEMM time; "
+                               # the GEMMs run inside a long step, back to back with the rest of it: the SUSTAINED peak applies; the
+                               # fraction against the burst figure (a kernel timed alone) is given beside it
+                               "peak_burst": peaks["bf16_burst"], "frac_burst": ach / peaks["bf16_burst"], "peak_applies": "sustained",
+                               # dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one step, read from the
+                               # committed ncu capture of this engine / batch size (profiles/*_gemm_traffic.json); null when there is none
+                               "traffic": traffic, "traffic_unit": "bytes per step (all GEMM launches of one step)", "traffic_source": traffic_src,
+                               "peak_source": peaks["source"] + " dense bf16.  achieved = algorithmic fp32 FLOPs (6*B*P) / GEMM time; "
                                               "both split engines issue 3 tensor-core products per algorithmic one, so the fp32-"
                                               "equivalent ceiling is 1/3 of the bf16 peak for bf16x3 and 1/6 for tc3x",
                                "tensor_pipe_frac": 3.0 * ach / peaks["bf16_sustained"] * (2.0 if args.engine == "tc3x" else 1.0),
@@ -423,9 +453,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             out["parity"] = parity_check(args.engine)
             threads = os.cpu_count() or 1
-            v, sec, _ = oracle_examples_per_sec(B, 3, 1, threads)
+            v, sec, nst = oracle_examples_per_sec(B, 10, 2, threads, budget_s=20.0)
             out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
-                                   "sample": "3 steps of %d examples, same tables/config (oracle, fp32 accumulate)" % B}
+                                   "sample": "%d steps of %d examples, same tables/config (oracle/fast.py: torch-CPU + C hashing, fp32)" % (nst, B)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

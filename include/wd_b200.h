@@ -209,6 +209,10 @@ int wd_debug_deep_input(WdModel *m, float *out, int64_t cap);
 int wd_debug_hidden(WdModel *m, int tower, int layer, float *out, int64_t cap);
 /* Kernel launch counter (launches of this library's kernels since creation). */
 int64_t wd_launch_count(WdModel *m);
+/* How many MLP GEMMs of a tensor-core engine (tc3x / tc1x) were handed to the fp32 FFMA kernel because their shape is not
+ * covered by the tcgen05 kernel.  0 for every plan the library builds itself (all widths are padded to whole k-blocks); the
+ * tests assert 0 so a silent downgrade cannot hide. */
+int64_t wd_gemm_fallback_count(WdModel *m);
 /* Per-phase device timings of the last synchronised step in milliseconds (CUDA events recorded on the model
  * stream between the stages, enabled by wd_set_profile).  Returns the number of phases n and fills
  * ms_out[0..min(n,cap)): [0] = whole step, [i] = the phase ending at mark wd_timing_name(m, i). */

@@ -80,7 +80,7 @@ def test_entry_points_train_then_eval(tmp_path):
     assert "average_loss:" in r2.stdout and "global_step:" in r2.stdout
     r3 = subprocess.run([sys.executable, "pred.py", "--model_dir", mdir, "--data_dir", "../data/pred", "--batch_size", "64"],
                         cwd=os.path.join(ROOT, "python"), env=env, capture_output=True, text=True, timeout=600)
-    assert r3.returncode == 0 and r3.stdout.count("Prediction is") == 64, r3.stdout[-1000:] + r3.stderr[-1000:]
+    assert r3.returncode == 0 and r3.stdout.count("Prediction is") == 5000, r3.stdout[-1000:] + r3.stderr[-1000:]
 
 
 def test_checkpoint_roundtrip(tmp_path):
@@ -104,14 +104,14 @@ def test_estimator_train_equals_direct_steps(tmp_path):
     from wide_deep_b200.dataset import input_fn
     from wide_deep_b200.estimator import build_custom_estimator
     cfg = Config()
-    data = os.path.join(ROOT, "data", "eval", "eval1")                      # 256 rows -> four batches of 64
+    data = os.path.join(ROOT, "data", "eval", "eval1")                      # 5000 rows -> 79 batches of 64
     est_a = build_custom_estimator(str(tmp_path / "a"), "wide_deep", config=cfg, max_batch=64)
     est_a.train(input_fn=lambda: input_fn(data, None, "train", 64, config=cfg, plan=est_a.plan))
     est_b = build_custom_estimator(str(tmp_path / "b"), "wide_deep", config=cfg, max_batch=64)
     mb = est_b._ensure_model()                                             # fresh model, same seed as est_a's
     losses = [mb.train_step(b) for b in input_fn(data, None, "train", 64, config=cfg, plan=est_b.plan)]
     ma = est_a._ensure_model()
-    assert ma.global_step == mb.global_step == 4 and np.isfinite(losses).all()
+    assert ma.global_step == mb.global_step == 79 and np.isfinite(losses).all()
     for name in ma.tensor_names()[:12]:
         np.testing.assert_array_equal(ma.get_tensor(name), mb.get_tensor(name))
 
@@ -128,3 +128,13 @@ def test_device_fingerprint64_bit_exact(native_lib):
     rc = native_lib.wd_fingerprint64_device(buf.ctypes.data, offs.ctypes.data, len(strs), out.ctypes.data)
     assert rc == 0
     assert [int(v) for v in out] == [H.fingerprint64(s) for s in strs]
+    # ... and against the Abseil-derived known answers (0..32 bytes) directly, not only through the oracle
+    import json
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "cityhash_le32_kat.json")))["vectors"]
+    strs = [bytes.fromhex(v["hex"]) for v in kat]
+    buf = np.frombuffer(b"".join(strs) + b"\0", dtype=np.uint8).copy()
+    offs = np.zeros(len(strs) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum([len(s) for s in strs])
+    out = np.zeros(len(strs), dtype=np.uint64)
+    assert native_lib.wd_fingerprint64_device(buf.ctypes.data, offs.ctypes.data, len(strs), out.ctypes.data) == 0
+    assert [int(v) for v in out] == [int(v["hash"]) for v in kat]

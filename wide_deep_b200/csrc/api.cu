@@ -1243,6 +1243,7 @@ extern "C" int wd_debug_hidden(WdModel* m, int tower, int layer, float* out, int
     return L.N_phys;
 }
 extern "C" int64_t wd_launch_count(WdModel* m) { return m ? m->launches : 0; }
+extern "C" int64_t wd_gemm_fallback_count(WdModel* m) { return m ? m->gemm_fallbacks : 0; }
 extern "C" int wd_last_timings(WdModel* m, float* ms_out, int cap) {
     if (!m) return WD_EINVAL;
     int n = m->timer.n_last;

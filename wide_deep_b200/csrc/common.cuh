@@ -288,6 +288,7 @@ struct WdModel {
     int64_t eval_batches = 0;
 
     int64_t launches = 0;
+    int64_t gemm_fallbacks = 0;             // tensor-core engine GEMMs that ran on the FFMA kernel instead (tests assert 0)
     int cur_slot = 0;
     bool graphs_enabled = true;              // WD_NO_GRAPH=1 disables step graphs
     int cur_layer = 0;                       // layer being launched (names the profiling marks)

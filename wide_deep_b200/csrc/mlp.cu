@@ -181,6 +181,9 @@ static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ld
     if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
         int rc = tc_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len, B_hi, B_lo);
         if (rc != WD_EUNSUPPORTED) { mark(m, kNames[mode]); return rc; }
+        m->gemm_fallbacks++;                              // loud: counted, reported by wd_gemm_fallback_count, asserted 0 in the tests
+        static bool warned = false;
+        if (!warned) { fprintf(stderr, "libwd_b200: tcgen05 engine does not cover a GEMM (M=%d N=%d segs=%d): running it on the FFMA kernel\n", M, N, A.n); warned = true; }
     }
     launch_gemm(m, mode, A, B, ldb, M, N, ep, splits, ksplit_len);
     mark(m, kNames[mode]);

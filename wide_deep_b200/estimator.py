@@ -24,7 +24,7 @@ CKPT_PREFIX = "model.ckpt-"
 
 
 class WideAndDeepClassifier(object):
-    def __init__(self, model_dir, model_type, config=None, device=0, max_batch=None, seed=None, tf_compat_pad=False,
+    def __init__(self, model_dir, model_type, config=None, device=0, max_batch=None, seed=None, tf_compat_pad=None,
                  gemm_engine="auto"):
         if model_type not in ("wide", "deep", "wide_deep"):
             raise ValueError("Invalid model type: {}, must be one of `wide`, `deep`, `wide_deep`".format(model_type))
@@ -34,7 +34,15 @@ class WideAndDeepClassifier(object):
         self.seed = run.get("tf_random_seed", 123) if seed is None else seed
         self.keep_checkpoint_max = run.get("keep_checkpoint_max") or 5
         mb = max_batch or self.config.train["batch_size"]
+        # quirk Q2: the reference pads multi-valued string fields with '' per batch and the padding takes
+        # part in SparseCross.  The file-based entry points reproduce that by default (train.yaml key `tf_compat_pad`, default
+        # true), so train.py / eval.py / pred.py produce the ids the reference produces on the same file.
+        if tf_compat_pad is None:
+            tf_compat_pad = bool(self.config.train.get("tf_compat_pad", True))
+        self.tf_compat_pad = bool(tf_compat_pad)
         slack = 8 if self.config.train.get("multivalue") else 1
+        if self.tf_compat_pad and self.config.train.get("multivalue"):
+            slack *= 4                                   # '' padding multiplies the ids of crosses over multi-valued fields
         self.plan = compile_plan(self.config, model_type, mb, tf_compat_pad=tf_compat_pad, gemm_engine=gemm_engine,
                                  max_nnz=mb * len(self.config.read_feature_conf()) * 4 * slack + mb * 64,
                                  max_keys=mb * max(1, len(self.config.read_feature_conf())) * slack)
@@ -49,10 +57,13 @@ class WideAndDeepClassifier(object):
                        if f.startswith(CKPT_PREFIX) and f.endswith(".npz"))
         return os.path.join(self.model_dir, "%s%d.npz" % (CKPT_PREFIX, steps[-1])) if steps else None
 
-    def _ensure_model(self, checkpoint_path=None):
+    def _ensure_model(self, checkpoint_path=None, need_trained=False):
         if self._model is None:
-            self._model = WideDeepModel(self.plan, device=self.device)
             path = checkpoint_path or self.latest_checkpoint()
+            if need_trained and not path:
+                # tf.estimator raises the same way: "Could not find trained model in model_dir"
+                raise ValueError("Could not find trained model in model_dir: {}.".format(self.model_dir))
+            self._model = WideDeepModel(self.plan, device=self.device)
             if path:
                 self.restore(path)
             else:
@@ -72,7 +83,12 @@ class WideAndDeepClassifier(object):
             for s in range(m.n_slots(name)):
                 blob["%s/slot%d" % (name, s + 1)] = m.get_tensor(name, slot=s + 1)
         path = os.path.join(self.model_dir, "%s%d.npz" % (CKPT_PREFIX, m.global_step))
-        np.savez(path, **blob)
+        tmp = path + ".tmp.%d" % os.getpid()                 # written beside, then renamed: a crash never leaves a truncated
+        with open(tmp, "wb") as fh:                          # checkpoint that latest_checkpoint() would pick up
+            np.savez(fh, **blob)
+            fh.flush()
+            os.fsync(fh.fileno())
+        os.replace(tmp, path)
         olds = sorted(int(f[len(CKPT_PREFIX):-4]) for f in os.listdir(self.model_dir) if f.startswith(CKPT_PREFIX) and f.endswith(".npz"))
         for st in olds[:-self.keep_checkpoint_max]:
             os.remove(os.path.join(self.model_dir, "%s%d.npz" % (CKPT_PREFIX, st)))
@@ -81,11 +97,22 @@ class WideAndDeepClassifier(object):
     def restore(self, path):
         m = self._model
         with np.load(path) as z:
-            m.global_step = int(z["global_step"])
+            have = set(z.files)
+            want = []
             for name in m.tensor_names():
-                m.set_tensor(name, z[name])
+                want.append((name, 0, tuple(self.plan.tensor_names[name][3])))
                 for s in range(m.n_slots(name)):
-                    m.set_tensor(name, z["%s/slot%d" % (name, s + 1)], slot=s + 1)
+                    want.append(("%s/slot%d" % (name, s + 1), s + 1, tuple(self.plan.tensor_names[name][3])))
+            missing = [k for k, _, _ in want if k not in have]
+            if missing or "global_step" not in have:
+                raise ValueError("checkpoint {} does not match this model (feature conf, model_type or optimizers changed?): "
+                                 "missing {} of {} tensors, e.g. {}".format(path, len(missing), len(want), missing[:3]))
+            for key, slot, shape in want:
+                if tuple(z[key].shape) != shape:
+                    raise ValueError("checkpoint {}: tensor {} has shape {}, the model expects {}".format(path, key, tuple(z[key].shape), shape))
+            m.global_step = int(z["global_step"])
+            for key, slot, _ in want:
+                m.set_tensor(key if slot == 0 else key[:key.rindex("/slot")], z[key], slot=slot)
 
     # ------------------------------------------------------------------ estimator API
     def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None):
@@ -118,7 +145,7 @@ class WideAndDeepClassifier(object):
         return self
 
     def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
-        m = self._ensure_model(checkpoint_path)
+        m = self._ensure_model(checkpoint_path, need_trained=True)
         m.eval_reset()
         n = 0
         for batch in input_fn():
@@ -134,7 +161,7 @@ class WideAndDeepClassifier(object):
         return out
 
     def predict(self, input_fn, predict_keys=None, hooks=None, checkpoint_path=None):
-        m = self._ensure_model(checkpoint_path)
+        m = self._ensure_model(checkpoint_path, need_trained=True)
         for batch in input_fn():
             logits, _ = m.forward(batch)
             p = 1.0 / (1.0 + np.exp(-logits.astype(np.float64)))

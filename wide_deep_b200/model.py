@@ -216,6 +216,10 @@ class WideDeepModel(object):
     def launch_count(self):
         return int(self._lib.wd_launch_count(self._h))
 
+    def gemm_fallback_count(self):
+        """Tensor-core-engine GEMMs that ran on the FFMA kernel instead (must stay 0)."""
+        return int(self._lib.wd_gemm_fallback_count(self._h))
+
     def set_profile(self, on=True):
         check(self._lib.wd_set_profile(self._h, 1 if on else 0))
 
