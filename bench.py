@@ -2,26 +2,34 @@
 """bench.py — CTR examples/sec of the Wide&Deep train step on N B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
-    python bench.py --impl reference ...                      (CPU restatement of the reference step)
+    python bench.py --impl reference ...                      (optimised CPU restatement of the reference step, host cores)
+    python bench.py --workload criteo|multihot|wide           (default criteo = BASELINE.json configs[1] / [2])
 
-Workload (config.workload): BASELINE.json configs[1] / [2] — synthetic Criteo shape, 13 dense + 26 categorical
-(Criteo-Kaggle cardinalities, 33.76 M embedding rows x 32), wide = 26 hash columns + 13 bucketized + 8 crosses
-@ 1 M buckets, MLP 1024-512-256 (relu, BN affine), Adagrad deep / FTRL wide, 8192 examples per GPU per step
-(weak scaling).  One "step" = ids + forward + sum-reduced sigmoid-CE + backward + both optimizers.
+Workloads (config.workload), one "step" = ids + forward + sum-reduced sigmoid-CE + backward + all optimizers:
+  criteo    configs[1] (N = 1) / configs[2] (N > 1): synthetic Criteo shape, 13 dense + 26 categorical (Criteo-Kaggle
+            cardinalities, 33.76 M embedding rows x 32), wide = 26 hash columns + 13 bucketized + 8 crosses @ 1 M buckets, MLP
+            1024-512-256 (relu, BN affine), Adagrad deep / FTRL wide, 8192 examples per GPU per step (weak scaling).
+  multihot  configs[3]: one hashed multihot slot (Poisson(30) ids per example), 64-wide embedding, ResDnn 4 x 512, 12.5 M table
+            rows PER GPU (100 M at N = 8, row-sharded), 8192 examples per GPU.
+  wide      configs[4]: wide-only, 9 hashed fields + 32 hashed crosses into 125 M buckets PER GPU (1 B at N = 8, row-sharded),
+            FTRL, 131072 examples per GPU (1 M at N = 8).
+N > 1: the batch is split by example; every table larger than 16384 rows is ROW-SHARDED over the ranks and exchanged through peer
+memory by the library's own kernels (wide_deep_b200/csrc/shard.cu), smaller tables are replicated and their gradients travel with
+the dense gradients in one two-shot all-reduce over peer memory.  WD_DP_MODE=lists selects round 1's replicated-table path
+(NCCL all-gather of (row, gradient) lists) instead.
 
 JSON keys beyond the base contract:
-  value     examples/s with the step's inputs already resident in HBM (a ring of distinct batches, so the
-            rows each step touches are not the ones left in L2 by the previous step)
+  value     examples/s with the step's inputs already resident in HBM (a ring of distinct batches, so the rows a step touches are
+            not the ones the previous step left in L2)
   e2e       the same metric fed from pinned host memory the way estimator.train feeds it: wd_batch_prefetch_slot refills two
             alternating slots on the upload stream (the copy of step i+1 overlaps step i, like dataset.prefetch in the reference),
-            wd_train_step_slot runs the step, and every step ends with a device -> host read of its loss — all timed
-  roofline  dominant kernel group (the nine MLP GEMM launches) as achieved fp32-equivalent TFLOP/s vs the measured dense-bf16
-            tensor peak, timed live with CUDA events on the model stream; `kernels` carries the same for the embedding gather (HBM)
-  gemm_engine   bf16x3 by default here (2^-16 products); `parity` re-checks it against the oracle in this run (bar 1e-4) and
-            `strict_engine` reports the same step on the fp32-faithful tc3x engine (the library default)
-  cpu_baseline  the oracle (CPU restatement of the reference; TensorFlow itself cannot run here) on the host cores
-Multi-GPU (config.exchange): one all-reduce for dense gradients + small-table gradient blocks, all-gather + on-device merge of the
-large tables' (row, gradient) lists; WD_DP_PROFILE=1 prints the phase timeline of a data-parallel step to stderr.
+            then the step, then a device -> host read of its loss — all inside the timed region
+  roofline  the dominant kernel group, timed live with CUDA events on the model stream (a few profiled steps, N = 1): criteo = the
+            nine MLP GEMM launches vs the measured bf16 tensor peak; multihot = embedding gather + pool vs measured HBM bandwidth;
+            wide = the wide-table kernels vs HBM bandwidth.  `kernels` carries the per-phase times and the gather's HBM figure.
+  dtype     arithmetic of the MLP GEMMs ("bf16x3" = fp32 operands split into bf16 hi + lo, three tensor-core products, fp32
+            accumulation); `parity` re-checks the engine against the oracle in this run, `strict_engine` = the same step on tf32x3
+  cpu_baseline  the optimised CPU restatement (oracle/fast.py) on the host cores, same workload, bounded sample
 """
 import argparse
 import json
@@ -36,8 +44,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PER_GPU_BATCH = 8192
 RING = 8
+DENSE_EXCHANGE_ROWS = int(os.environ.get("WD_DENSE_EXCHANGE_ROWS", "16384"))
 # arithmetic the MLP GEMMs run in (tables, optimizers, pooling and every reduction are fp32 in all engines)
 DTYPE_OF_ENGINE = {"bf16x3": "bf16x3 (fp32 operands split into bf16 hi+lo, 3 tensor-core products, fp32 accumulate; 2^-16)",
                    "tc3x": "tf32x3 (fp32 operands split into tf32 hi+lo, 3 tensor-core products, fp32 accumulate; 2^-21)",
@@ -150,29 +158,146 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvidia-smi -lms 100"}
 
 
-def workload(n_gpus, per_gpu_batch):
-    from wide_deep_b200 import synthetic
-    fc, cross, model, emb = synthetic.criteo_conf()
-    n_cat = sum(1 for c in fc.values() if c["type"] == "category")
-    n_dense = len(fc) - n_cat
-    P = (n_cat * emb + n_dense) * 1024 + 1024 * 512 + 512 * 256 + 256
-    return fc, cross, model, emb, n_cat, n_dense, P
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload(object):
+    """One BASELINE.json configuration: conf dicts, synthetic batches (product Batch + the oracle's raw dict), bookkeeping."""
+
+    def __init__(self, name, world, batch=None):
+        from wide_deep_b200 import synthetic
+        self.name, self.world = name, max(1, world)
+        self.syn = synthetic
+        if name == "criteo":
+            self.fc, self.cross, self.model, self.emb = synthetic.criteo_conf()
+            self.model_type, self.batch = "wide_deep", batch or 8192
+            n_cat = sum(1 for c in self.fc.values() if c["type"] == "category")
+            self.n_cat, self.n_dense = n_cat, len(self.fc) - n_cat
+            self.ids_per_row = len(self.fc) + len(self.cross)
+            self.keys_per_row = n_cat
+            self.P = (n_cat * self.emb + self.n_dense) * 1024 + 1024 * 512 + 512 * 256 + 256
+            self.desc = ("synthetic Criteo shape: 13 dense + 26 categorical (Criteo-Kaggle cardinalities, 33.76M rows), emb 32, "
+                         "wide 26 hash + 13 bucketized + 8 crosses@1M, MLP 1024-512-256 relu+BN, Adagrad/FTRL; train step")
+            self.l2 = "ring of %d distinct resident batches; touched rows per step ~60 MB, tables 8.6 GB >> 126 MB L2" % RING
+        elif name == "multihot":
+            self.rows = 12_500_000 * self.world
+            self.fc, self.cross, self.model, self.emb = synthetic.multihot_conf(rows=self.rows)
+            self.model_type, self.batch = "deep", batch or 8192
+            self.n_cat, self.n_dense, self.ids_per_row, self.keys_per_row = 1, 0, 128, 128
+            self.P = 64 * 512 + (512 + 64) * 512 + (1024 + 64) * 512 + (1536 + 64) * 512 + (2048 + 64)
+            self.desc = ("one hashed multihot slot, Poisson(30) ids per example clipped to [1,128], %d rows (12.5M per GPU) x 64, mean "
+                         "pooling, ResDnn 4x512 (resnet concatenations) relu+BN, Adagrad; train step" % self.rows)
+            self.l2 = "ring of %d distinct resident batches; ~246K random 256-byte rows per step of a 6.4 GB table >> 126 MB L2" % RING
+        elif name == "wide":
+            self.rows = 125_000_000 * self.world
+            self.fc, self.cross, self.model, self.emb = synthetic.wide_conf(total_cross_rows=self.rows)
+            self.model_type, self.batch = "wide", batch or 131072
+            self.n_cat, self.n_dense = len(self.fc), 0
+            self.ids_per_row = len(self.fc) + len(self.cross)
+            self.keys_per_row = len(self.fc)
+            self.P = 0
+            self.desc = ("wide-only: 9 hashed key fields + 32 hashed pairwise crosses into %d buckets (125M per GPU), FTRL(0.1, l1 0.5, "
+                         "l2 1); train step" % self.rows)
+            self.l2 = "ring of %d distinct resident batches; 4.2M random 16-byte records per step of a 2 GB table >> 126 MB L2" % RING
+        else:
+            raise SystemExit("unknown workload %r" % name)
+
+    def config(self, per_gpu_batch, exchange):
+        n = self.world
+        return {"workload": self.desc, "global_batch": per_gpu_batch * n, "per_gpu_batch": per_gpu_batch,
+                "parallelism": "dp%d" % n if n > 1 else "single",
+                "tables": ("tables > %d rows row-sharded over the ranks, smaller ones replicated" % DENSE_EXCHANGE_ROWS) if (n > 1 and exchange == "sharded")
+                else "replicated", "ids": "uniform", "exchange": exchange_text(exchange) if n > 1 else "none", "l2": self.l2}
+
+    def arrays(self, B, step):
+        """Host arrays of one batch: (keys uint64[nnz], offsets int32[B * F + 1] | None, dense float32[B, Nd] | None, label)."""
+        if self.name == "criteo":
+            keys, dense, label = self.syn.criteo_batch_arrays(self.fc, B, step=step)
+            return keys.reshape(-1), None, dense, label
+        if self.name == "multihot":
+            keys, offs, label = self.syn.multihot_batch_arrays(B, step=step)
+            return keys, offs, None, label
+        keys, label = self.syn.wide_batch_arrays(self.fc, B, step=step)
+        return keys.reshape(-1), None, None, label
+
+    def raw(self, B, arrays):
+        """The same batch in the oracle's format (feature -> CSR of fingerprints / float column)."""
+        keys, offs, dense, label = arrays
+        cats = [f for f, c in self.fc.items() if c["type"] == "category"]
+        dn = [f for f, c in self.fc.items() if c["type"] == "continuous"]
+        raw = {}
+        if offs is None:
+            k2 = keys.reshape(B, len(cats))
+            for j, f in enumerate(cats):
+                raw[f] = (np.arange(B + 1, dtype=np.int64), np.ascontiguousarray(k2[:, j]))
+        else:
+            raw[cats[0]] = (offs.astype(np.int64), keys)
+        for j, f in enumerate(dn):
+            raw[f] = np.ascontiguousarray(dense[:, j])
+        return raw, label
+
+    def plan(self, B, engine, rank=0, exchange="sharded"):
+        from wide_deep_b200.plan import Plan
+        n = self.world
+        kw = dict(max_batch=B, embedding_dim_override=self.emb, gemm_engine=engine, max_keys=B * self.keys_per_row)
+        if n > 1 and exchange == "sharded":
+            kw.update(max_nnz=B * self.ids_per_row, dense_exchange_max_rows=DENSE_EXCHANGE_ROWS, shard_world=n, shard_rank=rank,
+                      shard_slack=float(os.environ.get("WD_SHARD_SLACK", "1.5")))
+        elif n > 1:
+            kw.update(max_nnz=B * self.ids_per_row * n, dense_exchange_max_rows=DENSE_EXCHANGE_ROWS)
+        else:
+            kw.update(max_nnz=B * self.ids_per_row)
+        return Plan(self.fc, self.cross, self.model, self.model_type, **kw)
 
 
-def config_dict(n_gpus, per_gpu_batch):
-    return {"workload": "synthetic Criteo shape: 13 dense + 26 categorical (Criteo-Kaggle cardinalities, 33.76M rows), emb 32, "
-                        "wide 26 hash + 13 bucketized + 8 crosses@1M, MLP 1024-512-256 relu+BN, Adagrad/FTRL; train step",
-            "global_batch": per_gpu_batch * n_gpus, "per_gpu_batch": per_gpu_batch,
-            "parallelism": "dp%d" % n_gpus if n_gpus > 1 else "single",
-            "tables": "replicated", "ids": "uniform",
-            "exchange": ("dense all-reduce of MLP/wide-bias gradients + gradient blocks of tables <= %s rows; all-gather + on-device "
-                         "re-reduction of (row, gradient) lists for the larger tables" % os.environ.get("WD_DENSE_EXCHANGE_ROWS", "16384"))
-            if n_gpus > 1 else "none",
-            "l2": "ring of %d distinct resident batches; touched rows per step ~60 MB, tables 8.6 GB >> 126 MB L2" % RING}
+def exchange_text(exchange):
+    if exchange == "sharded":
+        return ("peer-memory exchange by the library's kernels: ids -> owners, owner-side pooled partial sums -> requesters, owners "
+                "pull gradients inside their segmented reduction + apply; dense gradients and the gradient blocks of tables <= %d rows: "
+                "two-shot all-reduce over peer memory; flag barriers; no NCCL on the data path" % DENSE_EXCHANGE_ROWS)
+    return ("dense all-reduce (NCCL) of MLP/wide-bias gradients + gradient blocks of tables <= %d rows; all-gather + on-device "
+            "re-reduction of (row, gradient) lists for the larger tables" % DENSE_EXCHANGE_ROWS)
 
 
 # ------------------------------------------------------------------------------------------- reference arm
-def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32, budget_s=None):
+def fast_fill(om, seed=1):
+    """Parameters for the CPU arm, filled by torch's multi-threaded generators (OracleModel.init's numpy truncated normal takes
+    minutes on the multi-GB tables; the timed step does not depend on the values)."""
+    import torch
+    from oracle import columns as C
+    g = torch.Generator().manual_seed(seed)
+    P = om.params = {}
+    if om.use_wide:
+        for c in om.wide_cols:
+            P[om.wname(c)] = np.zeros(c.num_buckets, dtype=np.float32)
+        P["linear/linear_model/bias_weights"] = np.zeros(1, dtype=np.float32)
+    if om.use_deep:
+        for c in om.deep_cols:
+            if isinstance(c, C.Embedding):
+                t = torch.empty((c.cat.num_buckets, c.dim), dtype=torch.float32)
+                t.normal_(0.0, float(1.0 / np.sqrt(c.dim)), generator=g).clamp_(-2.0 / np.sqrt(c.dim), 2.0 / np.sqrt(c.dim))
+                P[om.ename(c)] = t.numpy()
+        for t_i in range(len(om.towers)):
+            dims = om.layer_dims(t_i)
+            for l, (i, o) in enumerate(dims):
+                scope = "dnn/dnn_%d/" % (t_i + 1) + ("hiddenlayer_%d" % l if l < len(dims) - 1 else "logits")
+                lim = float(np.sqrt(6.0 / (i + o)))
+                P[scope + "/kernel"] = torch.empty((i, o)).uniform_(-lim, lim, generator=g).numpy()
+                P[scope + "/bias"] = np.zeros(o, dtype=np.float32)
+                if om.bn and l < len(dims) - 1:
+                    P[scope + "/batch_normalization/gamma"] = np.ones(o, dtype=np.float32)
+                    P[scope + "/batch_normalization/beta"] = np.zeros(o, dtype=np.float32)
+    om.slots = {}
+    for k, v in P.items():
+        o = om.opt_lin if k.startswith("linear/") else om.opt_dnn
+        if o["kind"] == "adagrad":
+            om.slots[k] = {"acc": torch.full(v.shape, o["init_acc"], dtype=torch.float32).numpy()}
+        elif o["kind"] == "ftrl":
+            om.slots[k] = {"n": torch.full(v.shape, o["init_acc"], dtype=torch.float32).numpy(), "z": torch.zeros(v.shape, dtype=torch.float32).numpy()}
+        else:
+            om.slots[k] = {}
+    return om
+
+
+def oracle_examples_per_sec(wl, batch_rows, steps, warmup, threads, budget_s=None):
     """Time the OPTIMISED CPU restatement (oracle/fast.py: torch-CPU matmuls + embedding_bag + sparse row updates, C hashing;
     checked against oracle/model.py by tests/test_oracle_fast.py) on the same workload with every host thread; returns
     (examples/s, seconds per step, steps timed).  torch.distributed.run exports OMP_NUM_THREADS=1: overridden explicitly."""
@@ -181,19 +306,13 @@ def oracle_examples_per_sec(batch_rows, steps, warmup, threads, acc=np.float32, 
     import torch
     torch.set_num_threads(threads)
     from oracle import fast as OF, model as OM
-    from wide_deep_b200 import synthetic
-    fc, cross, model, emb, n_cat, n_dense, _ = workload(1, batch_rows)
-    om = OF.FastCpuModel(OM.OracleModel(fc, cross, model, "wide_deep", embedding_dim_override=emb, acc=acc).init(1), threads=threads)
-    cats = [f for f, c in fc.items() if c["type"] == "category"]
-    dense_names = [f for f, c in fc.items() if c["type"] == "continuous"]
+    om = OM.OracleModel(wl.fc, wl.cross, wl.model, wl.model_type, embedding_dim_override=wl.emb, acc=np.float32)
+    fm = OF.FastCpuModel(fast_fill(om), threads=threads)
     times = []
     for s in range(warmup + steps):
-        keys, dense, label = synthetic.criteo_batch_arrays(fc, batch_rows, step=s)
-        raw = {f: (np.arange(batch_rows + 1, dtype=np.int64), np.ascontiguousarray(keys[:, j])) for j, f in enumerate(cats)}
-        for j, f in enumerate(dense_names):
-            raw[f] = np.ascontiguousarray(dense[:, j])
+        raw, label = wl.raw(batch_rows, wl.arrays(batch_rows, s))
         t0 = time.perf_counter()
-        om.train_step(raw, label)
+        fm.train_step(raw, label)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -208,16 +327,18 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # the same step as the GPU arm: same tables, same GLOBAL batch (N x 8192: the CPU arm is the whole box's host cores, whatever N
-    # is), a bounded number of steps
-    rows = args.batch * max(1, args.gpus)
+    wl = Workload(args.workload, args.gpus, args.batch)
+    # the same step as the GPU arm: same tables, same GLOBAL batch (N x per-GPU batch: the CPU arm is the whole box's host cores,
+    # whatever N is), a bounded number of steps
+    rows = wl.batch * max(1, args.gpus)
     warm = max(1, min(args.warmup, 2))
-    v, sec, steps = oracle_examples_per_sec(rows, max(1, args.steps), warm, threads, budget_s=90.0)   # K steps or 90 s of CPU work
+    v, sec, steps = oracle_examples_per_sec(wl, rows, max(1, args.steps), warm, threads, budget_s=90.0)   # K steps or 90 s of CPU work
     sample = "%d steps of %d examples (same tables/config as the GPU arm at N=%d), %d threads" % (steps, rows, args.gpus, threads)
+    exchange = "sharded" if os.environ.get("WD_DP_MODE", "sharded") != "lists" else "lists"
     out = {"impl": "reference", "metric": "CTR examples/sec (train step)", "value": v, "unit": "examples/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": config_dict(max(1, args.gpus), args.batch),
+           "config": wl.config(wl.batch, exchange),
            "cpu_baseline": {"value": v, "unit": "examples/s", "cores": threads, "kind": "port", "sample": sample,
                             "note": "optimised CPU restatement of the reference step (oracle/fast.py: torch-CPU sgemm + embedding_bag + "
                                     "sparse row updates, C hashing); TensorFlow 1.x is not installable here"},
@@ -228,7 +349,8 @@ def run_reference(args):
 def parity_check(engine, rows=2048):
     """Checker leg (oracle = test infrastructure): max relative logit error of `engine` against the CPU oracle on the benchmark
     model with every table scaled by 1e-3 (same columns, same 845-1024-512-256 towers, same kernels), parameters copied from the
-    oracle.  The bar is BASELINE.json's: |gpu - oracle| <= 1e-4 * max(|oracle|, 1)."""
+    oracle.  The bar is BASELINE.json's: |gpu - oracle| <= 1e-4 * max(|oracle|, 1).  (tests/test_gpu_bench_engine.py holds the
+    same engine to the same bar under pytest, plus a 50-step drift bound.)"""
     from oracle import model as OM
     from tests.helpers import copy_params_to_product
     from wide_deep_b200 import synthetic
@@ -267,7 +389,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="examples per GPU per step")
+    ap.add_argument("--workload", default=os.environ.get("WD_WORKLOAD", "criteo"), choices=["criteo", "multihot", "wide"])
+    ap.add_argument("--batch", type=int, default=None, help="examples per GPU per step (default: the workload's)")
     ap.add_argument("--engine", default=os.environ.get("WD_GEMM_ENGINE", "bf16x3"),
                     help="MLP GEMM engine: bf16x3 (tcgen05 kind::f16 on bf16 hi/lo copies, 2^-16 products; re-checked against the "
                          "oracle in this run) | tc3x (tcgen05 kind::tf32 3-pass, 2^-21, the library default) | ffma (fp32 CUDA cores)")
@@ -284,35 +407,33 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    exchange = "lists" if os.environ.get("WD_DP_MODE", "sharded") == "lists" else "sharded"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from wide_deep_b200 import synthetic
     from wide_deep_b200.model import Batch, WideDeepModel
-    from wide_deep_b200.plan import Plan
-    B = args.batch
-    fc, cross, model_conf, emb, n_cat, n_dense, P = workload(world, B)
-    n_cols = n_cat + n_dense + len(cross)
-    # data-parallel runs: tables / wide columns of <= 16384 rows (18 of the 26 embedding tables, 31 of the 47 wide columns) are
-    # exchanged as a dense gradient block inside the dense all-reduce; only the large tables' touched rows travel as lists
-    dense_rows = int(os.environ.get("WD_DENSE_EXCHANGE_ROWS", "16384")) if world > 1 else 0
-    plan = Plan(fc, cross, model_conf, "wide_deep", max_batch=B, embedding_dim_override=emb, gemm_engine=args.engine,
-                max_nnz=B * n_cols * (world if world > 1 else 1), max_keys=B * n_cat, dense_exchange_max_rows=dense_rows)
+    wl = Workload(args.workload, world, args.batch)
+    B = wl.batch
+    plan = wl.plan(B, args.engine, rank, exchange)
     model = WideDeepModel(plan, device=local)
-    model.init(seed=0x5EED0005)          # identical replicas on every rank
+    model.init(seed=0x5EED0005)          # identical replicas on every rank (shards of sharded tables draw their own stream)
     trainer = None
-    if world > 1:
+    if world > 1 and exchange == "sharded":
+        from wide_deep_b200.sharded import ShardedTrainer
+        trainer = ShardedTrainer(model)
+    elif world > 1:
         from wide_deep_b200.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(model, fixed_rows=plan.exchange_rows(B))
 
     # distinct batches per (rank, ring slot) in pinned host memory
     host = []
     for s in range(RING):
-        keys, dense, label = synthetic.criteo_batch_arrays(fc, B, step=rank * 1000 + s)
-        tk = torch.from_numpy(keys.view(np.int64).reshape(-1).copy()).pin_memory()
-        td = torch.from_numpy(dense.copy()).pin_memory()
-        tl = torch.from_numpy(label.copy()).pin_memory()
-        host.append((Batch(B, tk.numpy().view(np.uint64), None, td.numpy(), tl.numpy()), (tk, td, tl)))
+        keys, offs, dense, label = wl.arrays(B, rank * 1000 + s)
+        pins = [torch.from_numpy(keys.view(np.int64).copy()).pin_memory(), torch.from_numpy(label.copy()).pin_memory()]
+        po = torch.from_numpy(offs.copy()).pin_memory() if offs is not None else None
+        pd = torch.from_numpy(dense.copy()).pin_memory() if dense is not None else None
+        b = Batch(B, pins[0].numpy().view(np.uint64), None if po is None else po.numpy(), None if pd is None else pd.numpy(), pins[1].numpy())
+        host.append((b, (pins, po, pd)))
     for s in range(RING):
         model.upload_slot(s, host[s][0])
     model.sync()
@@ -341,7 +462,7 @@ def main():
 
     def step_resident(i):
         if trainer:
-            trainer.step_slot(i % RING)
+            trainer.step_slot(i % RING, want_loss=False)
         else:
             model.train_step_slot(i % RING, want_loss=False)
 
@@ -352,6 +473,8 @@ def main():
 
     def step_e2e(i):
         model.prefetch_slot(E2E0 + (i + 1) % 2, host[(i + 1) % RING][0])
+        if trainer and exchange == "sharded":
+            return trainer.step_slot(E2E0 + i % 2, want_loss=True)
         if trainer:
             trainer.step_slot(E2E0 + i % 2, want_loss=False)
             return model.last_loss()
@@ -372,13 +495,11 @@ def main():
     ms_e2e = timed(lambda i: step_e2e(i + 8), args.steps)
     clk = clocks.stop() if rank == 0 else None
 
-    if trainer and os.environ.get("WD_DP_PROFILE") and rank == 0:
+    if trainer and exchange == "lists" and os.environ.get("WD_DP_PROFILE"):
         for i in range(3):
             prof = trainer.profile_step(i % RING)
-        sys.stderr.write("dp phases (ms from step start): %s\n" % json.dumps({k: round(v, 3) for k, v in prof.items()}))
-    elif trainer and os.environ.get("WD_DP_PROFILE"):
-        for i in range(3):
-            trainer.profile_step(i % RING)
+        if rank == 0:
+            sys.stderr.write("dp phases (ms from step start): %s\n" % json.dumps({k: round(v, 3) for k, v in prof.items()}))
 
     # per-kernel timings (CUDA events between stages on the model stream), a few profiled steps
     phases = {}
@@ -396,18 +517,20 @@ def main():
         gb = B * world
         value = gb * args.steps / (ms / 1e3)
         e2e = gb * args.steps / (ms_e2e / 1e3)
+        has_mlp = wl.model_type != "wide"
         out = {"metric": "CTR examples/sec (train step)", "value": value, "unit": "examples/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF_ENGINE.get(args.engine, "f32"), "data": "synthetic",
-               "config": config_dict(world, B),
+               "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF_ENGINE.get(args.engine, "f32") if has_mlp else "f32 (no MLP: integer ids + fp32 FTRL)",
+               "data": "synthetic", "config": wl.config(B, exchange),
                "e2e": {"value": e2e, "unit": "examples/s", "ms_per_step": ms_e2e / args.steps,
                        "h2d_bytes_per_step": host[0][0].h2d_bytes(), "d2h_bytes_per_step": 8,
                        "input": "pinned host batches, wd_batch_prefetch_slot into two alternating slots (copy of step i+1 overlaps step i), loss read every step"},
                "gpu_launches": int(per_step_launches * args.steps), "launches_per_step": int(per_step_launches),
-               "clocks": clk, "gemm_engine": args.engine}
-        if phases:
+               "clocks": clk, "gemm_engine": args.engine if has_mlp else None}
+        nnz_avg = host[0][0].keys.shape[0] / float(B) if wl.name == "multihot" else float(wl.n_cat)
+        if phases and wl.name == "criteo":
             gemm_ms = sum(v for k, v in phases.items() if k.startswith("gemm_"))
-            flops = 6.0 * B * P                                   # 2BP forward + 4BP backward
+            flops = 6.0 * B * wl.P                                # 2BP forward + 4BP backward
             ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
             traffic, traffic_src = gemm_traffic_from_profile(args.engine, B)
             out["roofline"] = {"kernel": "mlp gemm (fwd+dgrad+wgrad)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
@@ -423,17 +546,36 @@ def main():
                                               "equivalent ceiling is 1/3 of the bf16 peak for bf16x3 and 1/6 for tc3x",
                                "tensor_pipe_frac": 3.0 * ach / peaks["bf16_sustained"] * (2.0 if args.engine == "tc3x" else 1.0),
                                "share_of_step": gemm_ms / phases.get("total", 1.0)}
-            gather_bytes = B * (n_cat * (4 * emb + 4) + 4 * n_cat + 4 * n_cat * emb)       # SURVEY 8(d) K3 formula
+        if phases and has_mlp:
+            # ids + offsets + rows + pooled output
+            gather_bytes = B * (nnz_avg * (4 * wl.emb + 4) + 4 * wl.n_cat + 4 * wl.n_cat * wl.emb)
             g_ms = phases.get("emb_fwd", 0.0)
             g_ach = gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
-            out["kernels"] = {"emb_gather_pool_fwd": {"bound": "hbm", "achieved": g_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                      "frac": g_ach / peaks["hbm_gbs"], "algorithmic_bytes": gather_bytes, "ms": g_ms},
-                              "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
-        if not args.no_cpu_baseline and world == 1 and args.engine != "tc3x":
+            gk = {"bound": "hbm", "achieved": g_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g_ach / peaks["hbm_gbs"],
+                  "algorithmic_bytes": gather_bytes, "ms": g_ms}
+            out["kernels"] = {"emb_gather_pool_fwd": gk, "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
+            if wl.name == "multihot":
+                # the table-bound kernels of this workload: gather + pool (K3) and the backward gradient sums + Adagrad (K8)
+                u = min(nnz_avg * B, wl.rows)
+                bwd_bytes = 4 * B * wl.emb + 4 * nnz_avg * B + 16 * u * wl.emb
+                b_ms = phases.get("emb_grad_sum", 0.0) + phases.get("sparse_apply", 0.0)
+                out["roofline"] = dict(gk, kernel="emb gather + mean pool (forward)", traffic=None, peak_source=peaks["source"] + " HBM copy bandwidth",
+                                       share_of_step=g_ms / phases.get("total", 1.0))
+                out["kernels"]["emb_grad_sum_apply_bwd"] = {"bound": "hbm", "achieved": bwd_bytes / (b_ms * 1e-3) / 1e9 if b_ms > 0 else 0.0,
+                                                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "algorithmic_bytes": bwd_bytes, "ms": b_ms}
+        if phases and wl.name == "wide":
+            nnz = float(wl.ids_per_row) * B
+            w_bytes = nnz * 8 + 4 * B + 4 * nnz + 4 * B + 24 * nnz          # SURVEY 8(d) K4 + K9 (U_w ~ nnz: uniform ids)
+            w_ms = phases.get("wide_fwd", 0.0) + phases.get("wide_grad_sum", 0.0) + phases.get("sparse_apply", 0.0)
+            ach = w_bytes / (w_ms * 1e-3) / 1e9 if w_ms > 0 else 0.0
+            out["roofline"] = {"kernel": "wide logit gather + gradient sums + FTRL (excludes the id hashing and the sort)", "bound": "hbm",
+                               "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                               "algorithmic_bytes": w_bytes, "ms": w_ms, "peak_source": peaks["source"] + " HBM copy bandwidth",
+                               "share_of_step": w_ms / phases.get("total", 1.0)}
+            out["kernels"] = {"phases_ms": {k: round(v, 4) for k, v in phases.items()}}
+        if not args.no_cpu_baseline and world == 1 and args.engine != "tc3x" and wl.name == "criteo":
             # the same step on the fp32-faithful engine (3xTF32, the library default), for reference next to the headline
-            plan2 = Plan(fc, cross, model_conf, "wide_deep", max_batch=B, embedding_dim_override=emb, gemm_engine="tc3x",
-                         max_nnz=B * n_cols, max_keys=B * n_cat)
-            m2 = WideDeepModel(plan2, device=local)
+            m2 = WideDeepModel(wl.plan(B, "tc3x"), device=local)
             m2.init(seed=0x5EED0005)
             for s_ in range(RING):
                 m2.upload_slot(s_, host[s_][0])
@@ -451,9 +593,11 @@ def main():
                                     "ms_per_step": e0.elapsed_time(e1) / 40, "steps": 40}
             del m2
         if not args.no_cpu_baseline and world == 1:
-            out["parity"] = parity_check(args.engine)
+            if wl.name == "criteo":
+                out["parity"] = parity_check(args.engine)
+            del model
             threads = os.cpu_count() or 1
-            v, sec, nst = oracle_examples_per_sec(B, 10, 2, threads, budget_s=20.0)
+            v, sec, nst = oracle_examples_per_sec(wl, B, 10, 2, threads, budget_s=20.0)
             out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
                                    "sample": "%d steps of %d examples, same tables/config (oracle/fast.py: torch-CPU + C hashing, fp32)" % (nst, B)}
         print(json.dumps(out))

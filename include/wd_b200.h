@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WD_API_VERSION 1
+#define WD_API_VERSION 2
 
 enum { WD_OK = 0, WD_EINVAL = -1, WD_ENODEVICE = -2, WD_ECUDA = -3, WD_ENOMEM = -4, WD_EUNSUPPORTED = -5, WD_ESTATE = -6 };
 
@@ -104,6 +104,18 @@ typedef struct WdPlanDesc {
      * columns large-first. */
     int64_t dense_exchange_max_rows;
     int64_t wide_small_base;
+    /* Row-sharded tables (the reference partitions large variables over its parameter servers with
+     * tf.min_max_variable_partitioner, reference python/lib/joint.py:141-143).  shard_world = G > 1: this handle is rank
+     * shard_rank of G; every embedding table with table_sharded[t] = 1 and every wide column with col_wide_sharded[c] = 1 keeps
+     * only the rows r with r mod G == shard_rank (local row r / G).  The plan marks exactly the tables larger than
+     * dense_exchange_max_rows, so a sharded run has no (row, gradient) lists: small tables exchange the dense block, large ones
+     * are reached through the peer-memory exchange of wd_shard_* below.  shard_capacity: upper bound on the ids one rank routes
+     * per step and table space (0: max_nnz); shard_slack x that bound is what one rank can receive as an owner. */
+    int32_t shard_world, shard_rank;
+    const uint8_t *table_sharded;       /* [n_tables] */
+    const uint8_t *col_wide_sharded;    /* [n_columns] */
+    int64_t shard_capacity;
+    float shard_slack;
 } WdPlanDesc;
 
 /* One batch in HOST memory (pinned for async copies).  Replaces the feature dict produced by input_fn
@@ -186,6 +198,28 @@ int wd_sparse_set(WdModel *m, int which, const void *rows_dev, const void *grads
  * every step the merge is replayed from a CUDA graph.  (Replaces the push of sparse updates to the parameter servers,
  * reference python/train.py:197-217.) */
 int wd_sparse_set_sorted(WdModel *m, int which, const void *rows_dev, const void *grads_dev, int32_t n_lists, int64_t list_len);
+
+/* ---- Row-sharded tables (WdPlanDesc::shard_world > 1).  Replaces the partitioned variables + parameter-server pulls / pushes of
+ * the reference's distributed mode (reference python/lib/joint.py:141-143 min_max_variable_partitioner; python/train.py:197-217)
+ * with a synchronous, exact exchange through PEER MEMORY over NVLink: ids go to their owners, owners return pooled partial sums,
+ * gradients are pulled by the owners inside their segmented reduction, dense gradients are all-reduced by a two-shot kernel.  No
+ * collective library is involved; the ranks only need each other's exchange segment mapped.
+ *   one process per GPU : every rank calls wd_shard_ipc_handle, the 64-byte handles are all-gathered by the host (any transport),
+ *                         wd_shard_connect_ipc maps the peers; then wd_shard_train_step_slot / wd_shard_forward_slot are
+ *                         COLLECTIVE calls (every rank, once per step); ranks meet at flag barriers in peer memory.
+ *   one process, G handles (tests, also on a single GPU): wd_shard_connect_local; then for phase k = 0..4: wd_shard_phase on
+ *                         every rank followed by wd_shard_local_sync (event barrier), wd_shard_finish for the loss.
+ * Parameters of sharded tables are addressed per rank: wd_tensor_io / wd_tensor_size see this rank's rows (global rows rank,
+ * rank + G, rank + 2G, ...). */
+int wd_shard_info(WdModel *m, int32_t *world, int32_t *rank, int64_t *segment_bytes);
+int wd_shard_ipc_handle(WdModel *m, void *handle_out64);                                   /* 64 bytes (cudaIpcMemHandle_t) */
+int wd_shard_connect_ipc(WdModel *m, const void *handles /* n_ranks x 64 bytes, rank order */, int32_t n_ranks);
+int wd_shard_connect_local(WdModel **models /* rank order */, int32_t n_ranks);
+int wd_shard_local_sync(WdModel **models, int32_t n_ranks);
+int wd_shard_phase(WdModel *m, int slot, int phase, int train);
+int wd_shard_finish(WdModel *m, float *loss_out /* nullable */, float *logits_out /* nullable, [batch] */);
+int wd_shard_train_step_slot(WdModel *m, int slot, float *loss_out /* NULL: enqueue only */);
+int wd_shard_forward_slot(WdModel *m, int slot, float *logits_out, float *loss_out);
 
 /* Streaming eval metrics (binary head, reference joint.py:402-406): accumulate per batch, then finish.
  * out[0..9] = accuracy, accuracy_baseline, auc, auc_precision_recall, average_loss, label/mean, loss,

@@ -57,6 +57,15 @@ SYMBOLS = {
                                        ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
     "wd_sparse_set": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _i64]),
     "wd_sparse_set_sorted": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int32, _i64]),
+    "wd_shard_info": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
+    "wd_shard_ipc_handle": (ctypes.c_int, [_vp, _vp]),
+    "wd_shard_connect_ipc": (ctypes.c_int, [_vp, _vp, _i32]),
+    "wd_shard_connect_local": (ctypes.c_int, [_vp, _i32]),
+    "wd_shard_local_sync": (ctypes.c_int, [_vp, _i32]),
+    "wd_shard_phase": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "wd_shard_finish": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), _vp]),
+    "wd_shard_train_step_slot": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    "wd_shard_forward_slot": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_float)]),
     "wd_eval_reset": (ctypes.c_int, [_vp]),
     "wd_eval_accumulate": (ctypes.c_int, [_vp, _vp]),
     "wd_eval_finish": (ctypes.c_int, [_vp, _vp]),

@@ -29,6 +29,13 @@ int dense_refresh_transposes(WdModel* m);
 int wide_bias_grad(WdModel* m);
 int metrics_setup();
 int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int64_t n);
+int shard_build(WdModel* m, const WdPlanDesc* d);
+int shard_phase0(WdModel* m, bool train);
+int shard_phase1(WdModel* m, bool train);
+int shard_phase2(WdModel* m, bool train);
+int shard_phase3(WdModel* m);
+int shard_phase4(WdModel* m);
+int shard_step_ipc(WdModel* m, bool train);
 
 static int pad_to(int n, int k) { return (n + k - 1) / k * k; }
 static int bits_for(int64_t n) {
@@ -166,6 +173,15 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     m->dense_exchange_max_rows = d->dense_exchange_max_rows > 0 ? d->dense_exchange_max_rows : 0;
     m->small_base[1] = (m->dense_exchange_max_rows > 0 && d->wide_small_base >= 0 && d->wide_small_base <= d->wide_rows) ? d->wide_small_base : d->wide_rows;
     m->max_nnz = d->max_nnz > 0 ? d->max_nnz : (int64_t)d->max_batch * std::max(C, 1) * 2;
+    const int G = d->shard_world > 1 ? d->shard_world : 1;
+    m->shard.world = G; m->shard.rank = G > 1 ? d->shard_rank : 0;
+    if (G > 1) {
+        if (d->shard_rank < 0 || d->shard_rank >= G) { set_error("shard_rank %d outside [0, %d)", d->shard_rank, G); return WD_EINVAL; }
+        // as an owner a rank can receive more ids than it routes itself (skewed ids): all per-entry scratch is sized for that
+        const int64_t route = d->shard_capacity > 0 ? d->shard_capacity : m->max_nnz;
+        const double slack = d->shard_slack >= 1.f ? d->shard_slack : 2.0;
+        m->max_nnz = std::max<int64_t>(m->max_nnz, (int64_t)(route * slack));
+    }
     m->keys_cap = d->max_keys > 0 ? d->max_keys : (int64_t)d->max_batch * std::max(d->n_cat_fields, 1) * 4;
     if (m->lin_opt.kind == WD_OPT_FTRL && m->lin_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
     if (m->dnn_opt.kind == WD_OPT_FTRL && m->dnn_opt.lr_power != -0.5f) { set_error("FTRL: only learning_rate_power=-0.5 is supported"); return WD_EUNSUPPORTED; }
@@ -225,7 +241,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         }
     }
     if ((rc = dev_alloc(m, &m->d_logits, Bm))) return rc;
-    if ((rc = dev_alloc(m, &m->d_dlogit, Bm))) return rc;
+    if (G == 1 && (rc = dev_alloc(m, &m->d_dlogit, Bm))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss_part, 512))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_metrics, 512))) return rc;
@@ -261,10 +277,12 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             tb.dim_logical = d->table_dim_logical[t];
             if (tb.dim_logical < 1 || tb.dim_logical > tb.dim) { set_error("table %d: bad logical width", t); return WD_EINVAL; }
             tb.row_base = 0; tb.stride = tb.dim * (1 + nslots); tb.col = -1;
+            tb.sharded = G > 1 && d->table_sharded && d->table_sharded[t];
+            tb.arows = tb.sharded ? (tb.rows - m->shard.rank + G - 1) / G : tb.rows;
             if (tb.dim % 4 || tb.x0_off % 4) { set_error("table %d: dim and deep-input offset must be multiples of 4", t); return WD_EINVAL; }
             for (int c = 0; c < C; ++c) if (d->col_emb_table[c] == t) tb.col = c;
             if (tb.col < 0) { set_error("table %d has no producing column", t); return WD_EINVAL; }
-            if ((rc = dev_alloc(m, &tb.data, tb.rows * tb.stride, true))) return rc;
+            if ((rc = dev_alloc(m, &tb.data, tb.arows * tb.stride, true))) return rc;
             for (int i = 0; i < tb.dim_logical; ++i) x->x0_real[tb.x0_off + i] = 1;
             m->emb_max_dim = std::max(m->emb_max_dim, tb.dim);
             m->tables.push_back(tb);
@@ -274,6 +292,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 1) m->small_base[0] = row_base;
             for (int t = 0; t < d->n_tables; ++t) {
+                if (m->tables[t].sharded) continue;                  // rows live in the sharded space (shard.cu), not here
                 const bool small = m->dense_exchange_max_rows > 0 && m->tables[t].rows <= m->dense_exchange_max_rows;
                 if (small != (pass == 1)) continue;
                 if (small) m->n_small_tab++;
@@ -321,6 +340,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         { const int64_t* t; if ((rc = upload_vec(m, h_row_base.data(), nt, &t))) return rc; m->d_tab_row_base = (int64_t*)t; p.table_row_base = t; }
         // group tables by width
         for (int t = 0; t < nt; ++t) {
+            if (m->tables[t].sharded) continue;                      // gathered by their owners, not by the local gather kernels
             int di = -1;
             for (int i = 0; i < m->n_dims; ++i) if (m->dims[i] == m->tables[t].dim) di = i;
             if (di < 0) {
@@ -331,7 +351,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         }
         for (int i = 0; i < m->n_dims; ++i) {
             std::vector<int32_t> ids;
-            for (int t = 0; t < nt; ++t) if (m->tables[t].dim == m->dims[i]) ids.push_back(t);
+            for (int t = 0; t < nt; ++t) if (m->tables[t].dim == m->dims[i] && !m->tables[t].sharded) ids.push_back(t);
             const int32_t* dp;
             if ((rc = upload_vec(m, ids.data(), (int64_t)ids.size(), &dp))) return rc;
             m->d_dim_tables[i] = (int32_t*)dp;
@@ -344,7 +364,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         const int64_t actn = (int64_t)m->max_batch_pad * d->d0_phys;
         if ((rc = dev_alloc(m, &m->d_X0, actn))) return rc;
         if ((rc = dev_alloc(m, &m->d_X0T, actn))) return rc;
-        if ((rc = dev_alloc(m, &m->d_dX0, actn))) return rc;
+        if (G == 1 && (rc = dev_alloc(m, &m->d_dX0, actn))) return rc;      // (sharded runs: inside the exchange segment, peers read it)
         if (m->gemm_engine == WD_GEMM_BF16X3)
             for (int part = 0; part < 2; ++part) {
                 if ((rc = dev_alloc(m, &m->d_X0s[part], actn))) return rc;
@@ -429,7 +449,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         if ((rc = dev_alloc(m, &m->d_P, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_S1, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_S2, m->dense_count))) return rc;
-        if ((rc = dev_alloc(m, &m->d_G, m->dense_count + m->gs_count))) return rc;
+        if (G == 1 && (rc = dev_alloc(m, &m->d_G, m->dense_count + m->gs_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_gpart, m->gpart_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_Wt, std::max<int64_t>(m->wt_count, 1)))) return rc;
         if ((rc = dev_alloc(m, &m->d_Wsplit, std::max<int64_t>(4 * m->wt_count, 1)))) return rc;
@@ -462,6 +482,17 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     }
     m->sort_hist_cap = 1024 * ((m->max_nnz + kSortTile - 1) / kSortTile + 1) + 4 * 1024 + 64;
     for (int k = 0; k < 3; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
+    if (G > 1) {
+        if ((rc = shard_build(m, d))) return rc;
+        DevPlan& dp = m->dplan;
+        dp.sh_world = G;
+        for (int sx = 0; sx < 2; ++sx) {
+            ShardSpace& sp = m->shard.sp[sx];
+            if (!sp.on) continue;
+            if (sx == 0) { dp.sh_col_emb = sp.d_col_slot; dp.sh_base_emb = sp.d_slot_base; dp.sh_own_emb = sp.d_own; dp.sh_lrow_emb = sp.d_lrow; }
+            else { dp.sh_col_wide = sp.d_col_slot; dp.sh_base_wide = sp.d_slot_base; dp.sh_own_wide = sp.d_own; dp.sh_lrow_wide = sp.d_lrow; }
+        }
+    }
     if ((rc = metrics_setup())) return rc;
     if ((rc = init_sparse_tables(m, 0, 0))) return rc;           // slots = initial accumulator, weights 0
     if ((rc = init_dense_slots(m))) return rc;
@@ -564,9 +595,14 @@ static int resolve_dense(WdModel* m, WdModelExtra* x, int did, int sub, int* out
 extern "C" int64_t wd_tensor_size(WdModel* m, int kind, int index, int sub) {
     if (!m) return WD_EINVAL;
     WdModelExtra* x = extra_of(m);
-    if (kind == WD_T_WIDE_COL) return (index >= 0 && index < m->n_columns && m->col_wide_base[index] >= 0) ? m->col_buckets[index] : WD_EINVAL;
+    if (kind == WD_T_WIDE_COL) {
+        if (index < 0 || index >= m->n_columns) return WD_EINVAL;
+        const ShardSpace& sw = m->shard.sp[1];
+        if (sw.on && sw.h_col_slot[index] >= 0) return (m->col_buckets[index] - m->shard.rank + m->shard.world - 1) / m->shard.world;   // this rank's rows
+        return m->col_wide_base[index] >= 0 ? m->col_buckets[index] : WD_EINVAL;
+    }
     if (kind == WD_T_WIDE_BIAS) return m->use_wide ? 1 : WD_EINVAL;
-    if (kind == WD_T_EMB_TABLE) return (index >= 0 && index < (int)m->tables.size()) ? m->tables[index].rows * m->tables[index].dim_logical : WD_EINVAL;
+    if (kind == WD_T_EMB_TABLE) return (index >= 0 && index < (int)m->tables.size()) ? m->tables[index].arows * m->tables[index].dim_logical : WD_EINVAL;
     if (kind == WD_T_DENSE) {
         int di;
         if (resolve_dense(m, x, index, sub, &di)) return WD_EINVAL;
@@ -586,7 +622,10 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
     if (slot < 0 || slot > 2) { set_error("slot out of range"); return WD_EINVAL; }
     const cudaMemcpyKind dir = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
     if (kind == WD_T_WIDE_COL) {
-        float* dev = reinterpret_cast<float*>(m->d_wide + m->col_wide_base[index]) + slot;
+        const ShardSpace& sw = m->shard.sp[1];
+        float* dev = (sw.on && sw.h_col_slot[index] >= 0)
+                         ? reinterpret_cast<float*>(sw.d_wide + sw.h_slot_base[sw.h_col_slot[index]]) + slot     // rows r = rank, rank + G, ...
+                         : reinterpret_cast<float*>(m->d_wide + m->col_wide_base[index]) + slot;
         if (to_device) WD_CUDA(cudaMemcpy2DAsync(dev, 16, host, 4, 4, count, dir, m->stream));
         else WD_CUDA(cudaMemcpy2DAsync(host, 4, dev, 16, 4, count, dir, m->stream));
         WD_CUDA(cudaStreamSynchronize(m->stream));
@@ -597,8 +636,8 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
         if (slot * tb.dim >= tb.stride) { set_error("table has no optimizer slot %d", slot); return WD_EINVAL; }
         float* dev = tb.data + slot * tb.dim;
         const size_t lw = (size_t)tb.dim_logical * 4;
-        if (to_device) WD_CUDA(cudaMemcpy2DAsync(dev, (size_t)tb.stride * 4, host, lw, lw, tb.rows, dir, m->stream));
-        else WD_CUDA(cudaMemcpy2DAsync(host, lw, dev, (size_t)tb.stride * 4, lw, tb.rows, dir, m->stream));
+        if (to_device) WD_CUDA(cudaMemcpy2DAsync(dev, (size_t)tb.stride * 4, host, lw, lw, tb.arows, dir, m->stream));
+        else WD_CUDA(cudaMemcpy2DAsync(host, lw, dev, (size_t)tb.stride * 4, lw, tb.arows, dir, m->stream));
         WD_CUDA(cudaStreamSynchronize(m->stream));
         return WD_OK;
     }
@@ -776,6 +815,16 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
         cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
         set_error("categorical-column id capacity exceeded (max_nnz=%lld): recreate the model with a larger max_nnz", (long long)m->max_nnz);
         return WD_EINVAL;
+    }
+    if (flags_host[0] & 2) {
+        cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
+        set_error("row-sharded exchange capacity exceeded (a rank received more than %lld ids): raise shard_slack / shard_capacity", (long long)m->max_nnz);
+        return WD_EINVAL;
+    }
+    if (flags_host[0] & 4) {
+        cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
+        set_error("row-sharded exchange: a peer rank did not reach a barrier within 20 s (ranks out of step, or a rank failed)");
+        return WD_ESTATE;
     }
     if (loss_out) *loss_out = m->batch_has_label ? m->h_loss_pinned[0] : 0.f;
     if (m->timer.enabled) {
@@ -1172,6 +1221,105 @@ extern "C" int wd_sparse_set(WdModel* m, int which, const void* rows_dev, const 
 extern "C" int wd_sparse_set_sorted(WdModel* m, int which, const void* rows_dev, const void* grads_dev, int32_t n_lists, int64_t list_len) {
     if (n_lists < 1 || list_len < 1) { set_error("wd_sparse_set_sorted: bad list shape"); return WD_EINVAL; }
     return sparse_set_impl(m, which, rows_dev, grads_dev, (int64_t)n_lists * list_len, n_lists);
+}
+
+// ------------------------------------------------------------------------------------- row-sharded tables
+namespace wd {
+int shard_group_async(WdModel* m) { return ::group_async(m); }
+int shard_backward_local(WdModel* m, bool) { return ::backward_core(m); }
+int shard_apply_local(WdModel* m) { return ::apply_core(m); }
+}
+
+static int shard_ready(WdModel* m, int slot) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (m->shard.world <= 1) { set_error("model has no row-sharded tables (shard_world <= 1)"); return WD_ESTATE; }
+    if (!m->shard.connected) { set_error("row-sharded model is not connected to its peers (wd_shard_connect_ipc / wd_shard_connect_local)"); return WD_ESTATE; }
+    if ((rc = select_slot(m, slot))) return rc;
+    if (!m->slots[slot].filled) { set_error("batch slot %d was never uploaded", slot); return WD_ESTATE; }
+    return WD_OK;
+}
+
+// One phase of a sharded step (ranks driven by ONE process: the caller runs phase k on every rank, then wd_shard_local_sync).
+extern "C" int wd_shard_phase(WdModel* m, int slot, int phase, int train) {
+    int rc = shard_ready(m, slot);
+    if (rc) return rc;
+    if (m->shard.ipc) { set_error("wd_shard_phase is for ranks of one process; multi-process ranks call wd_shard_train_step_slot"); return WD_ESTATE; }
+    if (train && !m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    switch (phase) {
+        case 0: return shard_phase0(m, train != 0);
+        case 1: return shard_phase1(m, train != 0);
+        case 2: rc = shard_phase2(m, train != 0); if (!train && rc == WD_OK) m->shard.step++; return rc;
+        case 3: return train ? shard_phase3(m) : WD_OK;
+        case 4: if (!train) return WD_OK; rc = shard_phase4(m); return rc ? rc : mark_slot_used(m);
+    }
+    set_error("wd_shard_phase: phase %d outside [0, 4]", phase);
+    return WD_EINVAL;
+}
+
+// Loss (and optionally logits) of the step / forward just issued; synchronises the model stream.
+extern "C" int wd_shard_finish(WdModel* m, float* loss_out, float* logits_out) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    return finish_step(m, loss_out, logits_out);
+}
+
+// The whole step of one rank of a multi-process job: ids, routing, serve, combine, towers, owners' updates, dense all-reduce and
+// optimizers, with flag barriers in peer memory between the phases.  Every rank must call it once per step (it is a collective).
+// After two eager steps per batch slot the step is captured into one CUDA graph (barrier kernels included) and replayed.
+extern "C" int wd_shard_train_step_slot(WdModel* m, int slot, float* loss_out) {
+    int rc = shard_ready(m, slot);
+    if (rc) return rc;
+    if (!m->shard.ipc) { set_error("wd_shard_train_step_slot needs wd_shard_connect_ipc (ranks of one process use wd_shard_phase)"); return WD_ESTATE; }
+    if (!m->batch_has_label) { set_error("training needs labels"); return WD_EINVAL; }
+    if (slot >= 64) { set_error("slot out of range"); return WD_EINVAL; }
+    ShardState& S = m->shard;
+    const bool can_graph = m->graphs_enabled && !m->timer.enabled;
+    if (can_graph && S.graph[slot] && same_view(S.graph_view[slot], m->dbatch)) {
+        WD_CUDA(cudaGraphLaunch(S.graph[slot], m->stream));
+        m->launches += S.graph_launches[slot];
+        S.step++;
+    } else if (can_graph && S.eager_steps[slot] >= 2) {
+        if (S.graph[slot]) { cudaGraphExecDestroy(S.graph[slot]); S.graph[slot] = nullptr; }
+        const int64_t l0 = m->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = shard_step_ipc(m, true);
+            cudaError_t e2 = cudaStreamEndCapture(m->stream, &g);
+            if (rc == WD_OK && e2 == cudaSuccess && g) e = cudaGraphInstantiate(&S.graph[slot], g, 0);
+            else e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
+            if (g) cudaGraphDestroy(g);
+        }
+        m->side_pending[0] = m->side_pending[1] = m->side_active[0] = m->side_active[1] = false; m->grads_pending = false;
+        if (e != cudaSuccess || !S.graph[slot]) {              // not capturable here: stay eager for good
+            cudaGetLastError();
+            m->graphs_enabled = false;
+            S.graph[slot] = nullptr;
+            if ((rc = shard_step_ipc(m, true))) return rc;
+        } else {
+            S.graph_view[slot] = m->dbatch;
+            S.graph_launches[slot] = m->launches - l0;
+            m->launches = l0;
+            WD_CUDA(cudaGraphLaunch(S.graph[slot], m->stream));
+            m->launches += S.graph_launches[slot];
+        }
+    } else {
+        if ((rc = shard_step_ipc(m, true))) return rc;
+        S.eager_steps[slot]++;
+    }
+    if ((rc = mark_slot_used(m))) return rc;
+    if (loss_out) return finish_step(m, loss_out, nullptr);
+    return WD_OK;
+}
+
+// Forward only on a sharded model (collective, multi-process ranks): logits of this rank's batch shard.
+extern "C" int wd_shard_forward_slot(WdModel* m, int slot, float* logits_out, float* loss_out) {
+    int rc = shard_ready(m, slot);
+    if (rc) return rc;
+    if (!m->shard.ipc) { set_error("wd_shard_forward_slot needs wd_shard_connect_ipc"); return WD_ESTATE; }
+    if ((rc = shard_step_ipc(m, false))) return rc;
+    return finish_step(m, loss_out, logits_out);
 }
 
 // ------------------------------------------------------------------------------------------------- eval

@@ -27,6 +27,11 @@ void set_error(const char* fmt, ...);
 constexpr uint32_t kInvalidRow = 0xFFFFFFFFu;
 constexpr int kMaxSegs = 8;      // sources concatenated into one MLP layer input
 constexpr int kMaxDims = 8;      // distinct embedding widths per model
+// sort / unique-row scratch sets ("lists"): 0 embedding rows and 1 wide rows of the replicated tables; row-sharded tables add
+// 2 / 3 = rows this rank OWNS that were touched by any rank this step (embedding / wide) and 4 / 5 = this rank's own ids
+// grouped by owner rank (routing; only the key / value ping-pong buffers exist)
+constexpr int kLists = 6;
+constexpr int kMaxRanks = 16;    // ranks of one box a row-sharded table can be split over
 
 // ---- device image of the categorical-column plan (all pointers are device pointers)
 struct DevPlan {
@@ -49,6 +54,12 @@ struct DevPlan {
     const int32_t* cross_key_idx;
     const int64_t* table_row_base;   // global embedding row id of row 0 of each table
     int d0_phys;
+    // row-sharded tables (shard_world > 1): per column the slot in the sharded embedding / wide space (-1: replicated), the first
+    // local row of each slot's shard, and per entry the owner rank / local row arrays the id stage fills (null: nothing sharded)
+    int sh_world;
+    const int32_t *sh_col_emb, *sh_col_wide;
+    const int64_t *sh_base_emb, *sh_base_wide;
+    uint32_t *sh_own_emb, *sh_lrow_emb, *sh_own_wide, *sh_lrow_wide;
 };
 
 // ---- device view of one batch
@@ -68,8 +79,10 @@ struct EmbTable {
     int x0_off;
     int col;                 // producing column
     int64_t row_base;        // global row id base
-    float* data;             // rows * stride floats; record = [w[dim] | slot1[dim] | slot2[dim]]
+    float* data;             // arows * stride floats; record = [w[dim] | slot1[dim] | slot2[dim]]
     int stride;              // dim * (1 + nslots)
+    bool sharded;            // row-sharded over the ranks: this rank holds rows r with r mod G == rank at local index r / G
+    int64_t arows;           // rows allocated on this rank (= rows unless sharded); row_base then counts in the shard's row space
 };
 
 struct TabDesc {            // per-table descriptor grouped by width (one 32-byte load in the gather kernels)
@@ -156,6 +169,67 @@ struct BatchSlot {           // one device-resident batch (ring used by benchmar
     bool bwd_side_active[2] = {false, false};
 };
 
+
+// ---- row-sharded tables (shard.cu) ------------------------------------------------------------------------------------
+// Pointers into ONE rank's exchange segment (a single cudaMalloc block that peers map through CUDA IPC, or address directly when
+// all ranks live in one process).  Every rank lays its segment out identically, so a peer pointer = peer base + own offset.
+struct ShardPeer {
+    uint2* inbox[2];          // [G][pair_cap] entries {local row, bag} written by requester ranks (double buffered by step parity)
+    int32_t* inbox_cnt[2];    // [G] entries each requester sent this step
+    float* recv;              // [G][nbags][width] pooled partial sums written by owner ranks
+    const float* bagscale;    // [nbags] 1 / (ids in the bag)   (embedding space: combiner = mean)
+    const float* gradbase;    // dX0 (embedding space) / dlogit (wide space) of that rank: owners pull gradients from here
+};
+struct ShardSpace {           // one sharded table space on this rank: 0 = embedding tables, 1 = wide columns
+    bool on = false;
+    int width = 0;            // floats per pooled vector: max width of the sharded embedding tables / 1
+    int n_slots = 0;          // sharded tables (embedding) / sharded wide columns
+    int bags_per_row = 0;     // embedding: n_slots (bag = example * n_slots + slot); wide: 1 (bag = example)
+    int64_t nbags_cap = 0;    // max_batch * bags_per_row
+    int64_t local_rows = 0;   // rows of this rank's shard of the space
+    int64_t pair_cap = 0;     // entries one rank may send to one owner per step
+    std::vector<int32_t> h_col_slot;   // host copies (tensor IO)
+    std::vector<int64_t> h_slot_base;
+    int32_t* d_col_slot = nullptr;     // [n_columns] slot fed by column c, -1
+    int64_t* d_slot_base = nullptr;    // [n_slots] first local row of the slot's shard
+    int32_t *d_slot_dim = nullptr, *d_slot_x0 = nullptr, *d_slot_stride = nullptr;
+    float** d_slot_data = nullptr;     // [n_slots] shard of the table (embedding space)
+    float4* d_wide = nullptr;          // wide space: {w, n, z, -} per local row
+    uint32_t* d_own = nullptr;         // [max_nnz] owner rank of entry j or kInvalidRow (not a sharded column)
+    uint32_t* d_lrow = nullptr;        // [max_nnz] local row at the owner
+    int32_t* d_ostart = nullptr;       // [G + 1] start of each owner's run in the routed (owner-sorted) list
+    int32_t* d_bagmask = nullptr;      // [nbags] bit o: owner o holds a partial sum of the bag
+    uint32_t* d_rtag = nullptr;        // owner side, per received entry: (source rank << 27) | bag
+    uint32_t* d_rrow = nullptr;        // owner side, per received entry: local row
+    int32_t* d_nrecv = nullptr;        // device scalar
+    ShardPeer* d_peers = nullptr;      // [G] device copy
+    ShardPeer peers[kMaxRanks];        // host copy (pointers are device addresses)
+    int64_t off_inbox[2] = {0, 0}, off_cnt[2] = {0, 0}, off_recv = 0, off_bagscale = 0, off_grad = 0;   // offsets in the segment
+};
+struct ShardState {
+    int world = 1, rank = 0;
+    bool connected = false, ipc = false;
+    uint8_t* seg = nullptr;            // this rank's exchange segment
+    int64_t seg_bytes = 0;
+    uint8_t* peer_seg[kMaxRanks] = {};
+    ShardSpace sp[2];
+    // flag barriers: flags[k][r] = last epoch rank r signalled on barrier k (written by rank r, through peer memory)
+    int64_t off_flags = 0, off_gred = 0, off_G = 0;
+    uint32_t** d_peer_flags = nullptr;  // [G] device array of peers' flag blocks
+    uint32_t* d_epoch = nullptr;        // [kBarriers] local epoch counters
+    float** d_peer_G = nullptr;         // [G] peers' dense gradient arenas
+    float** d_peer_gred = nullptr;      // [G] peers' reduced slices
+    float* gred = nullptr;              // this rank's reduced slice buffer (whole-arena sized; only the own slice is written)
+    int64_t ar_count = 0;               // floats all-reduced per step (dense gradients + small-table block)
+    uint64_t step = 0;                  // steps issued (inbox double buffering)
+    cudaEvent_t ev_a = nullptr;         // after barrier A on the main stream (owner-side grouping may start)
+    cudaGraphExec_t graph[64] = {};     // whole sharded step per batch slot
+    DevBatch graph_view[64];
+    int64_t graph_launches[64] = {};
+    int eager_steps[64] = {};
+};
+constexpr int kBarriers = 8;
+
 }  // namespace wd
 
 struct WdModel {
@@ -198,6 +272,7 @@ struct WdModel {
     int32_t *d_rtab_dim = nullptr, *d_rtab_stride = nullptr;
     int64_t* d_rtab_gs_off = nullptr;        // [n_rtab] float offset inside the block (-1: large table)
     int32_t* d_nubig[2] = {nullptr, nullptr};   // unique rows below small_base (what stays in the list)
+    wd::ShardState shard;                    // row-sharded tables (world == 1: unused)
     wd::DevPlan dplan{};
     std::vector<void*> allocs;               // everything cudaMalloc'ed (freed in destroy)
     int64_t bytes_allocated = 0;
@@ -264,24 +339,24 @@ struct WdModel {
     float* h_loss_pinned = nullptr;
 
     // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
-    uint32_t *d_sk[2] = {nullptr, nullptr}, *d_sv[2] = {nullptr, nullptr};     // ping-pong keys / values
-    uint32_t *d_sk2[2] = {nullptr, nullptr}, *d_sv2[2] = {nullptr, nullptr};
+    uint32_t *d_sk[wd::kLists] = {}, *d_sv[wd::kLists] = {};     // ping-pong keys / values
+    uint32_t *d_sk2[wd::kLists] = {}, *d_sv2[wd::kLists] = {};
     int32_t* d_sort_hist_s[3] = {nullptr, nullptr, nullptr};
     int64_t sort_hist_cap = 0;
     int32_t* d_sort_counter_s[3] = {nullptr, nullptr, nullptr};
-    uint32_t* d_urow[2] = {nullptr, nullptr};   // unique rows
-    int32_t* d_ustart[2] = {nullptr, nullptr};  // segment starts in the sorted list (+1 sentinel)
-    float* d_ugrad[2] = {nullptr, nullptr};     // [cap, width]
-    int32_t* d_nuniq[2] = {nullptr, nullptr};   // device scalars
-    int32_t* d_nvalid[2] = {nullptr, nullptr};
-    int32_t* d_choff[2] = {nullptr, nullptr};   // chunk offsets of hot rows (exclusive scan)
-    int32_t* d_nchunks[2] = {nullptr, nullptr};
-    float* d_cpart[2] = {nullptr, nullptr};     // chunk partial sums
+    uint32_t* d_urow[wd::kLists] = {};   // unique rows
+    int32_t* d_ustart[wd::kLists] = {};  // segment starts in the sorted list (+1 sentinel)
+    float* d_ugrad[wd::kLists] = {};     // [cap, width]
+    int32_t* d_nuniq[wd::kLists] = {};   // device scalars
+    int32_t* d_nvalid[wd::kLists] = {};
+    int32_t* d_choff[wd::kLists] = {};   // chunk offsets of hot rows (exclusive scan)
+    int32_t* d_nchunks[wd::kLists] = {};
+    float* d_cpart[wd::kLists] = {};     // chunk partial sums
     int64_t cpart_cap = 0;
     int64_t sparse_cap[2] = {0, 0};
     bool sparse_overridden[2] = {false, false};
     int64_t sparse_override_n[2] = {0, 0};
-    int sort_bits[2] = {0, 0};
+    int sort_bits[wd::kLists] = {};
 
     // ---- eval metrics
     double* d_metrics = nullptr;             // accumulators

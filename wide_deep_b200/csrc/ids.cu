@@ -152,11 +152,23 @@ __global__ void ids_fill_kernel(DevPlan p, DevBatch bt, const int32_t* __restric
             continue;
         }
         const int64_t ebase = tab >= 0 ? p.table_row_base[tab] : 0;
+        // row-sharded tables: the entry addresses row id / G of rank id mod G instead of a replicated row
+        const int she = p.sh_col_emb ? p.sh_col_emb[c] : -1, shw = p.sh_col_wide ? p.sh_col_wide[c] : -1;
+        const int64_t she_base = she >= 0 ? p.sh_base_emb[she] : 0, shw_base = shw >= 0 ? p.sh_base_wide[shw] : 0;
+        const uint32_t G = (uint32_t)p.sh_world;
         auto emit = [&](int j, int64_t id) {
             e_id[j] = (int32_t)id;
             e_bc[j] = (int32_t)t;
-            e_wide[j] = wbase >= 0 ? (uint32_t)(wbase + id) : kInvalidRow;
-            e_emb[j] = tab >= 0 ? (uint32_t)(ebase + id) : kInvalidRow;
+            e_wide[j] = (wbase >= 0 && shw < 0) ? (uint32_t)(wbase + id) : kInvalidRow;
+            e_emb[j] = (tab >= 0 && she < 0) ? (uint32_t)(ebase + id) : kInvalidRow;
+            if (p.sh_own_emb) {
+                p.sh_own_emb[j] = she >= 0 ? (uint32_t)id % G : kInvalidRow;
+                p.sh_lrow_emb[j] = (uint32_t)(she_base + (uint32_t)id / G);
+            }
+            if (p.sh_own_wide) {
+                p.sh_own_wide[j] = shw >= 0 ? (uint32_t)id % G : kInvalidRow;
+                p.sh_lrow_wide[j] = (uint32_t)(shw_base + (uint32_t)id / G);
+            }
             if (ind >= 0 && xrow) xrow[ind + id] += 1.f;       // indicator_column: multi-hot counts (A.7)
         };
         if (p.col_kind[c] != WD_COL_CROSS) {

@@ -54,13 +54,19 @@ int init_sparse_tables(WdModel* m, uint64_t seed, int random_w) {
     float s_dnn = (m->dnn_opt.kind == WD_OPT_SGD) ? 0.f : m->dnn_opt.init_acc;
     for (size_t t = 0; t < m->tables.size(); ++t) {
         auto& tb = m->tables[t];
-        emb_init_kernel<<<grid_for(tb.rows * tb.stride, 256, 148 * 32), 256, 0, m->stream>>>(tb.data, tb.rows, tb.dim, tb.dim_logical, tb.stride, s_dnn,
-                                                                                           splitmix64_host(seed + 1000 + t), random_w);
+        // (a shard draws from its own stream: rank r of a sharded table uses seed + 7919 * r)
+        emb_init_kernel<<<grid_for(tb.arows * tb.stride, 256, 148 * 32), 256, 0, m->stream>>>(tb.data, tb.arows, tb.dim, tb.dim_logical, tb.stride, s_dnn,
+                                                                                           splitmix64_host(seed + 1000 + t + (tb.sharded ? 7919ull * m->shard.rank : 0ull)), random_w);
         m->launches++;
     }
     if (m->use_wide && m->wide_rows > 0) {
         float s_lin = (m->lin_opt.kind == WD_OPT_SGD) ? 0.f : m->lin_opt.init_acc;
         wide_init_kernel<<<grid_for(m->wide_rows, 256, 148 * 32), 256, 0, m->stream>>>(m->d_wide, m->wide_rows, s_lin);
+        m->launches++;
+    }
+    if (m->use_wide && m->shard.sp[1].on) {
+        float s_lin = (m->lin_opt.kind == WD_OPT_SGD) ? 0.f : m->lin_opt.init_acc;
+        wide_init_kernel<<<grid_for(m->shard.sp[1].local_rows, 256, 148 * 32), 256, 0, m->stream>>>(m->shard.sp[1].d_wide, m->shard.sp[1].local_rows, s_lin);
         m->launches++;
     }
     WD_CUDA(cudaGetLastError());

@@ -13,20 +13,10 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sparse_dev.cuh"
 
 namespace wd {
 
-__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
 
 // ------------------------------------------------------------------------------------------- wide forward
 // one warp per example: sum of w[row] over the example's wide ids (+ bias)
@@ -447,7 +437,6 @@ __global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint
 // Rows touched at most kChunk times are summed by one lane group directly.  Hotter rows (small tables,
 // skewed ids) are split into chunks of kChunk occurrences that are summed in parallel and then combined in
 // chunk order, so the result stays deterministic and no single group walks thousands of occurrences.
-constexpr int kChunk = 16;
 
 // mch[u] = number of chunks of a multi-chunk row, 0 for rows summed directly (and for u >= nuniq)
 // (also pads the unique-row list with kInvalidRow up to its capacity, so fixed-size exchanges need no host-side count)
@@ -465,14 +454,6 @@ __global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const in
     }
 }
 
-__device__ __forceinline__ int chunk_owner(const int32_t* __restrict__ choff, int nu, int c) {
-    int lo = 0, hi = nu;                         // last u with choff[u] <= c
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (choff[mid] <= c) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 // embedding rows: contribution of occurrence j = dX0[b, x0_off : x0_off + dim] / bag_size(b, column)
 // 8 lanes per work item, each lane covers float4 chunks lig, lig+8, ... of the row
@@ -612,22 +593,6 @@ __global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nitems, const
 }
 
 // --------------------------------------------------------------------------------------------- optimizers
-struct OptParams { int kind; float lr, l1, l2, init_acc; };
-
-__device__ __forceinline__ void opt_update(const OptParams& o, float g, float& w, float& s1, float& s2) {
-    if (o.kind == WD_OPT_ADAGRAD) {                 // tf.train.AdagradOptimizer: acc += g^2; w -= lr*g/sqrt(acc)
-        s1 += g * g;
-        w -= o.lr * g / sqrtf(s1);
-    } else if (o.kind == WD_OPT_FTRL) {             // tf.train.FtrlOptimizer, lr_power = -0.5
-        float n1 = s1 + g * g;
-        float z1 = s2 + g - (sqrtf(n1) - sqrtf(s1)) / o.lr * w;
-        float wn = 0.f;
-        if (fabsf(z1) > o.l1) wn = (copysignf(o.l1, z1) - z1) / (sqrtf(n1) / o.lr + 2.f * o.l2);
-        w = wn; s1 = n1; s2 = z1;
-    } else {
-        w -= o.lr * g;
-    }
-}
 
 // embedding rows: record = [w[dim] | s1[dim] | s2[dim]]
 __global__ void __launch_bounds__(256) emb_apply_kernel(const int32_t* __restrict__ d_nuniq, const uint32_t* __restrict__ urow,
@@ -676,7 +641,6 @@ __global__ void wide_apply_kernel(const int32_t* __restrict__ d_nuniq, const uin
     }
 }
 
-static OptParams make_opt(const WdOptimizer& o) { return OptParams{o.kind, o.lr, o.l1, o.l2, o.init_acc}; }
 
 // sort (row, occurrence) pairs by row and find the unique rows; e_row: per-occurrence row ids (kInvalidRow = skip)
 static int group_tail(WdModel* m, int which, const int32_t* d_n);
@@ -718,11 +682,6 @@ __global__ void merged_sum_kernel(const int32_t* __restrict__ d_nuniq, const int
 }
 
 __global__ void set_count_kernel(int32_t* dst, int32_t v) { *dst = v; }
-__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
-    int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
-}
 
 // Replace the gradient list `which` by the row-wise sum of an external (rows, grads) list, e.g. the
 // all-gathered lists of every rank: keeps "sum duplicates, apply once" across data-parallel replicas.
@@ -743,11 +702,6 @@ int merge_sparse(WdModel* m, int which, const void* rows, const void* grads, int
 // Merge of G lists that are each sorted ascending, duplicate-free and padded with kInvalidRow (what wd_sparse_grads hands out, so
 // what a fixed-size all-gather of it yields): no sort — every element finds its position in the stable merged order with one
 // binary search per list (own list: its index), one kernel; then the usual unique-row / segment pass and the ordered sums.
-__device__ __forceinline__ int upper_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
-    int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
-    return lo;
-}
 __global__ void __launch_bounds__(256) merge_rank_kernel(const uint32_t* __restrict__ rows, int G, int K, uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ vals, int32_t* __restrict__ d_nvalid) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -969,6 +923,43 @@ int sparse_apply_which(WdModel* m, int which) {
     WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
+// ---- wrappers used by shard.cu (rows this rank owns in a row-sharded table space)
+// stable sort of (e_key[i], i) pairs, i < *d_n, by key; keys equal to kInvalidRow sort last; result in d_sk / d_sv of list `which`
+int list_sort_by_key(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_key) {
+    sort_keys_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(d_n, e_key, 1u << m->sort_bits[which], m->d_sk[which], m->d_sv[which]);
+    m->launches++;
+    return radix_sort_pairs(m, which, m->sort_bits[which] + 1, d_n);
+}
+int list_group(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row) {
+    int rc = group_rows(m, which, d_n, e_row);
+    if (rc) return rc;
+    chunk_count_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_choff[which], m->d_urow[which], m->max_nnz);
+    m->launches++;
+    if ((rc = exclusive_scan_i32(m, m->d_choff[which], m->max_nnz, m->d_nchunks[which]))) return rc;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+int list_chunk_combine(WdModel* m, int which, int width) {
+    chunk_combine_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_choff[which], m->d_cpart[which], m->d_ugrad[which], width);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+int list_apply_emb(WdModel* m, int which, int width, int ntab, const int64_t* d_row_base, float* const* d_data, const int32_t* d_dim,
+                   const int32_t* d_stride, const WdOptimizer& o) {
+    emb_apply_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_urow[which], m->d_ugrad[which], width, ntab,
+                                                                            d_row_base, d_data, d_dim, d_stride, make_opt(o));
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+int list_apply_wide(WdModel* m, int which, float4* wide, const WdOptimizer& o) {
+    wide_apply_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_urow[which], m->d_ugrad[which], wide, make_opt(o));
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int sparse_apply(WdModel* m) {
     int rc = sparse_apply_which(m, 0);
     return rc ? rc : sparse_apply_which(m, 1);

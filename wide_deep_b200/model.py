@@ -100,14 +100,20 @@ class WideDeepModel(object):
         return {"sgd": 0, "adagrad": 1, "ftrl": 2}[o["kind"]]
 
     def get_tensor(self, name, slot=0):
-        kind, index, sub, shape = self.plan.tensor_names[name]
+        """Parameter (slot 0) or optimizer slot by TensorFlow variable name.  Row-sharded tensors: this rank's rows
+        (global rows rank, rank + G, ...; Plan.local_shape)."""
+        kind, index, sub, _ = self.plan.tensor_names[name]
+        shape = self.plan.local_shape(name)
         out = np.empty(shape, dtype=np.float32)
         check(self._lib.wd_tensor_io(self._h, kind, index, sub, slot, out.ctypes.data, out.size, 0))
         return out
 
     def set_tensor(self, name, value, slot=0):
+        """``value`` has the GLOBAL shape; of a row-sharded tensor only this rank's rows are uploaded."""
         kind, index, sub, shape = self.plan.tensor_names[name]
         v = np.ascontiguousarray(value, dtype=np.float32).reshape(shape)
+        if self.plan.is_sharded_tensor(name):
+            v = np.ascontiguousarray(v[self.plan.shard_rank::self.plan.shard_world])
         check(self._lib.wd_tensor_io(self._h, kind, index, sub, slot, v.ctypes.data, v.size, 1))
 
     # ------------------------------------------------------------------ steps

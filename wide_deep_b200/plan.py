@@ -106,6 +106,9 @@ class PlanDescC(ctypes.Structure):
         ("max_batch", ctypes.c_int32), ("max_nnz", ctypes.c_int64), ("max_keys", ctypes.c_int64),
         ("gemm_engine", ctypes.c_int32),
         ("dense_exchange_max_rows", ctypes.c_int64), ("wide_small_base", ctypes.c_int64),
+        ("shard_world", ctypes.c_int32), ("shard_rank", ctypes.c_int32),
+        ("table_sharded", _P), ("col_wide_sharded", _P),
+        ("shard_capacity", ctypes.c_int64), ("shard_slack", ctypes.c_float),
     ]
 
 
@@ -132,7 +135,7 @@ class Plan(object):
 
     def __init__(self, feature_conf, cross_conf, model_conf, model_type="wide_deep", max_batch=8192,
                  embedding_dim_override=None, tf_compat_pad=False, gemm_engine="auto", max_nnz=0, max_keys=0,
-                 dense_exchange_max_rows=0):
+                 dense_exchange_max_rows=0, shard_world=1, shard_rank=0, shard_capacity=0, shard_slack=2.0):
         if model_type not in ("wide", "deep", "wide_deep"):
             raise ValueError("Invalid model type: {}, must be one of `wide`, `deep`, `wide_deep`".format(model_type))
         self.model_type, self.max_batch, self.tf_compat_pad = model_type, int(max_batch), bool(tf_compat_pad)
@@ -141,6 +144,18 @@ class Plan(object):
         # data-parallel exchange format: tables / wide columns with at most this many rows travel as a dense gradient block
         # (all-reduced with the dense gradients) instead of (row, gradient) list entries; 0 = lists for everything
         self.dense_exchange_max_rows = int(dense_exchange_max_rows)
+        # Row-sharded tables (the reference partitions large variables over the parameter servers with
+        # min_max_variable_partitioner, python/lib/joint.py:141-143): with shard_world = G > 1 every embedding table / wide
+        # column LARGER than dense_exchange_max_rows is split by row over the G ranks (row id -> rank id mod G, local row id // G);
+        # the smaller ones stay replicated and exchange a dense gradient block.  So in sharded runs every table is one or the other
+        # and no (row, gradient) list ever travels.
+        self.shard_world, self.shard_rank = int(shard_world), int(shard_rank)
+        self.shard_capacity, self.shard_slack = int(shard_capacity), float(shard_slack)
+        if self.shard_world > 1 and self.dense_exchange_max_rows <= 0:
+            self.dense_exchange_max_rows = 16384
+        if not (0 <= self.shard_rank < max(self.shard_world, 1)):
+            raise ValueError("shard_rank {} outside [0, {})".format(self.shard_rank, self.shard_world))
+        is_sharded = lambda rows: self.shard_world > 1 and rows > self.dense_exchange_max_rows
         edim = (lambda n: int(embedding_dim_override)) if embedding_dim_override else embedding_dim
 
         # ---- input fields
@@ -244,16 +259,19 @@ class Plan(object):
         is_wide = [c.wide_base == 0 and self.use_wide for c in order]
         small = [w and 0 < self.dense_exchange_max_rows >= c.buckets for c, w in zip(order, is_wide)]
         self.wide_small_base = None
+        self.wide_sharded = [bool(w and is_sharded(c.buckets)) for c, w in zip(order, is_wide)]
         for want_small in (False, True):
             if want_small:
                 self.wide_small_base = base
-            for c, w, sm in zip(order, is_wide, small):
-                if w and sm == want_small:
+            for c, w, sm, sh in zip(order, is_wide, small, self.wide_sharded):
+                if w and sm == want_small and not sh:
                     c.wide_base = base
                     base += c.buckets
-        for c, w in zip(order, is_wide):
+        for c, w, sh in zip(order, is_wide, self.wide_sharded):
             if w:
                 self.wide_columns.append(c)
+                if sh:
+                    c.wide_base = -1                  # rows live in the sharded wide space, not in the replicated one
             else:
                 c.wide_base = -1
         self.wide_rows = base
@@ -267,7 +285,7 @@ class Plan(object):
                 if kind == "emb":
                     col, dim = payload
                     col.emb_table = len(self.tables)
-                    self.tables.append(dict(name=name, column=col, rows=col.buckets, dim=dim, x0_off=po))
+                    self.tables.append(dict(name=name, column=col, rows=col.buckets, dim=dim, x0_off=po, sharded=bool(is_sharded(col.buckets))))
                     width = dim          # physical width is _pad(dim, 4); the next column re-aligns to 4 anyway
                 elif kind == "ind":
                     payload.ind_off = po
@@ -303,6 +321,12 @@ class Plan(object):
         self.dnn_opt = parse_optimizer(model_conf.get("dnn_optimizer") or "Adagrad",
                                        model_conf.get("dnn_initial_learning_rate") or 0.001)
 
+        if self.dense_exchange_max_rows > 0 and self.dnn_opt["kind"] == "ftrl" and self.tables:
+            # a touched embedding row whose summed gradient is exactly 0 still takes an FTRL step (w is rebuilt from z, n), which
+            # changes a randomly initialised row; the dense gradient block cannot tell "touched with g = 0" from "untouched"
+            raise ValueError("dnn_optimizer Ftrl with embedding tables is not supported together with the dense gradient block of "
+                             "multi-GPU runs (dense_exchange_max_rows / shard_world > 1); use Adagrad or SGD for the deep part")
+
         # ---- tensor names (TensorFlow variable names of the reference's checkpoint)
         T = self.tensor_names = OrderedDict()
         for c in self.wide_columns:
@@ -324,6 +348,25 @@ class Plan(object):
                     T[scope + "/batch_normalization/beta"] = (T_DENSE, did, D_BETA, (o,))
 
     # ------------------------------------------------------------------ helpers
+    def is_sharded_tensor(self, name):
+        """True for parameters of row-sharded tables / wide columns: a rank then holds global rows rank, rank + G, ..."""
+        kind, index, _, _ = self.tensor_names[name]
+        if self.shard_world <= 1:
+            return False
+        if kind == T_EMB_TABLE:
+            return bool(self.tables[index]["sharded"])
+        if kind == T_WIDE_COL:
+            return bool(self.wide_sharded[index])
+        return False
+
+    def local_shape(self, name):
+        """Shape of the part of tensor `name` this rank holds (the global shape unless the tensor is row-sharded)."""
+        shape = tuple(self.tensor_names[name][3])
+        if not self.is_sharded_tensor(name):
+            return shape
+        rows = (shape[0] - self.shard_rank + self.shard_world - 1) // self.shard_world
+        return (rows,) + shape[1:]
+
     def dense_tensor_id(self, tower, layer):
         return sum(len(t["hidden"]) + 1 for t in self.towers[:tower]) + layer
 
@@ -366,7 +409,7 @@ class Plan(object):
         number of ids one column contributes per step (batch size for single-valued columns): columns whose table is exchanged
         densely (dense_exchange_max_rows) contribute nothing."""
         t = self.dense_exchange_max_rows
-        big = lambda n: not (0 < t >= n)
+        big = lambda n: not (0 < t >= n) and self.shard_world <= 1
         k_emb = sum(rows_per_column for tb in self.tables if big(tb["rows"]))
         k_wide = sum(rows_per_column for c in self.wide_columns if big(c.buckets))
         return k_emb, k_wide
@@ -408,7 +451,7 @@ class Plan(object):
                 aux_off.append(0)
                 aux_n.append(0)
         d = PlanDescC()
-        d.api_version = 1
+        d.api_version = 2
         d.model_type = (1 if self.use_wide else 0) | (2 if self.use_deep else 0)
         d.n_cat_fields, d.n_dense_fields = len(self.cat_fields), len(self.dense_fields)
         d.cat_field_is_string = arr(self.cat_is_string, np.uint8)
@@ -448,6 +491,10 @@ class Plan(object):
             dst.lr_power, dst.init_acc = o["lr_power"], o["init_acc"]
         d.max_batch, d.max_nnz, d.max_keys, d.gemm_engine = self.max_batch, self.max_nnz, self.max_keys, GEMM[self.gemm_engine]
         d.dense_exchange_max_rows = self.dense_exchange_max_rows
+        d.shard_world, d.shard_rank = self.shard_world, self.shard_rank
+        d.table_sharded = arr([1 if t["sharded"] else 0 for t in self.tables], np.uint8)
+        d.col_wide_sharded = arr([1 if x else 0 for x in self.wide_sharded], np.uint8)
+        d.shard_capacity, d.shard_slack = self.shard_capacity, self.shard_slack
         d.wide_small_base = self.wide_small_base if self.wide_small_base is not None else self.wide_rows
         return d, keep
 
