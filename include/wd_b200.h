@@ -283,6 +283,11 @@ int64_t wd_tsv_parse(const WdTsvSpec *spec, const char *text, int64_t text_len, 
                      int32_t *offsets_out, uint64_t *keys_out, int64_t keys_cap,
                      float *dense_out, float *label_out, float *weight_out, int32_t n_threads);
 
+/* Page-locked host buffers for the input pipeline (the `dataset.prefetch` buffers of the reference's input_fn, python/lib/
+ * dataset.py:181-184): parse into these, hand them to wd_batch_prefetch_slot.  WD_ENODEVICE without a CUDA device. */
+int wd_host_alloc(size_t bytes, void **out);
+int wd_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,9 +6,9 @@
 
 Loop semantics follow reference python/train.py:65-164: `dynamic_train` (train on file i, evaluate on file
 i+1), `train_and_eval`, `train`; the model directory is wiped unless --keep_train (train.py:188-191).
-Multi-GPU: launch with torchrun; every rank trains on its shard of each file (dataset.shard semantics) with
-synchronous exact gradient exchange (wide_deep_b200/parallel.py) instead of the reference's asynchronous
-parameter server (train.py:197-217).
+Multi-GPU: `torchrun --nproc-per-node G train.py ...` (main_distributed below): every rank trains on its shard of each file
+(dataset.shard semantics) with synchronous, exact steps over row-sharded tables (wide_deep_b200/sharded.py) instead of the
+reference's asynchronous parameter servers (train.py:197-217); train only, as in the reference.
 """
 import argparse
 import os
@@ -44,7 +44,7 @@ def elapse_time(t0):
 
 
 def _fn(model, path, mode):
-    return lambda: input_fn(path, None, mode, FLAGS.batch_size, config=CONF, plan=model.plan)
+    return lambda: input_fn(path, None, mode, FLAGS.batch_size, config=CONF, plan=model.plan, pinned=(mode == "train"))
 
 
 def _show(results):
@@ -106,7 +106,19 @@ def train(model):
             print("INFO: <EPOCH {}>: Finish training {}, take {} mins".format(n + 1, f, elapse_time(t0)))
 
 
+def distributed_env():
+    """(rank, world, local_rank) when launched by torchrun / torch.distributed.run, else (0, 1, 0).  Counterpart of the reference's
+    `distribution` block (conf/train.yaml, python/train.py:201-217): workers there, ranks here; no parameter servers."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, 0
+    return int(os.environ["RANK"]), world, int(os.environ.get("LOCAL_RANK", "0"))
+
+
 def main():
+    rank, world, local = distributed_env()
+    if world > 1:
+        return main_distributed(rank, world, local)
     print("Using wide_deep_b200 (CUDA sm_100a) in place of TensorFlow")
     print("\nModel Type: {}".format(FLAGS.model_type))
     model_dir = os.path.join(FLAGS.model_dir, FLAGS.model_type)
@@ -127,6 +139,36 @@ def main():
         dynamic_train(model)
     else:
         train_and_eval(model)
+
+
+def main_distributed(rank, world, local):
+    """torchrun --nproc-per-node G train.py ...: rank r trains on every G-th line of each file (dataset.shard semantics, reference
+    python/lib/dataset.py:173-174) with synchronous, exact steps; tables larger than 16384 rows are row-sharded over the ranks
+    (the reference partitions them over its parameter servers, python/lib/joint.py:141-143).  As in the reference, distributed
+    runs train only ("distributed can not including eval", python/train.py:215-216); rank 0 alone touches the model directory."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")                    # plumbing only (IPC handles, checkpoint gather); data moves over NVLink
+    log = print if rank == 0 else (lambda *a, **k: None)
+    log("Using wide_deep_b200 (CUDA sm_100a) in place of TensorFlow: rank {} of {}".format(rank, world))
+    model_dir = os.path.join(FLAGS.model_dir, FLAGS.model_type)
+    if not FLAGS.keep_train and rank == 0:
+        shutil.rmtree(model_dir, ignore_errors=True)
+        log("Remove model directory: {}".format(model_dir))
+    dist.barrier()
+    model = build_custom_estimator(model_dir, FLAGS.model_type, config=CONF, max_batch=FLAGS.batch_size, device=local,
+                                   shard_world=world, shard_rank=rank)
+    log("INFO: Build estimator: {}".format(model))
+    for n in range(FLAGS.train_epochs):
+        log("INFO: " + "=" * 30 + " START EPOCH {} ".format(n + 1) + "=" * 30 + "\n")
+        for f in list_files(FLAGS.train_data):
+            t0 = time.time()
+            log("INFO: <EPOCH {}>: Start training {}".format(n + 1, f))
+            model.train(input_fn=lambda f=f: input_fn(f, None, "train", FLAGS.batch_size, config=CONF, plan=model.plan, rank=rank, world=world, pinned=True))
+            log("INFO: <EPOCH {}>: Finish training {}, take {} mins".format(n + 1, f, elapse_time(t0)))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -151,3 +151,44 @@ def test_dense_exchange_layout_and_list_bounds():
     assert p0.exchange_rows(512) == (512 * len(p0.tables), 512 * len(p0.wide_columns))
     d, _keep = p1.to_c()
     assert d.dense_exchange_max_rows == 16384 and d.wide_small_base == p1.wide_small_base
+
+
+@pytest.mark.parametrize("tf_compat_pad", [False, True])
+def test_pinned_ring_and_prefetch_thread_yield_the_same_batches(native_lib, tf_compat_pad):
+    """input_fn(pinned=True) parses into a ring of (page-locked, when a GPU exists) buffer sets and the estimator drains it from a
+    prefetch thread: same batches as the plain path, batch by batch; sharded input (rank, world) has equal batch counts."""
+    from wide_deep_b200.dataset import Prefetcher, input_fn
+    from wide_deep_b200.plan import compile_plan
+    cfg = Config()
+    plan = compile_plan(cfg, "wide_deep", 64, tf_compat_pad=tf_compat_pad)
+    data = os.path.join(ROOT, "data", "test", "test1")
+    plain = list(input_fn(data, None, "eval", 64, config=cfg, plan=plan))[:12]
+    got = 0
+    for i, b in enumerate(Prefetcher(input_fn(data, None, "eval", 64, config=cfg, plan=plan, pinned=True), depth=2)):
+        if i >= len(plain):
+            break
+        a = plain[i]
+        assert b.batch_size == a.batch_size
+        np.testing.assert_array_equal(b.keys, a.keys)
+        np.testing.assert_array_equal(b.offsets, a.offsets)
+        np.testing.assert_array_equal(b.dense, a.dense)
+        np.testing.assert_array_equal(b.label, a.label)
+        got += 1
+    assert got == len(plain)
+    counts = [sum(1 for _ in input_fn(data, None, "train", 64, config=cfg, plan=plan, rank=r, world=3)) for r in range(3)]
+    assert counts[0] == counts[1] == counts[2] == -(-(5000 // 3) // 64)
+
+
+def test_sharded_plan_marks_large_tables_only(native_lib):
+    from wide_deep_b200 import synthetic
+    from wide_deep_b200.plan import Plan
+    fc, cross, model, emb = synthetic.criteo_conf()
+    p = Plan(fc, cross, model, "wide_deep", max_batch=512, embedding_dim_override=emb, shard_world=8, shard_rank=3)
+    assert p.dense_exchange_max_rows == 16384
+    assert sum(1 for t in p.tables if t["sharded"]) == 8 and sum(p.wide_sharded) == 16
+    name = next(n for n in p.tensor_names if p.is_sharded_tensor(n) and "embedding_weights" in n)
+    rows = p.tensor_names[name][3][0]
+    assert p.local_shape(name) == ((rows - 3 + 7) // 8, 32)
+    assert p.exchange_rows(512) == (0, 0)                 # nothing travels as (row, gradient) lists in a sharded run
+    p1 = Plan(fc, cross, model, "wide_deep", max_batch=512, embedding_dim_override=emb)
+    assert not any(t["sharded"] for t in p1.tables) and not any(p1.wide_sharded)

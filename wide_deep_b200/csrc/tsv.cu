@@ -222,3 +222,21 @@ extern "C" int64_t wd_tsv_parse(const WdTsvSpec* sp, const char* text, int64_t t
     }
     return nnz;
 }
+
+// Page-locked host memory for the input pipeline (dataset.py parses TSV text straight into a ring of these buffers, so the
+// asynchronous refill of a batch slot, wd_batch_prefetch_slot, really is asynchronous).  Counterpart of the buffers tf.data's
+// prefetch owns in the reference's input_fn (python/lib/dataset.py:181-184).
+extern "C" int wd_host_alloc(size_t bytes, void** out) {
+    if (!out) { wd::set_error("wd_host_alloc: null output"); return WD_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { wd::set_error("no CUDA device: cannot page-lock host memory"); return WD_ENODEVICE; }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes > 0 ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { wd::set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return WD_ENOMEM; }
+    *out = p;
+    return WD_OK;
+}
+extern "C" int wd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return WD_OK;
+}

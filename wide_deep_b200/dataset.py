@@ -34,6 +34,57 @@ def list_files(path):
     return [path]
 
 
+class PinnedRing(object):
+    """A ring of page-locked host buffer sets (one set = the arrays of one batch), allocated ONCE through the library
+    (cudaHostAlloc).  The parser writes straight into a set and ``wd_batch_prefetch_slot`` copies from it asynchronously — the
+    counterpart of the buffers ``dataset.prefetch`` owns in the reference's input_fn (python/lib/dataset.py:181-184).  A set is
+    reused ``depth`` batches later, by which time the step that read its device copy has long been issued.  Without a CUDA
+    device (CPU tests) the sets are ordinary numpy arrays."""
+
+    def __init__(self, n_rows, n_cat_fields, n_dense_fields, key_cap, depth=4):
+        self._lib = _native.lib()
+        self.depth, self._i, self._raw = depth, 0, []
+        self.n_rows, self.F, self.Nd, self.key_cap = n_rows, n_cat_fields, n_dense_fields, int(key_cap)
+        self.pinned = self._lib.wd_device_count() > 0
+        self.sets = [self._make_set() for _ in range(depth)]
+
+    def _buf(self, nbytes):
+        if not self.pinned:
+            return np.zeros(max(nbytes, 8), dtype=np.uint8)
+        p = ctypes.c_void_p()
+        _native.check(self._lib.wd_host_alloc(max(nbytes, 8), ctypes.byref(p)))
+        self._raw.append(p)
+        return np.ctypeslib.as_array((ctypes.c_uint8 * max(nbytes, 8)).from_address(p.value))
+
+    def _make_set(self):
+        n, F, Nd = self.n_rows, self.F, self.Nd
+        return dict(offsets=self._buf((n * F + 1) * 4).view(np.int32), keys=self._buf(self.key_cap * 8).view(np.uint64),
+                    dense=self._buf(n * max(Nd, 1) * 4).view(np.float32), label=self._buf(n * 4).view(np.float32),
+                    weight=self._buf(n * 4).view(np.float32))
+
+    def grow_keys(self, key_cap):
+        """A batch needs more key room than the ring was sized for (long multi-valued rows): re-allocate every set's key buffer."""
+        self.key_cap = int(key_cap)
+        for s in self.sets:
+            s["keys"] = self._buf(self.key_cap * 8).view(np.uint64)
+
+    def next(self):
+        s = self.sets[self._i % self.depth]
+        self._i += 1
+        return s
+
+    def close(self):
+        for p in self._raw:
+            self._lib.wd_host_free(p)
+        self._raw, self.sets = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class TsvReader(object):
     """Parses TSV text into ``Batch`` objects for a given Plan."""
 
@@ -75,14 +126,17 @@ class TsvReader(object):
         self.n_threads = n_threads or min(os.cpu_count() or 1, 16)
         self._lib = _native.lib()
 
-    def parse(self, lines):
-        """list of text lines (str or bytes, no trailing newline needed) -> Batch"""
+    def parse(self, lines, ring=None):
+        """list of text lines (str or bytes, no trailing newline needed) -> Batch.  ``ring``: a PinnedRing whose next buffer set
+        receives the batch (the returned Batch then aliases it and is valid until the ring comes round again)."""
         if lines and isinstance(lines[0], bytes):
             text = b"\n".join(lines)                                  # input_fn's path: no decode / encode round trip
         else:
             text = ("\n".join(l.rstrip("\n") for l in lines)).encode("utf-8")
         n = len(lines)
         F, Nd = len(self.plan.cat_fields), len(self.plan.dense_fields)
+        if ring is not None:
+            return self._parse_into_ring(text, n, ring)
         offsets = np.zeros(n * F + 1, dtype=np.int32)
         dense = np.zeros((n, max(Nd, 1)), dtype=np.float32)
         label = np.zeros(n, dtype=np.float32)
@@ -105,10 +159,76 @@ class TsvReader(object):
                      weight if (self.use_weight and not self.is_pred) else None)
 
 
-def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=None, rank=0, world=1, seed=123):
-    """Generator of ``Batch`` for one pass over the data (one epoch), mirroring the reference's
+def _parse_into_ring(self, text, n, ring):
+    F, Nd = len(self.plan.cat_fields), len(self.plan.dense_fields)
+    if n > ring.n_rows:
+        raise ValueError("batch of %d lines, pinned ring sized for %d" % (n, ring.n_rows))
+    need = n * max(F, 1) + text.count(b",") + 1                      # every field holds at most (commas + 1) tokens
+    s = ring.next()                                                  # the oldest set: nothing in flight reads it any more
+    if self.plan.tf_compat_pad:
+        # padded string fields (quirk Q2) can exceed the token count: ask for the size first (keys_cap = 0)
+        need = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, s["offsets"].ctypes.data, None, 0,
+                                      s["dense"].ctypes.data, s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
+        if need < 0:
+            raise ValueError(self._lib.wd_last_error().decode())
+    if need > ring.key_cap:
+        ring.grow_keys(max(need, 2 * ring.key_cap))                  # (old key buffers stay allocated: in-flight batches alias them)
+    nnz = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, s["offsets"].ctypes.data, s["keys"].ctypes.data,
+                                 ring.key_cap, s["dense"].ctypes.data, s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
+    if nnz < 0:
+        raise ValueError(self._lib.wd_last_error().decode())
+    b = Batch.__new__(Batch)                                         # views of the pinned set: no copies (Batch() would copy)
+    b.batch_size = n
+    b.keys, b.offsets = s["keys"][:nnz], s["offsets"][:n * F + 1]
+    b.dense = s["dense"][:n * Nd].reshape(n, Nd) if Nd else None
+    b.label = None if self.is_pred else s["label"][:n]
+    b.weight = s["weight"][:n] if (self.use_weight and not self.is_pred) else None
+    return b
+
+
+TsvReader._parse_into_ring = _parse_into_ring
+
+
+class Prefetcher(object):
+    """Runs a batch generator on a background thread, ``depth`` batches ahead of the consumer: parsing (C++ worker threads, GIL
+    released) overlaps the consumer's Python and the GPU step — tf.data's prefetch thread in the reference's input_fn."""
+
+    def __init__(self, gen, depth=2):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=depth)
+        self._done = object()
+        self._err = None
+
+        def run():
+            try:
+                for item in gen:
+                    self._q.put(item)
+            except BaseException as e:          # surfaced on the consumer's thread
+                self._err = e
+            self._q.put(self._done)
+
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self._q.get()
+        if item is self._done:
+            if self._err is not None:
+                raise self._err
+            raise StopIteration
+        return item
+
+
+def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=None, rank=0, world=1, seed=123, pinned=False):
+    """Iterator of ``Batch`` for one pass over the data (one epoch), mirroring the reference's
     ``input_fn(csv_data_file, img_data_file, mode, batch_size)`` (dataset.py:293-310).  ``img_data_file`` is
-    accepted for signature compatibility and must be None (the CNN branch is out of scope)."""
+    accepted for signature compatibility and must be None (the CNN branch is out of scope).
+    The files are read and the pinned ring is allocated HERE (on the caller's thread, whose CUDA device is the model's); only
+    the per-batch parsing is lazy, so the returned iterator may be drained from a prefetch thread."""
     assert mode in ("train", "eval", "pred"), "mode must in `train`, `eval`, or `pred`, found {}".format(mode)
     if img_data_file:
         raise ValueError("image inputs are not supported by the B200 path (cnn_use_flag: 0)")
@@ -118,9 +238,22 @@ def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=N
         with open(f, "rb") as fh:
             lines.extend(l for l in fh.read().split(b"\n") if l != b"")
     if world > 1:
-        lines = lines[rank::world]
+        # dataset.shard(num_workers, worker_index) (reference dataset.py:173-174): every world-th line.  Synchronous training
+        # needs the same number of batches on every rank, so the few lines beyond a multiple of `world` are dropped.
+        per = len(lines) // world
+        lines = lines[rank::world][:per]
     if mode == "train":
         perm = np.random.Generator(np.random.Philox(seed)).permutation(len(lines))
         lines = [lines[i] for i in perm]
-    for i in range(0, len(lines), batch_size):
-        yield reader.parse(lines[i:i + batch_size])
+    # pinned=True (estimator.train, which consumes batch by batch): parse into a ring of page-locked buffers so the host->device
+    # refill of a batch slot is truly asynchronous; a yielded Batch stays valid for the next `depth - 1` batches
+    ring = None
+    if pinned:
+        F, Nd = len(plan.cat_fields), len(plan.dense_fields)
+        ring = PinnedRing(batch_size, F, Nd, key_cap=batch_size * max(F, 1) * 4, depth=6)
+
+    def batches():
+        for i in range(0, len(lines), batch_size):
+            yield reader.parse(lines[i:i + batch_size], ring=ring)
+
+    return batches()

@@ -25,7 +25,7 @@ CKPT_PREFIX = "model.ckpt-"
 
 class WideAndDeepClassifier(object):
     def __init__(self, model_dir, model_type, config=None, device=0, max_batch=None, seed=None, tf_compat_pad=None,
-                 gemm_engine="auto"):
+                 gemm_engine="auto", shard_world=1, shard_rank=0, group=None):
         if model_type not in ("wide", "deep", "wide_deep"):
             raise ValueError("Invalid model type: {}, must be one of `wide`, `deep`, `wide_deep`".format(model_type))
         self.config = config or Config()
@@ -43,7 +43,12 @@ class WideAndDeepClassifier(object):
         slack = 8 if self.config.train.get("multivalue") else 1
         if self.tf_compat_pad and self.config.train.get("multivalue"):
             slack *= 4                                   # '' padding multiplies the ids of crosses over multi-valued fields
+        # multi-GPU (python/train.py under torchrun): rank `shard_rank` of `shard_world`; large tables are row-sharded over the
+        # ranks, every rank trains on its shard of the input (wide_deep_b200/sharded.py)
+        self.shard_world, self.shard_rank, self.group = int(shard_world), int(shard_rank), group
+        self._trainer = None
         self.plan = compile_plan(self.config, model_type, mb, tf_compat_pad=tf_compat_pad, gemm_engine=gemm_engine,
+                                 shard_world=self.shard_world, shard_rank=self.shard_rank, shard_slack=float(max(2, self.shard_world)),
                                  max_nnz=mb * len(self.config.read_feature_conf()) * 4 * slack + mb * 64,
                                  max_keys=mb * max(1, len(self.config.read_feature_conf())) * slack)
         self._model = None
@@ -68,6 +73,9 @@ class WideAndDeepClassifier(object):
                 self.restore(path)
             else:
                 self._model.init(self.seed)
+            if self.shard_world > 1:
+                from .sharded import ShardedTrainer
+                self._trainer = ShardedTrainer(self._model, self.group)
         elif checkpoint_path:
             self.restore(checkpoint_path)
         return self._model
@@ -76,12 +84,16 @@ class WideAndDeepClassifier(object):
         """Flat .npz of every variable (TensorFlow variable names) + optimizer slots; keeps the newest
         keep_checkpoint_max files (reference conf/train.yaml runconfig)."""
         m = self._model
-        os.makedirs(self.model_dir, exist_ok=True)
+        # multi-GPU: a collective — row-sharded tensors are gathered from all ranks; rank 0 alone writes
+        get = self._trainer.get_tensor if self._trainer is not None else m.get_tensor
         blob = {"global_step": np.asarray(m.global_step)}
         for name in m.tensor_names():
-            blob[name] = m.get_tensor(name)
+            blob[name] = get(name)
             for s in range(m.n_slots(name)):
-                blob["%s/slot%d" % (name, s + 1)] = m.get_tensor(name, slot=s + 1)
+                blob["%s/slot%d" % (name, s + 1)] = get(name, slot=s + 1)
+        if self.shard_rank != 0:
+            return None
+        os.makedirs(self.model_dir, exist_ok=True)
         path = os.path.join(self.model_dir, "%s%d.npz" % (CKPT_PREFIX, m.global_step))
         tmp = path + ".tmp.%d" % os.getpid()                 # written beside, then renamed: a crash never leaves a truncated
         with open(tmp, "wb") as fh:                          # checkpoint that latest_checkpoint() would pick up
@@ -123,13 +135,17 @@ class WideAndDeepClassifier(object):
         log_every = (self.config.runconfig or {}).get("log_step_count_steps") or 1000
         # one batch of look-ahead, as the reference's input_fn prefetches (python/lib/dataset.py:181-184): while step i runs on the
         # GPU, batch i+1 is parsed and its host->device copy issued (wd_batch_prefetch_slot, two alternating slots)
-        it = iter(input_fn())
+        from .dataset import Prefetcher
+        it = Prefetcher(input_fn(), depth=2)             # batches are parsed on a background thread, two ahead of the step
         cur = next(it, None)
         slot = 0
         if cur is not None:
             m.prefetch_slot(slot, cur)
         while cur is not None:
-            m.train_step_slot(slot, want_loss=False)         # enqueue step i ...
+            if self._trainer is not None:
+                self._trainer.step_slot(slot, want_loss=False)   # collective: every rank steps on its shard of the batch
+            else:
+                m.train_step_slot(slot, want_loss=False)     # enqueue step i ...
             nxt = next(it, None)                             # ... parse batch i+1 on the host while it runs ...
             if nxt is not None:
                 m.prefetch_slot(1 - slot, nxt)               # ... start its copy on the upload stream ...
@@ -145,6 +161,9 @@ class WideAndDeepClassifier(object):
         return self
 
     def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
+        if self.shard_world > 1:
+            raise ValueError("evaluate() on a multi-GPU (row-sharded) estimator: the reference's distributed mode trains only "
+                             "(train.py:215-216); evaluate with a single-process estimator on the saved checkpoint")
         m = self._ensure_model(checkpoint_path, need_trained=True)
         m.eval_reset()
         n = 0
