@@ -60,6 +60,30 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def usable_cores():
+    """Host cores this process may actually use: logical CPUs, limited by the affinity mask and by the container's cgroup CPU
+    quota (the GPU box shows 128 logical CPUs behind a 16-CPU quota; 128 OpenMP threads on 16 CPUs' worth of time run 40x
+    slower than 16).  This is the `cores` the CPU arm reports and the thread count it runs with."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        t = open("/sys/fs/cgroup/cpu.max").read().split()
+        if t[0] != "max":
+            n = min(n, max(1, int(float(t[0]) / float(t[1]) + 0.5)))
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / p + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def gemm_traffic_from_profile(engine, batch):
     """DRAM bytes of the GEMM launches of one step, from the newest committed ncu capture that matches (engine, batch):
     profiles/*_gemm_traffic.json = {"engine", "batch", "dram_bytes_per_step", "command", "source"} written by
@@ -326,7 +350,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     wl = Workload(args.workload, args.gpus, args.batch)
     # the same step as the GPU arm: same tables, same GLOBAL batch (N x per-GPU batch: the CPU arm is the whole box's host cores,
     # whatever N is), a bounded number of steps
@@ -596,7 +620,7 @@ def main():
             if wl.name == "criteo":
                 out["parity"] = parity_check(args.engine)
             del model
-            threads = os.cpu_count() or 1
+            threads = usable_cores()
             v, sec, nst = oracle_examples_per_sec(wl, B, 10, 2, threads, budget_s=20.0)
             out["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
                                    "sample": "%d steps of %d examples, same tables/config (oracle/fast.py: torch-CPU + C hashing, fp32)" % (nst, B)}

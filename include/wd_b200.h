@@ -33,7 +33,9 @@ enum { WD_NORM_NONE = 0, WD_NORM_MINMAX = 1, WD_NORM_STANDARD = 2, WD_NORM_LOG =
 /* cross key sources: raw string field (dense input incl. padding) or a categorical column (sparse input) */
 enum { WD_KEY_FIELD = 0, WD_KEY_COLUMN = 1 };
 /* optimizers (reference python/lib/utils/model_util.py:62-105) */
-enum { WD_OPT_SGD = 0, WD_OPT_ADAGRAD = 1, WD_OPT_FTRL = 2 };
+enum { WD_OPT_SGD = 0, WD_OPT_ADAGRAD = 1, WD_OPT_FTRL = 2,
+       WD_OPT_ADAM = 3     /* tf.train.AdamOptimizer: slots m, v; sparse gradients decay m, v over the WHOLE table (TF semantics) */,
+       WD_OPT_RMSPROP = 4  /* tf.train.RMSPropOptimizer (not centered): slots rms (init 1), momentum; touched rows only */ };
 /* activations (reference python/lib/utils/model_util.py:28-59) */
 enum { WD_ACT_RELU = 0, WD_ACT_RELU6, WD_ACT_SIGMOID, WD_ACT_TANH, WD_ACT_LEAKY_RELU, WD_ACT_ELU, WD_ACT_SELU,
        WD_ACT_SOFTPLUS, WD_ACT_SOFTSIGN };
@@ -47,6 +49,8 @@ enum { WD_GEMM_AUTO = 0, WD_GEMM_FFMA = 1, WD_GEMM_TC3X = 2 /* tcgen05 kind::tf3
 typedef struct WdOptimizer {
     int32_t kind;        /* WD_OPT_* */
     float lr, l1, l2, lr_power, init_acc;
+    float beta1, beta2, epsilon;   /* Adam (epsilon also RMSProp) */
+    float rho, momentum;           /* RMSProp decay / momentum */
 } WdOptimizer;
 
 /* Immutable description of the model, produced by wide_deep_b200.plan.compile_plan() from conf/*.yaml.
@@ -146,6 +150,9 @@ int wd_model_create(const WdPlanDesc *plan, int device, WdModel **out);
 int wd_model_destroy(WdModel *m);
 /* Device-side initialisation with the TF initialisers (truncated normal / glorot uniform / zeros). */
 int wd_model_init(WdModel *m, uint64_t seed);
+/* Number of optimizer steps already taken (checkpoint resume): restores Adam's beta1^t / beta2^t (the non-slot variables of
+ * tf.train.AdamOptimizer); a no-op for the other optimizers. */
+int wd_set_opt_step(WdModel *m, int64_t steps);
 /* Copy a parameter or optimizer slot to/from host.  slot 0 = value, 1.. = optimizer accumulators
  * (Adagrad: acc; FTRL: n, z).  Logical (unpadded) shapes; kernels are [in, out] like tf.layers.dense. */
 int wd_tensor_io(WdModel *m, int kind, int index, int sub, int slot, void *host, int64_t count, int to_device);

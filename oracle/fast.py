@@ -40,6 +40,9 @@ class FastCpuModel(object):
 
     def __init__(self, oracle_model, threads=None):
         self.om = oracle_model
+        for o in (oracle_model.opt_lin, oracle_model.opt_dnn):
+            if o["kind"] not in ("adagrad", "ftrl", "sgd"):
+                raise NotImplementedError("the timed CPU arm covers Adagrad / Ftrl / SGD (the benchmark's optimizers), not %s" % o["kind"])
         if threads:
             torch.set_num_threads(int(threads))
         self.threads = torch.get_num_threads()

@@ -27,24 +27,33 @@ BN_EPS = 1e-3
 def parse_optimizer(spec, default_lr):
     """'Adagrad' | 'Ftrl' | 'SGD' (use default_lr) or 'tf.train.FtrlOptimizer(learning_rate=..., ...)'
     (whose own learning_rate wins, model_util.py:95-101).  -> dict(kind, lr, l1, l2, lr_power, init_acc)"""
-    names = {"Adagrad": "adagrad", "Ftrl": "ftrl", "SGD": "sgd"}
+    names = {"Adagrad": "adagrad", "Ftrl": "ftrl", "SGD": "sgd", "Adam": "adam", "RMSProp": "rmsprop"}
+    base = dict(l1=0.0, l2=0.0, lr_power=-0.5, init_acc=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8, rho=0.9, momentum=0.0)
     if spec in names:
-        return dict(kind=names[spec], lr=float(default_lr), l1=0.0, l2=0.0, lr_power=-0.5, init_acc=0.1)
+        o = dict(base, kind=names[spec], lr=float(default_lr))
+        if o["kind"] == "rmsprop":
+            o["epsilon"] = 1e-10                      # tf.train.RMSPropOptimizer default
+        return o
     m = re.match(r"^\s*tf\.train\.(\w+)Optimizer\((.*)\)\s*$", spec)
     if not m:
         raise ValueError("Unsupported optimizer option: `{}`".format(spec))
-    cls = {"Adagrad": "adagrad", "Ftrl": "ftrl", "GradientDescent": "sgd"}.get(m.group(1))
+    cls = {"Adagrad": "adagrad", "Ftrl": "ftrl", "GradientDescent": "sgd", "Adam": "adam", "RMSProp": "rmsprop"}.get(m.group(1))
     if cls is None:
         raise ValueError("Unsupported optimizer option: `{}`".format(spec))
     call = ast.parse("f(" + m.group(2) + ")", mode="eval").body
     kw = {k.arg: ast.literal_eval(k.value) for k in call.keywords}
     if call.args:
         kw.setdefault("learning_rate", ast.literal_eval(call.args[0]))
-    return dict(kind=cls, lr=float(kw["learning_rate"]),
+    if cls == "rmsprop" and kw.get("centered"):
+        raise ValueError("centered RMSProp is not supported")
+    return dict(kind=cls, lr=float(kw.get("learning_rate", 0.001 if cls == "adam" else default_lr)),
                 l1=float(kw.get("l1_regularization_strength", 0.0)),
                 l2=float(kw.get("l2_regularization_strength", 0.0)),
                 lr_power=float(kw.get("learning_rate_power", -0.5)),
-                init_acc=float(kw.get("initial_accumulator_value", 0.1)))
+                init_acc=float(kw.get("initial_accumulator_value", 0.1)),
+                beta1=float(kw.get("beta1", 0.9)), beta2=float(kw.get("beta2", 0.999)),
+                epsilon=float(kw.get("epsilon", 1e-8 if cls == "adam" else 1e-10)),
+                rho=float(kw.get("decay", 0.9)), momentum=float(kw.get("momentum", 0.0)))
 
 
 def act_fwd(name, z):
@@ -216,8 +225,15 @@ class OracleModel(object):
                 self.slots[k] = {"acc": np.full_like(v, o["init_acc"])}
             elif o["kind"] == "ftrl":
                 self.slots[k] = {"n": np.full_like(v, o["init_acc"]), "z": np.zeros_like(v)}
+            elif o["kind"] == "adam":                 # tf.train.AdamOptimizer slots m, v = 0
+                self.slots[k] = {"m": np.zeros_like(v), "v": np.zeros_like(v)}
+            elif o["kind"] == "rmsprop":              # tf.train.RMSPropOptimizer slots rms = 1, momentum = 0
+                self.slots[k] = {"ms": np.ones_like(v), "mom": np.zeros_like(v)}
             else:
                 self.slots[k] = {}
+        # Adam's non-slot variables, one pair per optimizer (linear / dnn): beta^t, multiplied in fp32 after every step
+        self.beta_pow = {"lin": [np.float32(self.opt_lin.get("beta1", 0.9)), np.float32(self.opt_lin.get("beta2", 0.999))],
+                         "dnn": [np.float32(self.opt_dnn.get("beta1", 0.9)), np.float32(self.opt_dnn.get("beta2", 0.999))]}
 
     # ---- forward
     def transform(self, batch):
@@ -400,8 +416,34 @@ class OracleModel(object):
                 l1, l2 = np.float32(o["l1"]), np.float32(o["l2"])
                 w1 = np.where(np.abs(z1) > l1, (np.sign(z1) * l1 - z1) / (np.sqrt(n1) / lr + np.float32(2.0) * l2), np.float32(0.0))
                 s["n"][rows], s["z"][rows], p[rows] = n1, z1, w1.astype(np.float32)
+            elif o["kind"] == "rmsprop":
+                # ApplyRMSProp / SparseApplyRMSProp (touched rows only): ms += (g^2 - ms)(1 - rho); mom = mom*momentum + lr*g*rsqrt(ms + eps)
+                rho, mo, eps = np.float32(o["rho"]), np.float32(o["momentum"]), np.float32(o["epsilon"])
+                ms = view(s["ms"]) + (gr * gr - view(s["ms"])) * (np.float32(1) - rho)
+                mom = view(s["mom"]) * mo + (gr * lr) / np.sqrt(ms + eps)
+                s["ms"][rows], s["mom"][rows] = ms, mom
+                p[rows] = view(p) - mom
+            elif o["kind"] == "adam":
+                # ApplyAdam; sparse gradients (AdamOptimizer._apply_sparse_shared): m and v decay over the WHOLE variable, the summed
+                # gradients are scatter-added, then every row moves
+                b1, b2, eps = np.float32(o["beta1"]), np.float32(o["beta2"]), np.float32(o["epsilon"])
+                b1p, b2p = self.beta_pow["lin" if name.startswith("linear/") else "dnn"]
+                lr_t = lr * np.sqrt(np.float32(1) - b2p) / (np.float32(1) - b1p)
+                if isinstance(g, tuple):
+                    s["m"] *= b1
+                    s["v"] *= b2
+                    s["m"][rows] += gr * (np.float32(1) - b1)
+                    s["v"][rows] += gr * gr * (np.float32(1) - b2)
+                else:
+                    s["m"] += (gr - s["m"]) * (np.float32(1) - b1)
+                    s["v"] += (gr * gr - s["v"]) * (np.float32(1) - b2)
+                p -= lr_t * s["m"] / (np.sqrt(s["v"]) + eps)
             else:
                 p[rows] = view(p) - lr * gr
+        for key, o in (("lin", self.opt_lin), ("dnn", self.opt_dnn)):      # AdamOptimizer._finish
+            if o["kind"] == "adam":
+                self.beta_pow[key][0] = np.float32(self.beta_pow[key][0] * np.float32(o["beta1"]))
+                self.beta_pow[key][1] = np.float32(self.beta_pow[key][1] * np.float32(o["beta2"]))
         self.global_step += 1
 
     def train_step(self, batch, labels, weights=None):

@@ -84,6 +84,12 @@ def copy_params_to_product(oracle_model, model):
         if "n" in slots:
             model.set_tensor(name, slots["n"], slot=1)
             model.set_tensor(name, slots["z"], slot=2)
+        if "m" in slots:
+            model.set_tensor(name, slots["m"], slot=1)
+            model.set_tensor(name, slots["v"], slot=2)
+        if "ms" in slots:
+            model.set_tensor(name, slots["ms"], slot=1)
+            model.set_tensor(name, slots["mom"], slot=2)
 
 
 def rel_err(a, b, floor=1.0):

@@ -125,6 +125,12 @@ def test_train_steps_modes(mode):
     ("wide_deep", "tf.train.GradientDescentOptimizer(learning_rate=0.00002)", "Adagrad", 1),
     ("wide_deep", "tf.train.FtrlOptimizer(learning_rate=0.05,l1_regularization_strength=0.001,l2_regularization_strength=0.01)", "SGD", 1),
     ("wide_deep", "Adagrad", "tf.train.FtrlOptimizer(learning_rate=0.1,l1_regularization_strength=0.5,l2_regularization_strength=1)", 1),
+    # the reference's remaining factory names (model_util.py:84-90): Adam (dense m / v decay over whole tables, TF's sparse Adam)
+    # and RMSProp (touched rows only), by name and as tf.train expressions
+    ("wide_deep", "Adam", "RMSProp", 1),
+    ("deep", "tf.train.AdamOptimizer(learning_rate=0.001)", "Ftrl", 1),
+    ("wide", "Adagrad", "Adam", 0),
+    ("wide_deep", "tf.train.RMSPropOptimizer(learning_rate=0.001,decay=0.8,momentum=0.5)", "tf.train.AdamOptimizer(0.002, beta1=0.8)", 1),
 ])
 def test_train_steps_optimizers(model_type, dnn_opt, lin_opt, bn):
     fc, cross, model = small_conf(hidden=(64, 32), dnn_opt=dnn_opt, lin_opt=lin_opt, bn=bn)
@@ -158,7 +164,7 @@ def _train_compare(fc, cross, model, model_type, steps, seed, weighted=False, B=
         got, exp = pm.get_tensor(name), om.params[name]
         scale = max(float(np.abs(exp).max()), 1e-3)
         assert np.max(np.abs(got - exp)) <= 2e-4 * scale, "%s: max abs diff %g (scale %g)" % (name, np.max(np.abs(got - exp)), scale)
-        for si, key in enumerate([k for k in ("acc", "n", "z") if k in om.slots[name]]):
+        for si, key in enumerate([k for k in ("acc", "n", "z", "m", "v", "ms", "mom") if k in om.slots[name]]):
             g2, e2 = pm.get_tensor(name, slot=si + 1), om.slots[name][key]
             sc = max(float(np.abs(e2).max()), 1e-3)
             assert np.max(np.abs(g2 - e2)) <= 5e-4 * sc, "%s slot %s" % (name, key)

@@ -59,7 +59,7 @@ def test_plan_matches_reference_dimensions(native_lib):
     # cross key order = SparseCross op order: categorical-column keys first, then raw string keys
     c = next(c for c in p.columns if c.name == "age_bucketized_X_scheduling_id")
     assert [k[0] for k in c.keys] == [1, 0]
-    assert p.lin_opt == dict(kind="ftrl", lr=0.1, l1=0.5, l2=1.0, lr_power=-0.5, init_acc=0.1)
+    assert {k: p.lin_opt[k] for k in ("kind", "lr", "l1", "l2", "lr_power", "init_acc")} == dict(kind="ftrl", lr=0.1, l1=0.5, l2=1.0, lr_power=-0.5, init_acc=0.1)
     assert p.dnn_opt["kind"] == "adagrad" and p.dnn_opt["lr"] == 0.05
 
 
@@ -70,8 +70,12 @@ def test_optimizer_parsing():
     assert (o["kind"], o["lr"], o["l1"], o["l2"]) == ("ftrl", 0.1, 0.5, 1.0)
     with pytest.raises(ValueError):
         parse_optimizer("__import__('os').system('true')", 0.1)     # never eval()'ed
+    a = parse_optimizer("Adam", 0.1)                                 # the reference's five names are all offered (model_util.py:84-90)
+    assert (a["kind"], a["lr"], a["beta1"], a["beta2"], a["epsilon"]) == ("adam", 0.1, 0.9, 0.999, 1e-8)
+    r = parse_optimizer("tf.train.RMSPropOptimizer(learning_rate=0.01, decay=0.8, momentum=0.5)", 9.9)
+    assert (r["kind"], r["lr"], r["rho"], r["momentum"], r["epsilon"]) == ("rmsprop", 0.01, 0.8, 0.5, 1e-10)
     with pytest.raises(ValueError):
-        parse_optimizer("Adam", 0.1)
+        parse_optimizer("tf.train.MomentumOptimizer(0.1, 0.9)", 0.1)
 
 
 def test_layer_sources_match_oracle():

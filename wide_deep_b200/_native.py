@@ -41,6 +41,7 @@ SYMBOLS = {
     "wd_model_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "wd_model_destroy": (ctypes.c_int, [_vp]),
     "wd_model_init": (ctypes.c_int, [_vp, _u64]),
+    "wd_set_opt_step": (ctypes.c_int, [_vp, _i64]),
     "wd_tensor_io": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _i64, ctypes.c_int]),
     "wd_tensor_size": (_i64, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "wd_train_step": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "farmhash.cuh"
+#include "sparse_dev.cuh"
 
 namespace wd {
 static thread_local char g_err[1024] = "";
@@ -141,7 +142,7 @@ static int init_dense_slots(WdModel* m) {
     std::vector<float> S1(m->dense_count, 0.f);
     for (size_t i = 0; i < m->dense.size(); ++i) {
         const WdOptimizer& o = (m->use_wide && i == 0) ? m->lin_opt : m->dnn_opt;
-        float s1 = o.kind == WD_OPT_SGD ? 0.f : o.init_acc;
+        float s1 = slot1_init(o);
         int64_t end = i + 1 < m->dense.size() ? m->dense[i + 1].off : m->dense_count;
         for (int64_t j = m->dense[i].off; j < end; ++j) S1[j] = s1;
     }
@@ -244,6 +245,13 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if (G == 1 && (rc = dev_alloc(m, &m->d_dlogit, Bm))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss_part, 512))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_head_counter, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_bpow, 4))) return rc;
+    {
+        const float bp[4] = {m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2};     // beta^1: state before the first step
+        WD_CUDA(cudaMemcpyAsync(m->d_bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, m->stream));
+        WD_CUDA(cudaStreamSynchronize(m->stream));
+    }
     if ((rc = dev_alloc(m, &m->d_metrics, 512))) return rc;
     WD_CUDA(cudaMallocHost(&m->h_loss_pinned, 64));
 
@@ -270,7 +278,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if (m->use_deep) {
         int64_t row_base = 0;
         std::vector<int64_t> h_row_base;
-        const int nslots = m->dnn_opt.kind == WD_OPT_FTRL ? 2 : (m->dnn_opt.kind == WD_OPT_ADAGRAD ? 1 : 0);
+        const int nslots = opt_nslots(m->dnn_opt);
         for (int t = 0; t < d->n_tables; ++t) {
             EmbTable tb{};
             tb.rows = d->table_rows[t]; tb.dim = d->table_dim[t]; tb.x0_off = d->table_x0_off[t];
@@ -560,7 +568,7 @@ static int init_dense(WdModel* m, WdModelExtra* x, uint64_t seed) {
     }
     for (size_t i = 0; i < m->dense.size(); ++i) {
         const WdOptimizer& o = (m->use_wide && i == 0) ? m->lin_opt : m->dnn_opt;
-        float s1 = o.kind == WD_OPT_SGD ? 0.f : o.init_acc;
+        float s1 = slot1_init(o);
         for (int64_t j = 0; j < m->dense[i].count; ++j) S1[m->dense[i].off + j] = s1;
     }
     WD_CUDA(cudaMemcpyAsync(m->d_P, P.data(), P.size() * 4, cudaMemcpyHostToDevice, m->stream));
@@ -936,6 +944,13 @@ static int apply_core(WdModel* m) {
     if ((rc = dense_apply(m))) return rc;
     if ((rc = small_apply(m))) return rc;
     mark(m, "dense_apply");
+    if (m->lin_opt.kind == WD_OPT_ADAM || m->dnn_opt.kind == WD_OPT_ADAM) {
+        // AdamOptimizer._finish: beta powers advance once per step, after every variable of the optimizer has been updated (the
+        // sparse lists may still be running on their side streams and read the powers: join them first)
+        for (int w = 0; w < 2; ++w)
+            if (m->side_active[w]) WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0));
+        if ((rc = adam_tick(m))) return rc;
+    }
     for (int w = 0; w < 2; ++w)
         if (m->side_active[w]) { WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_done[w], 0)); m->side_active[w] = false; }
     m->grads_pending = false;
@@ -944,9 +959,14 @@ static int apply_core(WdModel* m) {
 
 static int train_eager(WdModel* m) {
     int rc;
-    if ((rc = forward_core(m, true))) return rc;
-    if ((rc = backward_core(m))) return rc;
-    return apply_core(m);
+    // the whole step runs here, nothing exchanges the dense gradient arena between backward and optimizer: reduce the gradient
+    // partials inside the optimizer kernel (mlp.cu dense_vec_kernel<2>)
+    m->fuse_dense = true;
+    rc = forward_core(m, true);
+    if (!rc) rc = backward_core(m);
+    if (!rc) rc = apply_core(m);
+    m->fuse_dense = false;
+    return rc;
 }
 
 static bool same_view(const DevBatch& a, const DevBatch& b) {

@@ -336,6 +336,8 @@ struct WdModel {
     float* d_dlogit = nullptr;               // [max_batch]
     float* d_loss_part = nullptr;            // per-block partials
     float* d_loss = nullptr;                 // scalar
+    int32_t* d_head_counter = nullptr;       // blocks of the fused head kernel that have finished (last one sums the loss)
+    float* d_bpow = nullptr;                 // Adam: {linear beta1^t, linear beta2^t, dnn beta1^t, dnn beta2^t}, multiplied in fp32 after every step (AdamOptimizer._finish)
     float* h_loss_pinned = nullptr;
 
     // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
@@ -363,7 +365,8 @@ struct WdModel {
     int64_t eval_batches = 0;
 
     int64_t launches = 0;
-    int64_t gemm_fallbacks = 0;             // tensor-core engine GEMMs that ran on the FFMA kernel instead (tests assert 0)
+    bool fuse_dense = false;                // whole local step (train_eager): dense gradient reduction fused into the optimizer kernel
+    int64_t gemm_fallbacks = 0;            // tensor-core engine GEMMs that ran on the FFMA kernel instead (tests assert 0)
     int cur_slot = 0;
     bool graphs_enabled = true;              // WD_NO_GRAPH=1 disables step graphs
     int cur_layer = 0;                       // layer being launched (names the profiling marks)
@@ -392,6 +395,7 @@ int dense_reduce_grads(WdModel* m);                              // mlp.cu
 int dense_apply(WdModel* m);                                     // mlp.cu
 int loss_forward(WdModel* m, bool need_grad);                    // mlp.cu: logits = wide + deep, loss, dlogit
 int model_init_params(WdModel* m, uint64_t seed);                // init.cu
+int adam_tick(WdModel* m);                                       // misc.cu: beta powers advance (after every optimizer of the step)
 int metrics_accumulate(WdModel* m);                              // metrics.cu
 int metrics_finish(WdModel* m, double* out10);
 

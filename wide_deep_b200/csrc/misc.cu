@@ -3,6 +3,7 @@
 //   wide        zeros                                       (linear_model, A.7)
 //   metrics     accuracy / auc(200 thresholds) / ...        (reference joint.py:402-406 head)
 #include "common.cuh"
+#include "sparse_dev.cuh"
 
 namespace wd {
 
@@ -51,7 +52,7 @@ static uint64_t splitmix64_host(uint64_t x) {
 // random_w = 0: weights zero, optimizer slots at their initial accumulator value (state of a freshly created model,
 // so padding entries never see a 0/sqrt(0) update)
 int init_sparse_tables(WdModel* m, uint64_t seed, int random_w) {
-    float s_dnn = (m->dnn_opt.kind == WD_OPT_SGD) ? 0.f : m->dnn_opt.init_acc;
+    float s_dnn = slot1_init(m->dnn_opt);
     for (size_t t = 0; t < m->tables.size(); ++t) {
         auto& tb = m->tables[t];
         // (a shard draws from its own stream: rank r of a sharded table uses seed + 7919 * r)
@@ -60,12 +61,12 @@ int init_sparse_tables(WdModel* m, uint64_t seed, int random_w) {
         m->launches++;
     }
     if (m->use_wide && m->wide_rows > 0) {
-        float s_lin = (m->lin_opt.kind == WD_OPT_SGD) ? 0.f : m->lin_opt.init_acc;
+        float s_lin = slot1_init(m->lin_opt);
         wide_init_kernel<<<grid_for(m->wide_rows, 256, 148 * 32), 256, 0, m->stream>>>(m->d_wide, m->wide_rows, s_lin);
         m->launches++;
     }
     if (m->use_wide && m->shard.sp[1].on) {
-        float s_lin = (m->lin_opt.kind == WD_OPT_SGD) ? 0.f : m->lin_opt.init_acc;
+        float s_lin = slot1_init(m->lin_opt);
         wide_init_kernel<<<grid_for(m->shard.sp[1].local_rows, 256, 148 * 32), 256, 0, m->stream>>>(m->shard.sp[1].d_wide, m->shard.sp[1].local_rows, s_lin);
         m->launches++;
     }
@@ -164,3 +165,33 @@ int metrics_finish(WdModel* m, double* out) {
 }
 
 }  // namespace wd
+
+// ---- Adam's non-slot variables (beta1^t, beta2^t per optimizer) live in device memory so that a replayed CUDA graph advances them
+namespace wd {
+__global__ void adam_tick_kernel(float* bpow, float lb1, float lb2, float db1, float db2, int lin, int dnn) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (lin) { bpow[0] *= lb1; bpow[1] *= lb2; }
+        if (dnn) { bpow[2] *= db1; bpow[3] *= db2; }
+    }
+}
+int adam_tick(WdModel* m) {
+    adam_tick_kernel<<<1, 32, 0, m->stream>>>(m->d_bpow, m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2,
+                                             m->lin_opt.kind == WD_OPT_ADAM, m->dnn_opt.kind == WD_OPT_ADAM);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+}  // namespace wd
+
+// Restores the optimizers' step count (checkpoint resume): beta^(steps + 1), multiplied up in fp32 exactly as training does.
+extern "C" int wd_set_opt_step(WdModel* m, int64_t steps) {
+    if (!m || steps < 0) { wd::set_error("wd_set_opt_step: bad arguments"); return WD_EINVAL; }
+    WD_CUDA(cudaSetDevice(m->device));
+    float bp[4] = {m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2};
+    const float b[4] = {m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2};
+    for (int64_t s = 0; s < steps && s < 100000000; ++s)
+        for (int i = 0; i < 4; ++i) bp[i] *= b[i];
+    WD_CUDA(cudaMemcpyAsync(m->d_bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, m->stream));
+    WD_CUDA(cudaStreamSynchronize(m->stream));
+    return WD_OK;
+}

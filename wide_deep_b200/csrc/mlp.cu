@@ -325,6 +325,106 @@ __global__ void __launch_bounds__(256) logits_wgrad_kernel(int B, int K, const f
     }
 }
 
+// ---- fused head: logits layers of all towers (one warp per example) + wide logit + sigmoid cross entropy + dlogit + the batch
+// loss (block partials, summed in block order by the last block to finish) — one launch instead of logits_fwd per tower, head
+// and loss_final
+constexpr int kFusedTowers = 4;
+struct HeadIn { int n; GemvSegs S[kFusedTowers]; const float* kernel[kFusedTowers]; const float* bias[kFusedTowers]; float* tower_logit[kFusedTowers]; };
+__global__ void __launch_bounds__(256) logits_head_kernel(HeadIn in, int B, const float* __restrict__ wide_logit, const float* __restrict__ label,
+                                                        const float* __restrict__ weight, float* __restrict__ logits, float* __restrict__ dlogit,
+                                                        float* __restrict__ loss_part, int32_t* __restrict__ counter, float* __restrict__ loss_out) {
+    __shared__ float red[8];
+    __shared__ bool is_last;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    float lsum = 0.f;
+    for (int b = warp; b < B; b += nw) {
+        float x = wide_logit ? wide_logit[b] : 0.f;
+        for (int t = 0; t < in.n; ++t) {
+            const GemvSegs& S = in.S[t];
+            float acc = 0.f;
+            for (int s = 0; s < S.n; ++s) {
+                const float* row = S.ptr[s] + (int64_t)b * S.ld[s];
+                const float* kw = in.kernel[t] + S.koff[s];
+                for (int k = lane * 4; k < S.k[s]; k += 128) {
+                    float4 xv = *reinterpret_cast<const float4*>(row + k);
+                    float4 w = *reinterpret_cast<const float4*>(kw + k);
+                    acc = fmaf(xv.x, w.x, acc); acc = fmaf(xv.y, w.y, acc); acc = fmaf(xv.z, w.z, acc); acc = fmaf(xv.w, w.w, acc);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            const float tl = acc + in.bias[t][0];
+            if (lane == 0) in.tower_logit[t][b] = tl;
+            x += tl;
+        }
+        if (lane == 0) {
+            logits[b] = x;
+            if (label) {
+                const float y = label[b], w = weight ? weight[b] : 1.f;
+                lsum += w * (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));      // sigmoid cross entropy with logits
+                if (dlogit) dlogit[b] = (1.f / (1.f + expf(-x)) - y) * w;
+            }
+        }
+    }
+    if (lane == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        loss_part[blockIdx.x] = s;
+        __threadfence();
+        is_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = 0; i < (int)gridDim.x; ++i) s += (double)((volatile float*)loss_part)[i];
+        *loss_out = (float)s;
+        *counter = 0;
+    }
+}
+
+// ---- fused logits-layer backward for one input segment: weight-gradient partials per 128-row tile, the data gradient of the
+// segment, and (first segment) the bias partial — which is also the wide bias's gradient partial (both are sums of dlogit)
+__global__ void __launch_bounds__(256) logits_bwd_kernel(int B, int K, const float* __restrict__ src, int ld, const float* __restrict__ dlogit,
+                                                        const float* __restrict__ kw, float* __restrict__ gpart, int64_t gstride,
+                                                        float* __restrict__ bias_part, int64_t bias_stride, float* __restrict__ wide_bias_part,
+                                                        int64_t wide_bias_stride, float* __restrict__ dst, int dld, int accumulate) {
+    __shared__ float red[4][64];
+    __shared__ float dl[128];
+    const int rt = blockIdx.y, kx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const int k = blockIdx.x * 64 + kx;
+    const int b0 = rt * 128;
+    if (threadIdx.x < 128) dl[threadIdx.x] = (b0 + threadIdx.x < B) ? dlogit[b0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    float acc = 0.f;
+    if (k < K) {
+        const int r0 = b0 + ry * 32;
+        const float w = dst ? kw[k] : 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i)
+            if (r0 + i < B) {
+                const float g = dl[ry * 32 + i];
+                acc = fmaf(src[(int64_t)(r0 + i) * ld + k], g, acc);
+                if (dst) {
+                    float* d = dst + (int64_t)(r0 + i) * dld + k;
+                    *d = accumulate ? *d + g * w : g * w;
+                }
+            }
+    }
+    red[ry][kx] = acc;
+    __syncthreads();
+    if (ry == 0 && k < K) gpart[(int64_t)rt * gstride + k] = red[0][kx] + red[1][kx] + red[2][kx] + red[3][kx];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (bias_part || wide_bias_part)) {
+        float s = 0.f;
+        for (int i = 0; i < 128; ++i) s += dl[i];
+        if (bias_part) bias_part[(int64_t)rt * bias_stride] = s;
+        if (wide_bias_part) wide_bias_part[(int64_t)rt * wide_bias_stride] = s;
+    }
+}
+
 // hidden layer backward through [BN affine] and activation:
 //   da = dH * gamma/sqrt(1+eps); dZ = da * act'(a); column partial sums of dZ (bias), dH*a/sqrt(1+eps) (gamma), dH (beta)
 // block = 32 columns x 128 rows (one row tile); writes dZ and dZT (zero padded to the tile)
@@ -379,6 +479,62 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
     }
 }
 
+// The same for the 3xBF16 engine (dZ leaves as bf16 hi / lo copies only, no transposed copy), vectorised: a block covers one
+// 128-row tile x 128 columns; a thread owns 4 consecutive columns (16-byte loads of dH and A, 8-byte stores of the bf16 copies)
+// and every 8th row; the column partial sums go through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_logical, const float* __restrict__ dH, const float* __restrict__ Aact,
+                                                          int ld, const float* __restrict__ gamma, int act, int bn,
+                                                          float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
+                                                          int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo) {
+    __shared__ float red[3][8][128];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 128 + cx * 4, rt = blockIdx.y;
+    const float inv = 0.99950037468777f;
+    float gsc[4], sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sbe[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gsc[j] = (bn && n0 + j < n_logical) ? gamma[n0 + j] * inv : 1.f;
+    if (n0 < N) {
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int mm = rt * 128 + i * 8 + ry;
+            if (mm >= B) break;
+            const float4 dh4 = *reinterpret_cast<const float4*>(dH + (int64_t)mm * ld + n0);
+            const float4 a4 = *reinterpret_cast<const float4*>(Aact + (int64_t)mm * ld + n0);
+            const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float dz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dz[j] = 0.f;
+                if (n0 + j < n_logical) {
+                    dz[j] = dh[j] * gsc[j] * act_bwd(act, a[j]);
+                    sb[j] += dz[j]; sg[j] += dh[j] * a[j] * inv; sbe[j] += dh[j];
+                }
+            }
+            __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+            split_bf16(dz[0], h0, l0); split_bf16(dz[1], h1, l1); split_bf16(dz[2], h2, l2); split_bf16(dz[3], h3, l3);
+            uint2 ph, pl;
+            ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+            *reinterpret_cast<uint2*>(q_hi + (int64_t)mm * ld + n0) = ph;
+            *reinterpret_cast<uint2*>(q_lo + (int64_t)mm * ld + n0) = pl;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][ry][cx * 4 + j] = sb[j]; red[1][ry][cx * 4 + j] = sg[j]; red[2][ry][cx * 4 + j] = sbe[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int n = blockIdx.x * 128 + threadIdx.x;
+        if (n < N) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            for (int i = 0; i < 8; ++i) { x += red[0][i][threadIdx.x]; y += red[1][i][threadIdx.x]; z += red[2][i][threadIdx.x]; }
+            p_bias[(int64_t)rt * pstride + n] = x;
+            if (bn) { p_gamma[(int64_t)rt * pstride + n] = y; p_beta[(int64_t)rt * pstride + n] = z; }
+        }
+    }
+}
+
 // wide bias gradient partials: per 128-row tile sum of dlogit
 __global__ void rowtile_sum_kernel(int B, const float* __restrict__ v, float* __restrict__ part, int64_t stride) {
     int rt = blockIdx.x;
@@ -391,6 +547,7 @@ __global__ void rowtile_sum_kernel(int B, const float* __restrict__ v, float* __
 }
 int wide_bias_grad(WdModel* m) {
     if (!m->use_wide) return WD_OK;
+    if (m->use_deep && !m->towers.empty()) return WD_OK;               // written by the first logits_bwd_kernel launch of the step
     const int rts = (m->dbatch.B + 127) / 128;
     rowtile_sum_kernel<<<rts, 32, 0, m->stream>>>(m->dbatch.B, m->d_dlogit, m->d_gpart + m->dense[0].gpart_off, m->dense[0].gstride);
     m->launches++;
@@ -418,7 +575,10 @@ __global__ void dense_reduce_kernel(const DenseTensor* __restrict__ T, int nt, i
     }
 }
 
-struct OptParamsD { int kind; float lr, l1, l2; };
+struct OptParamsD { int kind; float lr, l1, l2, beta1, beta2, epsilon, rho, momentum; const float* bpow; };
+static OptParamsD make_opt_d(const WdOptimizer& o, const float* bpow) {
+    return OptParamsD{o.kind, o.lr, o.l1, o.l2, o.beta1, o.beta2, o.epsilon, o.rho, o.momentum, bpow};
+}
 __device__ __forceinline__ void opt_update_d(const OptParamsD& o, float g, float& w, float& s1, float& s2) {
     if (o.kind == WD_OPT_ADAGRAD) {
         s1 += g * g;
@@ -429,6 +589,15 @@ __device__ __forceinline__ void opt_update_d(const OptParamsD& o, float g, float
         float wn = 0.f;
         if (fabsf(z1) > o.l1) wn = (copysignf(o.l1, z1) - z1) / (sqrtf(n1) / o.lr + 2.f * o.l2);
         w = wn; s1 = n1; s2 = z1;
+    } else if (o.kind == WD_OPT_ADAM) {             // ApplyAdam; bpow = {beta1^t, beta2^t} (device: advances after every step)
+        const float lr_t = o.lr * sqrtf(1.f - o.bpow[1]) / (1.f - o.bpow[0]);
+        s1 += (g - s1) * (1.f - o.beta1);
+        s2 += (g * g - s2) * (1.f - o.beta2);
+        w -= lr_t * s1 / (sqrtf(s2) + o.epsilon);
+    } else if (o.kind == WD_OPT_RMSPROP) {          // ApplyRMSProp (not centered)
+        s1 += (g * g - s1) * (1.f - o.rho);
+        s2 = s2 * o.momentum + (g * o.lr) / sqrtf(s1 + o.epsilon);
+        w -= s2;
     } else {
         w -= o.lr * g;
     }
@@ -475,6 +644,70 @@ __global__ void dense_apply_kernel(const DenseTensor* __restrict__ T, int nt, in
         }
     }
 }
+// Vectorised dense-gradient reduction / optimizer for the 3xBF16 engine (no transposed weight copies to scatter): one thread per
+// four consecutive arena floats (tensor offsets, partial strides and kernel widths are multiples of 4), one tensor lookup per
+// thread instead of per element.
+//   MODE 0: G = sum of the live partials                      (data-parallel runs: G is exchanged before the optimizer)
+//   MODE 1: optimizer from G                                   (after the exchange)
+//   MODE 2: both in one pass, G never materialised            (single-GPU step: saves a 6 MB round trip and a launch)
+template <int MODE>
+__global__ void __launch_bounds__(256) dense_vec_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total4, const float* __restrict__ gpart,
+                                                        float* __restrict__ G, float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2,
+                                                        float* __restrict__ Wsplit, int64_t wt_count, OptParamsD dnn, OptParamsD lin, int lin_tensor,
+                                                        int live_row_tiles) {
+    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i4 * 4;
+        int lo = 0, hi = nt - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (T[mid].off <= i) lo = mid; else hi = mid - 1;
+        }
+        const DenseTensor t = T[lo];
+        const int64_t e = i - t.off;
+        if (e >= t.count) {                                               // alignment gap between tensors
+            if (MODE == 0) reinterpret_cast<float4*>(G)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        float4 g;
+        if (MODE != 1) {
+            const int parts = t.g_rowtiles ? live_row_tiles : t.gparts;
+            const float* p = gpart + t.gpart_off + e;
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < parts; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)q * t.gstride);
+                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            }
+            if (e + 1 >= t.count) g.y = 0.f;                              // tensors shorter than the vector (scalar biases): the tail
+            if (e + 2 >= t.count) g.z = 0.f;                              // lanes read neighbouring partials, not gradients
+            if (e + 3 >= t.count) g.w = 0.f;
+            if (MODE == 0) { reinterpret_cast<float4*>(G)[i4] = g; continue; }
+        } else {
+            g = reinterpret_cast<const float4*>(G)[i4];
+        }
+        const OptParamsD o = lo == lin_tensor ? lin : dnn;
+        float4 w = reinterpret_cast<float4*>(P)[i4], s1 = reinterpret_cast<float4*>(S1)[i4], s2 = reinterpret_cast<float4*>(S2)[i4];
+        opt_update_d(o, g.x, w.x, s1.x, s2.x);
+        if (e + 1 < t.count) opt_update_d(o, g.y, w.y, s1.y, s2.y);
+        if (e + 2 < t.count) opt_update_d(o, g.z, w.z, s1.z, s2.z);
+        if (e + 3 < t.count) opt_update_d(o, g.w, w.w, s1.w, s2.w);
+        reinterpret_cast<float4*>(P)[i4] = w;
+        reinterpret_cast<float4*>(S1)[i4] = s1;
+        reinterpret_cast<float4*>(S2)[i4] = s2;
+        if (t.wt_off >= 0) {                                              // bf16 hi / lo copies of W [K, N] (what the GEMMs read)
+            __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(Wsplit);
+            __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+            split_bf16(w.x, h0, l0); split_bf16(w.y, h1, l1); split_bf16(w.z, h2, l2); split_bf16(w.w, h3, l3);
+            uint2 ph, pl;
+            ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+            *reinterpret_cast<uint2*>(q + t.wt_off + e) = ph;
+            *reinterpret_cast<uint2*>(q + wt_count + t.wt_off + e) = pl;
+        }
+    }
+}
+
 // Wt refresh only (after init / tensor upload)
 __global__ void dense_transpose_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total, const float* __restrict__ P, float* __restrict__ Wt,
                                        float* __restrict__ Wsplit, int64_t wt_count, int bf16) {
@@ -569,6 +802,7 @@ int mlp_forward(WdModel* m, bool train) {
             S.k[s] = LL.segs[s].width_phys;
             S.koff[s] = LL.segs[s].k_off;
         }
+        if ((int)m->towers.size() <= kFusedTowers) continue;            // logits layers run inside the fused head kernel (loss_forward)
         logits_fwd_kernel<<<grid_for((int64_t)B * 32, 256), 256, 0, m->stream>>>(S, m->d_P + m->dense[LL.t_kernel].off,
                                                                                 m->d_P + m->dense[LL.t_bias].off, B, tw.logit);
         m->launches++;
@@ -579,6 +813,32 @@ int mlp_forward(WdModel* m, bool train) {
 
 int loss_forward(WdModel* m, bool need_grad) {
     const int B = m->dbatch.B;
+    const int ntow = m->use_deep ? (int)m->towers.size() : 0;
+    if (ntow <= kFusedTowers) {
+        HeadIn in{};
+        in.n = ntow;
+        for (int t = 0; t < ntow; ++t) {
+            Tower& tw = m->towers[t];
+            Layer& LL = tw.layers[tw.n_hidden];
+            in.S[t].n = LL.n_in_segs;
+            for (int s = 0; s < LL.n_in_segs; ++s) {
+                in.S[t].ptr[s] = src_ptr(m, tw, LL.segs[s].src, false);
+                in.S[t].ld[s] = src_ld(m, tw, LL.segs[s].src, false);
+                in.S[t].k[s] = LL.segs[s].width_phys;
+                in.S[t].koff[s] = LL.segs[s].k_off;
+            }
+            in.kernel[t] = m->d_P + m->dense[LL.t_kernel].off;
+            in.bias[t] = m->d_P + m->dense[LL.t_bias].off;
+            in.tower_logit[t] = tw.logit;
+        }
+        const int blocks = grid_for((int64_t)B * 32, 256, 512);          // (loss_part holds 512 block partials)
+        logits_head_kernel<<<blocks, 256, 0, m->stream>>>(in, B, m->use_wide ? m->d_wide_logit : nullptr, m->batch_has_label ? m->d_label : nullptr,
+                                                         m->dbatch.weight, m->d_logits, need_grad ? m->d_dlogit : nullptr, m->d_loss_part,
+                                                         m->d_head_counter, m->d_loss);
+        m->launches++;
+        WD_CUDA(cudaGetLastError());
+        return WD_OK;
+    }
     TowerLogits T{};
     T.n = m->use_deep ? (int)m->towers.size() : 0;
     for (int t = 0; t < T.n; ++t) T.p[t] = m->towers[t].logit;
@@ -615,14 +875,14 @@ int mlp_backward(WdModel* m) {
             const float* src = src_ptr(m, tw, sg.src, false);
             int ld = src_ld(m, tw, sg.src, false);
             dim3 g((sg.width_phys + 63) / 64, rts);
-            logits_wgrad_kernel<<<g, 256, 0, m->stream>>>(B, sg.width_phys, src, ld, m->d_dlogit, m->d_gpart + tk.gpart_off + sg.k_off,
-                                                         tk.gstride, s == 0 ? m->d_gpart + tb.gpart_off : nullptr, tb.gstride);
-            m->launches++;
-            if (sg.src < 0 && !need_dx0) continue;
-            float* dst; int dld, acc;
-            grad_dst(sg.src, &dst, &dld, &acc);
-            logits_dgrad_kernel<<<grid_for((int64_t)B * sg.width_phys / 4, 256), 256, 0, m->stream>>>(
-                B, sg.width_phys, m->d_dlogit, m->d_P + tk.off + sg.k_off, dst, dld, acc);
+            float* dst = nullptr; int dld = 0, acc = 0;
+            if (!(sg.src < 0 && !need_dx0)) grad_dst(sg.src, &dst, &dld, &acc);
+            // (the first segment of the first tower also leaves the wide bias's gradient partials: both are tile sums of dlogit)
+            const bool wb = m->use_wide && s == 0 && &tw == &m->towers.front();
+            logits_bwd_kernel<<<g, 256, 0, m->stream>>>(B, sg.width_phys, src, ld, m->d_dlogit, m->d_P + tk.off + sg.k_off,
+                                                       m->d_gpart + tk.gpart_off + sg.k_off, tk.gstride,
+                                                       s == 0 ? m->d_gpart + tb.gpart_off : nullptr, tb.gstride,
+                                                       wb ? m->d_gpart + m->dense[0].gpart_off : nullptr, wb ? m->dense[0].gstride : 0, dst, dld, acc);
             m->launches++;
         }
         // ---- hidden layers, last to first
@@ -637,6 +897,11 @@ int mlp_backward(WdModel* m) {
                 WD_CUDA(cudaMemsetAsync(L.dH, 0, (size_t)m->max_batch_pad * L.N_phys * sizeof(float), m->stream));
             }
             dim3 g((L.N_phys + 31) / 32, rts);
+            if (q)
+                act_bn_bwd_q_kernel<<<dim3((L.N_phys + 127) / 128, rts), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
+                    L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation, m->batch_norm, pb, pg, pbe,
+                    m->dense[L.t_bias].gstride, L.dZs[0], L.dZs[1]);
+            else
             act_bn_bwd_kernel<<<g, 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                                                        L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
                                                        m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride,
@@ -689,6 +954,15 @@ int mlp_backward(WdModel* m) {
 int dense_reduce_grads(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
     const int rts = (m->dbatch.B + 127) / 128;
+    if (m->gemm_engine == WD_GEMM_BF16X3) {
+        if (m->fuse_dense) return WD_OK;                              // single-GPU step: reduced inside dense_apply's kernel
+        OptParamsD z{};
+        dense_vec_kernel<0><<<grid_for(m->dense_count / 4, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart,
+            m->d_G, nullptr, nullptr, nullptr, nullptr, 0, z, z, -1, rts);
+        m->launches++;
+        WD_CUDA(cudaGetLastError());
+        return WD_OK;
+    }
     dense_reduce_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count,
                                                                              m->d_gpart, m->d_G, rts);
     m->launches++;
@@ -698,9 +972,22 @@ int dense_reduce_grads(WdModel* m) {
 
 int dense_apply(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
-    OptParamsD d{m->dnn_opt.kind, m->dnn_opt.lr, m->dnn_opt.l1, m->dnn_opt.l2};
-    OptParamsD l{m->lin_opt.kind, m->lin_opt.lr, m->lin_opt.l1, m->lin_opt.l2};
+    OptParamsD d = make_opt_d(m->dnn_opt, m->d_bpow + 2);
+    OptParamsD l = make_opt_d(m->lin_opt, m->d_bpow);
     int lin_tensor = m->use_wide ? 0 : -1;                       // tensor 0 is the wide bias when the wide part exists
+    if (m->gemm_engine == WD_GEMM_BF16X3) {
+        const int rts = (m->dbatch.B + 127) / 128;
+        const int g = grid_for(m->dense_count / 4, 256);
+        if (m->fuse_dense)
+            dense_vec_kernel<2><<<g, 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart, m->d_G, m->d_P, m->d_S1,
+                                                          m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts);
+        else
+            dense_vec_kernel<1><<<g, 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart, m->d_G, m->d_P, m->d_S1,
+                                                          m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts);
+        m->launches++;
+        WD_CUDA(cudaGetLastError());
+        return WD_OK;
+    }
     dense_apply_kernel<<<grid_for(m->dense_count, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count, m->d_G,
                                                                             m->d_P, m->d_S1, m->d_S2, m->d_Wt, m->d_Wsplit, m->wt_count, d, l, lin_tensor, m->gemm_engine == WD_GEMM_BF16X3);
     m->launches++;

@@ -686,6 +686,7 @@ int shard_phase2(WdModel* m, bool train) {
     if ((rc = mlp_forward(m, train))) return rc;
     if ((rc = loss_forward(m, train))) return rc;
     if (!train) return WD_OK;
+    if (m->side_pending[0] || m->side_pending[1]) WD_CUDA(cudaEventRecord(m->ev_head, m->stream));   // dlogit exists (as forward_core does)
     return shard_backward_local(m, false);
 }
 // phase 3: owners pull gradients and update their shards; first half of the all-reduce

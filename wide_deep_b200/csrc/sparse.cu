@@ -908,17 +908,59 @@ int small_apply(WdModel* m) {
     return WD_OK;
 }
 
+// ---- sparse Adam (tf.train.AdamOptimizer on IndexedSlices, AdamOptimizer._apply_sparse_shared): m *= beta1, v *= beta2 over the
+// WHOLE variable, scatter-add of the summed gradients (opt_update's Adam branch, touched rows), then every row moves by
+// lr_t * m / (sqrt(v) + eps) with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t).  Record layout [w | m | v]; bpow = {beta1^t, beta2^t}.
+__global__ void __launch_bounds__(256) adam_decay_kernel(float* __restrict__ data, int64_t rows, int dim, int stride, float b1, float b2) {
+    const int64_t total = rows * dim;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float* rec = data + (i / dim) * stride + (i % dim);
+        rec[dim] *= b1;
+        rec[2 * dim] *= b2;
+    }
+}
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ data, int64_t rows, int dim, int stride, float lr, float eps,
+                                                       const float* __restrict__ bpow) {
+    const int64_t total = rows * dim;
+    const float lr_t = lr * sqrtf(1.f - bpow[1]) / (1.f - bpow[0]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float* rec = data + (i / dim) * stride + (i % dim);
+        rec[0] -= lr_t * rec[dim] / (sqrtf(rec[2 * dim]) + eps);
+    }
+}
+static int adam_dense_pass(WdModel* m, int which, bool step) {
+    const WdOptimizer& o = which == 0 ? m->dnn_opt : m->lin_opt;
+    const float* bpow = m->d_bpow + (which == 0 ? 2 : 0);
+    auto run = [&](float* data, int64_t rows, int dim, int stride) {
+        if (rows <= 0) return;
+        if (!step) adam_decay_kernel<<<grid_for(rows * dim, 256), 256, 0, m->stream>>>(data, rows, dim, stride, o.beta1, o.beta2);
+        else adam_step_kernel<<<grid_for(rows * dim, 256), 256, 0, m->stream>>>(data, rows, dim, stride, o.lr, o.epsilon, bpow);
+        m->launches++;
+    };
+    if (which == 0) { for (auto& tb : m->tables) run(tb.data, tb.arows, tb.dim, tb.stride); }
+    else run(reinterpret_cast<float*>(m->d_wide), m->wide_rows, 1, 4);          // wide record {w, m, v, -}
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int sparse_apply_which(WdModel* m, int which) {
+    int rc;
     if (which == 0 && m->use_deep && !m->tables.empty()) {
+        const bool adam = m->dnn_opt.kind == WD_OPT_ADAM;
+        if (adam && (rc = adam_dense_pass(m, 0, false))) return rc;
         emb_apply_kernel<<<grid_for(m->max_nnz * 8, 256), 256, 0, m->stream>>>(
             m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim, m->n_rtab, m->d_rtab_row_base, m->d_rtab_data,
             m->d_rtab_dim, m->d_rtab_stride, make_opt(m->dnn_opt));          // tables in row order (binary search by row)
         m->launches++;
+        if (adam && (rc = adam_dense_pass(m, 0, true))) return rc;
     }
     if (which == 1 && m->use_wide) {
+        const bool adam = m->lin_opt.kind == WD_OPT_ADAM;
+        if (adam && (rc = adam_dense_pass(m, 1, false))) return rc;
         wide_apply_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_urow[1], m->d_ugrad[1], m->d_wide,
                                                                           make_opt(m->lin_opt));
         m->launches++;
+        if (adam && (rc = adam_dense_pass(m, 1, true))) return rc;
     }
     WD_CUDA(cudaGetLastError());
     return WD_OK;

@@ -40,9 +40,19 @@ __device__ __forceinline__ int upper_bound_u32(const uint32_t* __restrict__ a, i
     return lo;
 }
 
-struct OptParams { int kind; float lr, l1, l2, init_acc; };
-inline OptParams make_opt(const WdOptimizer& o) { return OptParams{o.kind, o.lr, o.l1, o.l2, o.init_acc}; }
+struct OptParams { int kind; float lr, l1, l2, init_acc, beta1, beta2, epsilon, rho, momentum; };
+inline OptParams make_opt(const WdOptimizer& o) { return OptParams{o.kind, o.lr, o.l1, o.l2, o.init_acc, o.beta1, o.beta2, o.epsilon, o.rho, o.momentum}; }
+// initial value of optimizer slot 1 (Adagrad accumulator / FTRL n / Adam m / RMSProp rms); slot 2 always starts at 0
+inline float slot1_init(const WdOptimizer& o) {
+    if (o.kind == WD_OPT_ADAGRAD || o.kind == WD_OPT_FTRL) return o.init_acc;
+    return o.kind == WD_OPT_RMSPROP ? 1.f : 0.f;
+}
+inline int opt_nslots(const WdOptimizer& o) { return o.kind == WD_OPT_SGD ? 0 : (o.kind == WD_OPT_ADAGRAD ? 1 : 2); }
 
+// One update of a TOUCHED row element from its summed gradient g (duplicates already summed: "sum duplicates, apply once").
+// Adam is the exception: TensorFlow's sparse Adam decays m and v over the whole variable and moves every row each step
+// (AdamOptimizer._apply_sparse_shared), so here the touched rows only receive the scatter-add of (1 - beta) * g terms; the decay
+// before it and the step after it are dense passes over the table (adam_decay_kernel / adam_step_kernel in sparse.cu).
 __device__ __forceinline__ void opt_update(const OptParams& o, float g, float& w, float& s1, float& s2) {
     if (o.kind == WD_OPT_ADAGRAD) {                 // tf.train.AdagradOptimizer: acc += g^2; w -= lr*g/sqrt(acc)
         s1 += g * g;
@@ -53,6 +63,13 @@ __device__ __forceinline__ void opt_update(const OptParams& o, float g, float& w
         float wn = 0.f;
         if (fabsf(z1) > o.l1) wn = (copysignf(o.l1, z1) - z1) / (sqrtf(n1) / o.lr + 2.f * o.l2);
         w = wn; s1 = n1; s2 = z1;
+    } else if (o.kind == WD_OPT_RMSPROP) {          // SparseApplyRMSProp: ms += (g^2 - ms)(1 - rho); mom = mom * momentum + lr * g * rsqrt(ms + eps)
+        s1 += (g * g - s1) * (1.f - o.rho);
+        s2 = s2 * o.momentum + (g * o.lr) / sqrtf(s1 + o.epsilon);
+        w -= s2;
+    } else if (o.kind == WD_OPT_ADAM) {             // scatter-add stage of sparse Adam
+        s1 += g * (1.f - o.beta1);
+        s2 += g * g * (1.f - o.beta2);
     } else {
         w -= o.lr * g;
     }

@@ -123,6 +123,7 @@ class WideAndDeepClassifier(object):
                 if tuple(z[key].shape) != shape:
                     raise ValueError("checkpoint {}: tensor {} has shape {}, the model expects {}".format(path, key, tuple(z[key].shape), shape))
             m.global_step = int(z["global_step"])
+            m.set_opt_step(m.global_step)
             for key, slot, _ in want:
                 m.set_tensor(key if slot == 0 else key[:key.rindex("/slot")], z[key], slot=slot)
 

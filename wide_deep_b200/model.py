@@ -92,12 +92,16 @@ class WideDeepModel(object):
         check(self._lib.wd_model_init(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
         return self
 
+    def set_opt_step(self, steps):
+        """Restore the optimizers' step count (Adam's beta powers) after loading a checkpoint."""
+        check(self._lib.wd_set_opt_step(self._h, int(steps)))
+
     def tensor_names(self):
         return list(self.plan.tensor_names.keys())
 
     def n_slots(self, name):
         o = self.plan.lin_opt if name.startswith("linear/") else self.plan.dnn_opt
-        return {"sgd": 0, "adagrad": 1, "ftrl": 2}[o["kind"]]
+        return {"sgd": 0, "adagrad": 1, "ftrl": 2, "adam": 2, "rmsprop": 2}[o["kind"]]
 
     def get_tensor(self, name, slot=0):
         """Parameter (slot 0) or optimizer slot by TensorFlow variable name.  Row-sharded tensors: this rank's rows

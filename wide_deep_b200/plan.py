@@ -30,7 +30,7 @@ import numpy as np
 COL_HASH, COL_VOCAB, COL_IDENTITY, COL_BUCKET, COL_CROSS = range(5)
 NORM = {None: 0, "min_max": 1, "standard": 2, "log": 3}
 KEY_FIELD, KEY_COLUMN = 0, 1
-OPT = {"sgd": 0, "adagrad": 1, "ftrl": 2}
+OPT = {"sgd": 0, "adagrad": 1, "ftrl": 2, "adam": 3, "rmsprop": 4}
 ACTS = ["relu", "relu6", "sigmoid", "tanh", "leaky_relu", "elu", "selu", "softplus", "softsign"]
 MODES = ["simple", "first_dense", "last_dense", "dense", "resnet"]
 T_WIDE_COL, T_EMB_TABLE, T_DENSE, T_WIDE_BIAS = range(4)
@@ -48,37 +48,45 @@ def _pad(n, m):
 
 
 def parse_optimizer(spec, default_lr):
-    """'Adagrad' | 'Ftrl' | 'SGD' with the conf learning rate, or a ``tf.train.XOptimizer(...)`` constructor
-    string whose own arguments win (reference model_util.py:62-105 eval()s it; here it is parsed, never
-    evaluated).  Adam / RMSProp touch every row of every table each step and are not offered."""
-    simple = {"Adagrad": "adagrad", "Ftrl": "ftrl", "SGD": "sgd"}
+    """'Adagrad' | 'Adam' | 'Ftrl' | 'RMSProp' | 'SGD' with the conf learning rate — the five names of the reference's factory
+    (reference model_util.py:84-90) — or a ``tf.train.XOptimizer(...)`` constructor string whose own arguments win (the
+    reference eval()s it, model_util.py:95-101; here it is parsed, never evaluated).  TensorFlow's defaults: Adam beta1 0.9 /
+    beta2 0.999 / epsilon 1e-8 / learning_rate 0.001; RMSProp decay 0.9 / momentum 0 / epsilon 1e-10."""
+    simple = {"Adagrad": "adagrad", "Ftrl": "ftrl", "SGD": "sgd", "Adam": "adam", "RMSProp": "rmsprop"}
+    base = dict(l1=0.0, l2=0.0, lr_power=-0.5, init_acc=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8, rho=0.9, momentum=0.0)
     if spec in simple:
-        return dict(kind=simple[spec], lr=float(default_lr), l1=0.0, l2=0.0, lr_power=-0.5, init_acc=0.1)
-    if spec in ("Adam", "RMSProp"):
-        raise ValueError("Unsupported optimizer option: `{}` (dense-state optimizers are out of scope; "
-                         "use Adagrad, Ftrl or SGD)".format(spec))
+        o = dict(base, kind=simple[spec], lr=float(default_lr))
+        if o["kind"] == "rmsprop":
+            o["epsilon"] = 1e-10
+        return o
     m = re.match(r"^\s*tf\.train\.(\w+)Optimizer\((.*)\)\s*$", str(spec))
-    cls = {"Adagrad": "adagrad", "Ftrl": "ftrl", "GradientDescent": "sgd"}.get(m.group(1)) if m else None
+    cls = {"Adagrad": "adagrad", "Ftrl": "ftrl", "GradientDescent": "sgd", "Adam": "adam", "RMSProp": "rmsprop"}.get(m.group(1)) if m else None
     if cls is None:
         raise ValueError("Unsupported optimizer option: `{}`. Supported names are: "
-                         "('Adagrad', 'Ftrl', 'SGD') or a tf.train.{{Adagrad,Ftrl,GradientDescent}}Optimizer(...) "
-                         "expression.".format(spec))
+                         "('Adagrad', 'Adam', 'Ftrl', 'RMSProp', 'SGD') or a tf.train.{{Adagrad,Adam,Ftrl,RMSProp,GradientDescent}}"
+                         "Optimizer(...) expression.".format(spec))
     call = ast.parse("f(" + m.group(2) + ")", mode="eval").body
     kw = {k.arg: ast.literal_eval(k.value) for k in call.keywords}
     if call.args:
         kw.setdefault("learning_rate", ast.literal_eval(call.args[0]))
-    if "learning_rate" not in kw:
+    if "learning_rate" not in kw and cls != "adam":           # (tf.train.AdamOptimizer has a default learning rate, 0.001)
         raise ValueError("learning_rate must be specified in `{}`".format(spec))
-    return dict(kind=cls, lr=float(kw["learning_rate"]),
+    if cls == "rmsprop" and kw.get("centered"):
+        raise ValueError("centered RMSProp is not supported: `{}`".format(spec))
+    return dict(kind=cls, lr=float(kw.get("learning_rate", 0.001)),
                 l1=float(kw.get("l1_regularization_strength", 0.0)),
                 l2=float(kw.get("l2_regularization_strength", 0.0)),
                 lr_power=float(kw.get("learning_rate_power", -0.5)),
-                init_acc=float(kw.get("initial_accumulator_value", 0.1)))
+                init_acc=float(kw.get("initial_accumulator_value", 0.1)),
+                beta1=float(kw.get("beta1", 0.9)), beta2=float(kw.get("beta2", 0.999)),
+                epsilon=float(kw.get("epsilon", 1e-8 if cls == "adam" else 1e-10)),
+                rho=float(kw.get("decay", 0.9)), momentum=float(kw.get("momentum", 0.0)))
 
 
 class _OptC(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("lr", ctypes.c_float), ("l1", ctypes.c_float), ("l2", ctypes.c_float),
-                ("lr_power", ctypes.c_float), ("init_acc", ctypes.c_float)]
+                ("lr_power", ctypes.c_float), ("init_acc", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+                ("epsilon", ctypes.c_float), ("rho", ctypes.c_float), ("momentum", ctypes.c_float)]
 
 
 class PlanDescC(ctypes.Structure):
@@ -321,6 +329,9 @@ class Plan(object):
         self.dnn_opt = parse_optimizer(model_conf.get("dnn_optimizer") or "Adagrad",
                                        model_conf.get("dnn_initial_learning_rate") or 0.001)
 
+        if self.dense_exchange_max_rows > 0 and (self.dnn_opt["kind"] in ("adam", "rmsprop") or self.lin_opt["kind"] in ("adam", "rmsprop")):
+            raise ValueError("Adam / RMSProp are single-GPU only here: the dense gradient block of multi-GPU runs treats rows with a "
+                             "zero summed gradient as untouched, which these optimizers do not (use Adagrad, Ftrl or SGD)")
         if self.dense_exchange_max_rows > 0 and self.dnn_opt["kind"] == "ftrl" and self.tables:
             # a touched embedding row whose summed gradient is exactly 0 still takes an FTRL step (w is rebuilt from z, n), which
             # changes a randomly initialised row; the dense gradient block cannot tell "touched with g = 0" from "untouched"
@@ -489,6 +500,8 @@ class Plan(object):
         for dst, o in ((d.lin_opt, self.lin_opt), (d.dnn_opt, self.dnn_opt)):
             dst.kind, dst.lr, dst.l1, dst.l2 = OPT[o["kind"]], o["lr"], o["l1"], o["l2"]
             dst.lr_power, dst.init_acc = o["lr_power"], o["init_acc"]
+            dst.beta1, dst.beta2, dst.epsilon = o.get("beta1", 0.9), o.get("beta2", 0.999), o.get("epsilon", 1e-8)
+            dst.rho, dst.momentum = o.get("rho", 0.9), o.get("momentum", 0.0)
         d.max_batch, d.max_nnz, d.max_keys, d.gemm_engine = self.max_batch, self.max_nnz, self.max_keys, GEMM[self.gemm_engine]
         d.dense_exchange_max_rows = self.dense_exchange_max_rows
         d.shard_world, d.shard_rank = self.shard_world, self.shard_rank
