@@ -380,7 +380,7 @@ int shard_build(WdModel* m, const WdPlanDesc* d) {
             col_slot[tb.col] = sp.n_slots++;
             base.push_back(rows); dim.push_back(tb.dim); x0.push_back(tb.x0_off); stride.push_back(tb.stride); data.push_back(tb.data);
             tb.row_base = rows;
-            rows += tb.arows;
+            rows += (tb.rows + G - 1) / G;            // the SAME layout on every rank (a requester computes the owner's local row): ceil(rows / G) per table
             sp.width = std::max(sp.width, tb.dim);
         }
         sp.on = sp.n_slots > 0;
@@ -407,7 +407,7 @@ int shard_build(WdModel* m, const WdPlanDesc* d) {
                 if (d->col_wide_sharded[c]) {
                     col_slot[c] = sp.n_slots++;
                     base.push_back(rows);
-                    rows += (d->col_buckets[c] - S.rank + G - 1) / G;
+                    rows += (d->col_buckets[c] + G - 1) / G;     // rank-independent layout: ceil(buckets / G) rows per column
                 }
         sp.h_col_slot = col_slot; sp.h_slot_base = base;
         sp.on = sp.n_slots > 0;
