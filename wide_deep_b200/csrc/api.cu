@@ -452,7 +452,15 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             m->towers.push_back(tw);
         }
     }
-    m->gs_count = m->gs_emb_floats + (m->use_wide ? m->wide_rows - m->small_base[1] : 0);
+    {
+        // block layout: [embedding gradients | wide gradients | touched counts of the small embedding rows | ... of the small wide rows]
+        const int64_t nw_small = m->use_wide ? m->wide_rows - m->small_base[1] : 0;
+        const int64_t ne_small = (m->use_deep && m->n_small_tab > 0) ? m->emb_total_rows - m->small_base[0] : 0;
+        const int64_t grads = m->gs_emb_floats + nw_small;
+        m->gs_touch_off[0] = grads;
+        m->gs_touch_off[1] = grads + ne_small;
+        m->gs_count = grads > 0 ? grads + ne_small + nw_small : 0;
+    }
     if (m->dense_count > 0) {
         if ((rc = dev_alloc(m, &m->d_P, m->dense_count))) return rc;
         if ((rc = dev_alloc(m, &m->d_S1, m->dense_count))) return rc;

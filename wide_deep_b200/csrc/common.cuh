@@ -266,6 +266,7 @@ struct WdModel {
     int64_t dense_exchange_max_rows = 0;
     int64_t small_base[2] = {0, 0};          // first global row of the small embedding tables / small wide columns
     int64_t gs_count = 0, gs_emb_floats = 0; // floats of the small-table gradient block behind d_G[dense_count]; its embedding part
+    int64_t gs_touch_off[2] = {0, 0};        // offsets (floats, inside the block) of the per-row "touched" counts: small embedding rows / small wide rows
     int n_rtab = 0, n_small_tab = 0;         // tables in row order (large first, then small); how many of them are small
     int64_t* d_rtab_row_base = nullptr;      // [n_rtab] row base, ascending
     float** d_rtab_data = nullptr;

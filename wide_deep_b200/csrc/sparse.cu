@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(256) small_scatter_emb_kernel(const int32_t* _
                                                                 const float* __restrict__ ugrad, int width, uint32_t small_base, int ntab,
                                                                 const int64_t* __restrict__ rtab_row_base, const int32_t* __restrict__ rtab_dim,
                                                                 const int64_t* __restrict__ rtab_gs_off, float* __restrict__ Gs,
-                                                                int32_t* __restrict__ d_nubig) {
+                                                                float* __restrict__ touched, int32_t* __restrict__ d_nubig) {
     const int nu = *d_nuniq;
     const int lb = lower_bound_u32(urow, nu, small_base);        // (a concurrently invalidated tail entry still compares >= small_base)
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_nubig = lb;
@@ -821,17 +821,21 @@ __global__ void __launch_bounds__(256) small_scatter_emb_kernel(const int32_t* _
         for (int q = lig; q * 4 < dim; q += 8)
             *reinterpret_cast<float4*>(dst + q * 4) = *reinterpret_cast<const float4*>(ugrad + u * width + q * 4);
         __syncwarp();
-        if (lig == 0) urow[u] = kInvalidRow;
+        if (lig == 0) {
+            touched[row - small_base] = 1.f;                      // "this rank touched the row" (summed over ranks with the block)
+            urow[u] = kInvalidRow;
+        }
     }
 }
 __global__ void __launch_bounds__(256) small_scatter_wide_kernel(const int32_t* __restrict__ d_nuniq, uint32_t* __restrict__ urow,
                                                                  const float* __restrict__ ugrad, uint32_t small_base, float* __restrict__ Gs,
-                                                                 int32_t* __restrict__ d_nubig) {
+                                                                 float* __restrict__ touched, int32_t* __restrict__ d_nubig) {
     const int nu = *d_nuniq;
     const int lb = lower_bound_u32(urow, nu, small_base);
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_nubig = lb;
     for (int64_t u = lb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += (int64_t)gridDim.x * blockDim.x) {
         Gs[urow[u] - small_base] = ugrad[u];
+        touched[urow[u] - small_base] = 1.f;
         urow[u] = kInvalidRow;
     }
 }
@@ -843,11 +847,12 @@ int small_scatter(WdModel* m, int which) {
     if (which == 0) {
         if (m->n_small_tab == 0 || !(m->use_deep && !m->tables.empty())) return WD_OK;
         small_scatter_emb_kernel<<<grid_for(m->max_nnz * 8, 256, 148 * 8), 256, 0, m->stream>>>(m->d_nuniq[0], m->d_urow[0], m->d_ugrad[0], m->emb_max_dim,
-            (uint32_t)m->small_base[0], m->n_rtab, m->d_rtab_row_base, m->d_rtab_dim, m->d_rtab_gs_off, block, m->d_nubig[0]);
+            (uint32_t)m->small_base[0], m->n_rtab, m->d_rtab_row_base, m->d_rtab_dim, m->d_rtab_gs_off, block,
+            block + m->gs_touch_off[0], m->d_nubig[0]);
     } else {
         if (!m->use_wide || m->small_base[1] >= m->wide_rows) return WD_OK;
         small_scatter_wide_kernel<<<grid_for(m->max_nnz, 256, 148 * 8), 256, 0, m->stream>>>(m->d_nuniq[1], m->d_urow[1], m->d_ugrad[1],
-            (uint32_t)m->small_base[1], block + m->gs_emb_floats, m->d_nubig[1]);
+            (uint32_t)m->small_base[1], block + m->gs_emb_floats, block + m->gs_touch_off[1], m->d_nubig[1]);
     }
     copy_count_kernel<<<1, 1, 0, m->stream>>>(m->d_nuniq[which], m->d_nubig[which]);
     m->launches += 2;
@@ -855,18 +860,21 @@ int small_scatter(WdModel* m, int which) {
     return WD_OK;
 }
 
-// optimizer over the dense block: one update per small-table row whose (all-reduced) gradient is not identically zero —
-// untouched rows have an exactly zero gradient and every optimizer here leaves a row unchanged for g = 0
-__global__ void __launch_bounds__(256) small_apply_emb_kernel(const float* __restrict__ Gs, int64_t n4, int ntab, int first_small,
+// optimizer over the dense block: one update per small-table row that ANY rank touched this step.  "Touched" travels with the
+// block as a per-row count (summed by the same all-reduce), not as "gradient != 0": a touched row whose summed gradient is
+// exactly zero (saturated sigmoids give dlogit == 0.0) still takes its optimizer step in TensorFlow — FTRL then rebuilds w from
+// (z, n) and RMSProp decays its mean square.
+__global__ void __launch_bounds__(256) small_apply_emb_kernel(const float* __restrict__ Gs, const float* __restrict__ touched, int64_t n4, int ntab,
+                                                              int first_small, int64_t small_base, const int64_t* __restrict__ rtab_row_base,
                                                               const int64_t* __restrict__ rtab_gs_off, float* const* __restrict__ rtab_data,
                                                               const int32_t* __restrict__ rtab_dim, const int32_t* __restrict__ rtab_stride, OptParams o) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 g = *reinterpret_cast<const float4*>(Gs + i * 4);
-        if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
         int lo = first_small, hi = ntab - 1;                       // small tables are the last entries, offsets ascending
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rtab_gs_off[mid] <= i * 4) lo = mid; else hi = mid - 1; }
         const int dim = rtab_dim[lo], stride = rtab_stride[lo];
         const int64_t local = i * 4 - rtab_gs_off[lo];
+        if (touched[rtab_row_base[lo] - small_base + local / dim] == 0.f) continue;
+        const float4 g = *reinterpret_cast<const float4*>(Gs + i * 4);
         float* rec = rtab_data[lo] + (local / dim) * stride + (local % dim);
         const int nslots = stride / dim - 1;
         float4 w = *reinterpret_cast<float4*>(rec);
@@ -881,10 +889,11 @@ __global__ void __launch_bounds__(256) small_apply_emb_kernel(const float* __res
         if (nslots >= 2) *reinterpret_cast<float4*>(rec + 2 * dim) = s2;
     }
 }
-__global__ void __launch_bounds__(256) small_apply_wide_kernel(const float* __restrict__ Gs, int64_t n, float4* __restrict__ wide, OptParams o) {
+__global__ void __launch_bounds__(256) small_apply_wide_kernel(const float* __restrict__ Gs, const float* __restrict__ touched, int64_t n,
+                                                               float4* __restrict__ wide, OptParams o) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (touched[i] == 0.f) continue;
         const float g = Gs[i];
-        if (g == 0.f) continue;
         float4 r = wide[i];
         opt_update(o, g, r.x, r.y, r.z);
         wide[i] = r;
@@ -894,13 +903,14 @@ int small_apply(WdModel* m) {
     if (m->gs_count == 0) return WD_OK;
     const float* block = m->d_G + m->dense_count;
     if (m->gs_emb_floats > 0) {
-        small_apply_emb_kernel<<<grid_for(m->gs_emb_floats / 4, 256), 256, 0, m->stream>>>(block, m->gs_emb_floats / 4, m->n_rtab, m->n_rtab - m->n_small_tab,
-            m->d_rtab_gs_off, m->d_rtab_data, m->d_rtab_dim, m->d_rtab_stride, make_opt(m->dnn_opt));
+        small_apply_emb_kernel<<<grid_for(m->gs_emb_floats / 4, 256), 256, 0, m->stream>>>(block, block + m->gs_touch_off[0], m->gs_emb_floats / 4, m->n_rtab,
+            m->n_rtab - m->n_small_tab, m->small_base[0], m->d_rtab_row_base, m->d_rtab_gs_off, m->d_rtab_data, m->d_rtab_dim, m->d_rtab_stride,
+            make_opt(m->dnn_opt));
         m->launches++;
     }
     const int64_t nw = m->use_wide ? m->wide_rows - m->small_base[1] : 0;
     if (nw > 0) {
-        small_apply_wide_kernel<<<grid_for(nw, 256), 256, 0, m->stream>>>(block + m->gs_emb_floats, nw,
+        small_apply_wide_kernel<<<grid_for(nw, 256), 256, 0, m->stream>>>(block + m->gs_emb_floats, block + m->gs_touch_off[1], nw,
             reinterpret_cast<float4*>(m->d_wide) + m->small_base[1], make_opt(m->lin_opt));
         m->launches++;
     }

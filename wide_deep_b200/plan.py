@@ -330,14 +330,8 @@ class Plan(object):
                                        model_conf.get("dnn_initial_learning_rate") or 0.001)
 
         if self.dense_exchange_max_rows > 0 and (self.dnn_opt["kind"] in ("adam", "rmsprop") or self.lin_opt["kind"] in ("adam", "rmsprop")):
-            raise ValueError("Adam / RMSProp are single-GPU only here: the dense gradient block of multi-GPU runs treats rows with a "
-                             "zero summed gradient as untouched, which these optimizers do not (use Adagrad, Ftrl or SGD)")
-        if self.dense_exchange_max_rows > 0 and self.dnn_opt["kind"] == "ftrl" and self.tables:
-            # a touched embedding row whose summed gradient is exactly 0 still takes an FTRL step (w is rebuilt from z, n), which
-            # changes a randomly initialised row; the dense gradient block cannot tell "touched with g = 0" from "untouched"
-            raise ValueError("dnn_optimizer Ftrl with embedding tables is not supported together with the dense gradient block of "
-                             "multi-GPU runs (dense_exchange_max_rows / shard_world > 1); use Adagrad or SGD for the deep part")
-
+            raise ValueError("Adam / RMSProp are single-GPU only here (the multi-GPU paths implement Adagrad, Ftrl and SGD: sparse Adam "
+                             "decays its moments over whole tables every step)")
         # ---- tensor names (TensorFlow variable names of the reference's checkpoint)
         T = self.tensor_names = OrderedDict()
         for c in self.wide_columns:
