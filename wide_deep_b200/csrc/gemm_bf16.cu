@@ -339,6 +339,353 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * TBN)));
 }
 
+// ================================================================================================================================
+// CTA-PAIR variant (tcgen05 cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile.  CTA r stages
+// rows [128 r, 128 r + 128) of A and columns [128 r, 128 r + 128) of B; the pair's tensor cores read the two B halves from both
+// shared memories, so each SM reads 4 KB (A) + 4 KB (its B half) per UMMA instead of 4 + 8 KB and fills 64 KB instead of 96 KB per
+// k-block: 160 KB over the 128 B/clk shared-memory port per 1536 tensor clocks (the single-CTA tile needs 240 KB = 1920 clocks), and
+// the freed shared memory holds a third pipeline stage.  One thread of the LEADER CTA (cluster rank 0) issues the UMMAs for both;
+// every TMA load of either CTA signals the leader's `full` barrier; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to
+// both CTAs; the epilogue warps of both CTAs read their own TMEM halves and release the accumulator on the leader's barrier.
+// Every barrier wait carries a watchdog (trap instead of a hung device).
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {       // shared::cluster address of the same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 27)) { printf("libwd_b200: 2-CTA GEMM barrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {          // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+constexpr bool kPairDefault = false; // flipped once the pair kernel is validated and measured faster on B200
+constexpr int P_TBN = 256;           // tile columns of the pair (each CTA stages 128 of them)
+constexpr int P_NST = 3;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
+tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, int M, int N, int ktot, int ksplit_len, int nsplit, Epi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr bool A_MN = MODE == EPI_WGRAD;
+    constexpr bool B_MN = MODE != EPI_STORE;
+    constexpr int A_BYTES = QBM * 128, B_BYTES = (P_TBN / 2) * 128;          // per CTA: 128 rows of A, 128 columns of B, 64 k each
+    constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);                     // 64 KB
+    auto a_hi = [&](int s) { return base + s * STAGE_BYTES; };
+    auto a_lo = [&](int s) { return base + s * STAGE_BYTES + A_BYTES; };
+    auto b_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_BYTES; };
+    auto b_lo = [&](int s) { return base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+    uint8_t* stage_out = base + P_NST * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 16384);
+    uint64_t* full = bars; uint64_t* empty = bars + P_NST;
+    uint64_t* tmem_full = bars + 2 * P_NST; uint64_t* tmem_empty = bars + 2 * P_NST + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_NST + 4);
+    float* epi_params = reinterpret_cast<float*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = (N + P_TBN - 1) / P_TBN, tiles_m = (M + 2 * QBM - 1) / (2 * QBM);
+    const int ntiles = tiles_n * tiles_m * nsplit;
+    int nkb_all = 0;
+    for (int s = 0; s < segs.n; ++s) nkb_all += (segs.k[s] + QBK - 1) / QBK;
+    auto tile_range = [&](int tile, int& m0, int& n0, int& z, int& kbeg, int& nkb) {
+        z = tile / (tiles_n * tiles_m);
+        int r = tile % (tiles_n * tiles_m);
+        m0 = (r / tiles_n) * (2 * QBM) + (int)rank * QBM;         // this CTA's 128 rows
+        n0 = (r % tiles_n) * P_TBN;
+        kbeg = 0;
+        nkb = nkb_all;
+        if (MODE == EPI_WGRAD) {
+            kbeg = z * ksplit_len;
+            int kend = min(ktot, kbeg + ksplit_len);
+            nkb = kend > kbeg ? (kend - kbeg + QBK - 1) / QBK : 0;
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }       // 8 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * P_TBN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                            // both CTAs' barriers exist before anything arrives remotely
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = pair; tile < ntiles; tile += npairs) {
+                int m0, n0, z, kbeg, nkb;
+                tile_range(tile, m0, n0, z, kbeg, nkb);
+                const int nh = n0 + (int)rank * (P_TBN / 2);       // this CTA's half of the B tile
+                int seg = 0, kin = 0;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % P_NST, it = g / P_NST;
+                    if (it > 0) mbar_wait_wd(&empty[s], (it - 1) & 1);
+                    int ka, kbcoord;
+                    if (MODE == EPI_WGRAD) { ka = kbeg + kb * QBK; kbcoord = ka; }
+                    else {
+                        if (kin >= segs.k[seg]) { ++seg; kin = 0; }
+                        ka = kin; kbcoord = segs.koff[seg] + kin;
+                        kin += QBK;
+                    }
+                    const uint32_t lbar = map_to_cta(smem_u32(&full[s]), 0);
+                    if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);             // the bytes of both CTAs land on this barrier
+                    if (!A_MN) {
+                        tma_load_2d_pair(a_hi(s), &maps.a_hi[seg], lbar, ka, m0);
+                        tma_load_2d_pair(a_lo(s), &maps.a_lo[seg], lbar, ka, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < QBM / 64; ++i) {
+                            tma_load_2d_pair(a_hi(s) + i * 8192, &maps.a_hi[seg], lbar, m0 + 64 * i, ka);
+                            tma_load_2d_pair(a_lo(s) + i * 8192, &maps.a_lo[seg], lbar, m0 + 64 * i, ka);
+                        }
+                    }
+                    if (!B_MN) {
+                        tma_load_2d_pair(b_hi(s), &maps.b_hi, lbar, kbcoord, nh);
+                        tma_load_2d_pair(b_lo(s), &maps.b_lo, lbar, kbcoord, nh);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < P_TBN / 128; ++i) {
+                            tma_load_2d_pair(b_hi(s) + i * 8192, &maps.b_hi, lbar, nh + 64 * i, kbcoord);
+                            tma_load_2d_pair(b_lo(s) + i * 8192, &maps.b_lo, lbar, nh + 64 * i, kbcoord);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                       ((uint32_t)(P_TBN >> 3) << 17) | ((uint32_t)((2 * QBM) >> 4) << 24);
+            constexpr uint32_t a_step = A_MN ? 2048u : 32u, b_step = B_MN ? 2048u : 32u;
+            int g = 0, use = 0;
+            for (int tile = pair; tile < ntiles; tile += npairs) {
+                int m0, n0, z, kbeg, nkb;
+                tile_range(tile, m0, n0, z, kbeg, nkb);
+                if (nkb == 0) continue;
+                const int a = use & 1, au = use >> 1;
+                if (au > 0) mbar_wait_wd(&tmem_empty[a], (au - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(a * P_TBN);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % P_NST, it = g / P_NST;
+                    mbar_wait_wd(&full[s], it & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t sa_hi = smem_u32(a_hi(s)), sb_hi = smem_u32(b_hi(s));
+                        const uint32_t sa_lo = smem_u32(a_lo(s)), sb_lo = smem_u32(b_lo(s));
+#pragma unroll
+                        for (int k = 0; k < QBK / 16; ++k) {
+                            const uint64_t da_hi = A_MN ? make_desc_mn(sa_hi + k * a_step) : make_desc(sa_hi + k * a_step);
+                            const uint64_t da_lo = A_MN ? make_desc_mn(sa_lo + k * a_step) : make_desc(sa_lo + k * a_step);
+                            const uint64_t db_hi = B_MN ? make_desc_mn(sb_hi + k * b_step) : make_desc(sb_hi + k * b_step);
+                            const uint64_t db_lo = B_MN ? make_desc_mn(sb_lo + k * b_step) : make_desc(sb_lo + k * b_step);
+                            umma_bf16_pair(tacc, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16_pair(tacc, da_hi, db_lo, idesc, 1u);
+                            umma_bf16_pair(tacc, da_hi, db_hi, idesc, 1u);
+                        }
+                        umma_commit_pair(&empty[s]);
+                        if (kb == nkb - 1) umma_commit_pair(&tmem_full[a]);
+                    }
+                    __syncwarp();
+                }
+                ++use;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: warps 2..9 of both CTAs (own TMEM half)
+        const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+        uint8_t* stg = stage_out + ew * 2048;
+        int use = 0;
+        auto put64 = [&](const uint32_t* x) {
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            __syncwarp();
+        };
+        auto flush64 = [&](uint8_t* __restrict__ dst, int64_t ld_bytes, int mw, bool accumulate) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + (lane >> 2), c = lane & 3;
+                uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                if (mw + r < M) {
+                    uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
+                    if (accumulate) {
+                        const uint4 p = *g;
+                        v4.x = __float_as_uint(__uint_as_float(v4.x) + __uint_as_float(p.x)); v4.y = __float_as_uint(__uint_as_float(v4.y) + __uint_as_float(p.y));
+                        v4.z = __float_as_uint(__uint_as_float(v4.z) + __uint_as_float(p.z)); v4.w = __float_as_uint(__uint_as_float(v4.w) + __uint_as_float(p.w));
+                    }
+                    *g = v4;
+                }
+            }
+        };
+        auto store_f32 = [&](float* __restrict__ dst, int64_t ld, int mw, int nb, const uint32_t* x, bool accumulate) {
+            uint8_t* d = reinterpret_cast<uint8_t*>(dst + (int64_t)mw * ld + nb);
+            put64(x); flush64(d, ld * 4, mw, accumulate);
+            put64(x + 16); flush64(d + 64, ld * 4, mw, accumulate);
+        };
+        const uint32_t lead_empty[2] = {map_to_cta(smem_u32(&tmem_empty[0]), 0), map_to_cta(smem_u32(&tmem_empty[1]), 0)};
+        for (int tile = pair; tile < ntiles; tile += npairs) {
+            int m0, n0, z, kbeg, nkb;
+            tile_range(tile, m0, n0, z, kbeg, nkb);
+            const int mw = m0 + q * 32;
+            const int m = mw + lane;
+            const int a = use & 1, au = use >> 1;
+            const int c_beg = half * (P_TBN / 64), c_end = c_beg + P_TBN / 64;
+            float pb = 0.f, pg = 1.f, pe = 0.f;
+            auto load_params = [&](int nbx, float& b_, float& g_, float& e_) {
+                const int gn = nbx + lane;
+                const bool in = gn < ep.n_logical;
+                b_ = in ? ep.bias[gn] : 0.f;
+                g_ = (in && ep.bn) ? ep.gamma[gn] * 0.99950037468777f : 1.f;
+                e_ = (in && ep.bn) ? ep.beta[gn] : 0.f;
+            };
+            if (MODE == EPI_FWD && n0 + c_beg * 32 < N) load_params(n0 + c_beg * 32, pb, pg, pe);
+            if (nkb > 0) {
+                mbar_wait_wd(&tmem_full[a], au & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+#pragma unroll 1
+            for (int c = c_beg; c < c_end; ++c) {
+                const int nb = n0 + c * 32;
+                if (nb >= N) break;
+                float qb = 0.f, qg = 1.f, qe = 0.f;
+                if (MODE == EPI_FWD && c + 1 < c_end && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
+                uint32_t v[32];
+                if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P_TBN + c * 32), v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (MODE == EPI_FWD) {
+                    float* wp = epi_params + ew * 96;
+                    __syncwarp();
+                    wp[lane] = pb; wp[32 + lane] = pg; wp[64 + lane] = pe;
+                    pb = qb; pg = qg; pe = qe;
+                    __syncwarp();
+                    uint32_t h[32];
+                    const bool rv = m < ep.m_valid;
+                    if (ep.act == WD_ACT_RELU) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(wp + 4 * j4);
+                            const float4 g4 = *reinterpret_cast<const float4*>(wp + 32 + 4 * j4);
+                            const float4 e4 = *reinterpret_cast<const float4*>(wp + 64 + 4 * j4);
+                            const float a0 = fmaxf(__uint_as_float(v[4 * j4]) + b4.x, 0.f), a1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b4.y, 0.f);
+                            const float a2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f), a3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
+                            v[4 * j4] = __float_as_uint(a0); v[4 * j4 + 1] = __float_as_uint(a1); v[4 * j4 + 2] = __float_as_uint(a2); v[4 * j4 + 3] = __float_as_uint(a3);
+                            h[4 * j4] = __float_as_uint(fmaf(a0, g4.x, e4.x)); h[4 * j4 + 1] = __float_as_uint(fmaf(a1, g4.y, e4.y));
+                            h[4 * j4 + 2] = __float_as_uint(fmaf(a2, g4.z, e4.z)); h[4 * j4 + 3] = __float_as_uint(fmaf(a3, g4.w, e4.w));
+                        }
+                        if (nb + 32 > ep.n_logical) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nb + j >= ep.n_logical) { v[j] = 0u; h[j] = 0u; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const bool ok = (nb + j) < ep.n_logical;
+                            const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + wp[j]) : 0.f;
+                            v[j] = __float_as_uint(av);
+                            h[j] = __float_as_uint(ok ? fmaf(av, wp[32 + j], wp[64 + j]) : 0.f);
+                        }
+                    }
+                    if (!rv) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = 0u; h[j] = 0u; }
+                    }
+                    if (ep.A_out != ep.H_out) store_f32(ep.A_out, ep.ldh, mw, nb, v, false);
+                    if (ep.H_out) store_f32(ep.H_out, ep.ldh, mw, nb, h, false);
+                    uint32_t hh[16], hl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x0 = __uint_as_float(h[2 * j]), x1 = __uint_as_float(h[2 * j + 1]);
+                        const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+                        const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xFFFF0000u));
+                        hh[j] = hb;
+                        hl[j] = *reinterpret_cast<const uint32_t*>(&lp);
+                    }
+                    uint8_t* dh = reinterpret_cast<uint8_t*>(ep.Hs_hi + (int64_t)mw * ep.ldh + nb);
+                    uint8_t* dl = reinterpret_cast<uint8_t*>(ep.Hs_lo + (int64_t)mw * ep.ldh + nb);
+                    put64(hh); flush64(dh, (int64_t)ep.ldh * 2, mw, false);
+                    put64(hl); flush64(dl, (int64_t)ep.ldh * 2, mw, false);
+                } else {
+                    store_f32(ep.C + (MODE == EPI_WGRAD ? (int64_t)z * ep.split_stride : 0), ep.ldc, mw, nb, v, MODE == EPI_STORE && ep.accumulate);
+                }
+            }
+            if (nkb > 0) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(lead_empty[a]);          // this warp is done with accumulator buffer a (of its CTA)
+                ++use;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                            // the peer may still be reading this CTA's B half / signalling its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * P_TBN)));
+}
+
+template <int MODE>
+int launch_pair(WdModel* m, const QMaps& maps, const QSegs& segs, int M, int N, int ktot, int splits, int ksplit_len, const Epi& ep) {
+    constexpr int smem = P_NST * 2 * (QBM * 128 + (P_TBN / 2) * 128) + 16384 + 1024 + 128 + 3072;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        WD_CUDA(cudaFuncSetAttribute(tc_gemm_bf16_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        WD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, m->device));
+        configured = true;
+    }
+    const int nsplit = MODE == EPI_WGRAD ? splits : 1;
+    const int ntiles = ((N + P_TBN - 1) / P_TBN) * ((M + 2 * QBM - 1) / (2 * QBM)) * nsplit;
+    const int pairs = std::min(ntiles, num_sms / 2);
+    tc_gemm_bf16_pair_kernel<MODE><<<2 * pairs, Q_THREADS, smem, m->stream>>>(maps, segs, M, N, ktot, ksplit_len, nsplit, ep);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 int g_probe_slot = 0;
 
 template <int TBN, int MODE>
@@ -375,7 +722,9 @@ extern "C" int wd_debug_gemm_probe(unsigned long long* out) {
 // whether the engine uses 128 x 256 output tiles for this problem (also consulted when the split-K factor is chosen)
 bool tc_bf16_wide_tile(int mode, int M, int N, int splits, int num_sms) {
     static const bool no_wide = getenv("WD_TC_N128") != nullptr;
+    static const bool force_wide = getenv("WD_TC_FORCE_WIDE") != nullptr;       // tests: take the 128x256 / pair path whenever N allows
     if (no_wide || N <= 128) return false;
+    if (force_wide) return true;
     // rounds of the persistent grid x cost of one k-block (shared-memory bytes per k-block: 160 KB vs 240 KB)
     const int64_t tm = (M + QBM - 1) / QBM, sp = mode == EPI_WGRAD ? splits : 1;
     const int64_t t128 = tm * ((N + 127) / 128) * sp, t256 = tm * ((N + 255) / 256) * sp;
@@ -408,10 +757,13 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
     }
     for (int s = A.n; s < kMaxSegs; ++s) { maps.a_hi[s] = maps.a_hi[0]; maps.a_lo[s] = maps.a_lo[0]; }
     const bool wide = tc_bf16_wide_tile(mode, M, N, splits, num_sms);
+    // CTA pairs (cta_group::2) for the wide tiles: WD_GEMM_2CTA=0 keeps the single-CTA kernel
+    static const bool pair_on = getenv("WD_GEMM_2CTA") ? atoi(getenv("WD_GEMM_2CTA")) != 0 : kPairDefault;
+    const bool pair = wide && pair_on && M >= 256;
     const int tbn = wide ? 256 : 128;
     if (!b_mn) {
-        if ((rc = tc_make_map_bf16(&maps.b_hi, B_hi, N, ktot, ldb, tbn))) return rc;
-        if ((rc = tc_make_map_bf16(&maps.b_lo, B_lo, N, ktot, ldb, tbn))) return rc;
+        if ((rc = tc_make_map_bf16(&maps.b_hi, B_hi, N, ktot, ldb, pair ? 128 : tbn))) return rc;      // a pair's CTA stages half of the tile's columns
+        if ((rc = tc_make_map_bf16(&maps.b_lo, B_lo, N, ktot, ldb, pair ? 128 : tbn))) return rc;
     } else {
         if ((rc = tc_make_map_bf16(&maps.b_hi, B_hi, ktot, N, ldb, 64))) return rc;
         if ((rc = tc_make_map_bf16(&maps.b_lo, B_lo, ktot, N, ldb, 64))) return rc;
@@ -419,6 +771,7 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
     if (mode == EPI_WGRAD) ksplit_len = (ksplit_len + QBK - 1) / QBK * QBK;
     if (mode == EPI_FWD && (!ep.Hs_hi || !ep.Hs_lo)) { set_error("bf16 GEMM engine: forward without hi/lo outputs"); return WD_EINVAL; }
 #define WD_Q_LAUNCH(MODE_) \
+    if (pair) return launch_pair<MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep); \
     return wide ? launch_q<256, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep) : launch_q<128, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep)
     if (mode == EPI_FWD) { WD_Q_LAUNCH(EPI_FWD); }
     if (mode == EPI_STORE) { WD_Q_LAUNCH(EPI_STORE); }

@@ -132,9 +132,20 @@ __global__ void ids_count_kernel(DevPlan p, DevBatch bt, int32_t* counts) {
     }
 }
 
+// numeric deep columns (X0[b, off] = normalise(dense[b, field])) ride along in the same launch
+struct NumericArgs { int n; const int32_t *field, *kind, *x0_off; const float *a, *bb; };
+
 __global__ void ids_fill_kernel(DevPlan p, DevBatch bt, const int32_t* __restrict__ offs, int64_t cap,
                                 uint32_t* e_wide, uint32_t* e_emb, int32_t* e_bc, int32_t* e_id, float* X0,
-                                int32_t* flags) {
+                                int32_t* flags, NumericArgs num) {
+    if (X0 && num.n > 0) {
+        const int64_t tn = (int64_t)bt.B * num.n;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tn; t += (int64_t)gridDim.x * blockDim.x) {
+            const int b = (int)(t / num.n), i = (int)(t % num.n);
+            const float x = bt.dense[(int64_t)b * p.n_dense_fields + num.field[i]];
+            X0[(int64_t)b * p.d0_phys + num.x0_off[i]] = normalise(num.kind[i], num.a[i], num.bb[i], x);
+        }
+    }
     int64_t total = (int64_t)bt.B * p.n_columns;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int b = (int)(t / p.n_columns), c = (int)(t % p.n_columns);
@@ -218,12 +229,13 @@ int ids_prepare(WdModel* m) {
     int rc = exclusive_scan_i32(m, m->d_col_offs, total, m->d_nnz);
     if (rc) return rc;
     if (total > 0) {
+        NumericArgs num{m->use_deep ? m->n_numeric : 0, m->d_num_field, m->d_num_norm_kind, m->d_num_x0_off, m->d_num_a, m->d_num_b};
         ids_fill_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->dplan, bt, m->d_col_offs, m->max_nnz, m->d_e_wide,
                                                                     m->d_e_emb, m->d_e_bc, m->d_e_id,
-                                                                    m->use_deep ? m->d_X0 : nullptr, m->d_flags);
+                                                                    m->use_deep ? m->d_X0 : nullptr, m->d_flags, num);
         m->launches++;
     }
-    if (m->use_deep && m->n_numeric > 0) {
+    if (m->use_deep && m->n_numeric > 0 && total <= 0) {
         int64_t tn = (int64_t)bt.B * m->n_numeric;
         numeric_kernel<<<grid_for(tn, 256), 256, 0, m->stream>>>(bt, m->n_dense_fields, m->n_numeric, m->d_num_field,
                                                                 m->d_num_norm_kind, m->d_num_a, m->d_num_b,

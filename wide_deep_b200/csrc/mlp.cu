@@ -377,12 +377,19 @@ __global__ void __launch_bounds__(256) logits_head_kernel(HeadIn in, int B, cons
         is_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {                                                    // fixed-order tree over the block partials (<= 512): deterministic
+        __shared__ double dred[256];
         __threadfence();
+        const int nb = (int)gridDim.x;
         double s = 0.0;
-        for (int i = 0; i < (int)gridDim.x; ++i) s += (double)((volatile float*)loss_part)[i];
-        *loss_out = (float)s;
-        *counter = 0;
+        for (int i = threadIdx.x; i < nb; i += 256) s += (double)__ldcg(loss_part + i);
+        dred[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) dred[threadIdx.x] += dred[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { *loss_out = (float)dred[0]; *counter = 0; }
     }
 }
 
@@ -494,12 +501,20 @@ __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_l
 #pragma unroll
     for (int j = 0; j < 4; ++j) gsc[j] = (bn && n0 + j < n_logical) ? gamma[n0 + j] * inv : 1.f;
     if (n0 < N) {
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int mm = rt * 128 + i * 8 + ry;
-            if (mm >= B) break;
-            const float4 dh4 = *reinterpret_cast<const float4*>(dH + (int64_t)mm * ld + n0);
-            const float4 a4 = *reinterpret_cast<const float4*>(Aact + (int64_t)mm * ld + n0);
+      for (int i0 = 0; i0 < 16; i0 += 4) {
+        // the loads of four rows are issued before anything depends on them (rows past the batch re-read the last valid row)
+        float4 dhv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int mr = min(rt * 128 + (i0 + u) * 8 + ry, B - 1);
+            dhv[u] = *reinterpret_cast<const float4*>(dH + (int64_t)mr * ld + n0);
+            av[u] = *reinterpret_cast<const float4*>(Aact + (int64_t)mr * ld + n0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int mm = rt * 128 + (i0 + u) * 8 + ry;
+            if (mm >= B) continue;
+            const float4 dh4 = dhv[u], a4 = av[u];
             const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
             float dz[4];
 #pragma unroll
@@ -520,6 +535,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_l
             *reinterpret_cast<uint2*>(q_hi + (int64_t)mm * ld + n0) = ph;
             *reinterpret_cast<uint2*>(q_lo + (int64_t)mm * ld + n0) = pl;
         }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red[0][ry][cx * 4 + j] = sb[j]; red[1][ry][cx * 4 + j] = sg[j]; red[2][ry][cx * 4 + j] = sbe[j]; }
@@ -673,7 +689,18 @@ __global__ void __launch_bounds__(256) dense_vec_kernel(const DenseTensor* __res
             const int parts = t.g_rowtiles ? live_row_tiles : t.gparts;
             const float* p = gpart + t.gpart_off + e;
             g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < parts; ++q) {
+            int q = 0;
+            for (; q + 4 <= parts; q += 4) {                              // four partials in flight, summed in index order
+                const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)q * t.gstride);
+                const float4 v1 = *reinterpret_cast<const float4*>(p + (int64_t)(q + 1) * t.gstride);
+                const float4 v2 = *reinterpret_cast<const float4*>(p + (int64_t)(q + 2) * t.gstride);
+                const float4 v3 = *reinterpret_cast<const float4*>(p + (int64_t)(q + 3) * t.gstride);
+                g.x += v0.x; g.y += v0.y; g.z += v0.z; g.w += v0.w;
+                g.x += v1.x; g.y += v1.y; g.z += v1.z; g.w += v1.w;
+                g.x += v2.x; g.y += v2.y; g.z += v2.z; g.w += v2.w;
+                g.x += v3.x; g.y += v3.y; g.z += v3.z; g.w += v3.w;
+            }
+            for (; q < parts; ++q) {
                 const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)q * t.gstride);
                 g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
             }
