@@ -704,23 +704,53 @@ int shard_phase4(WdModel* m) {
     return WD_OK;
 }
 
-// The whole step of one rank of a multi-process job (flag barriers between the phases).
-// Buffer hazards across steps need no extra barrier and no double buffering: an inbox is last read in phase 1 (the owner keeps
-// copies of what it needs), and a peer writes it again only in its next phase 0, i.e. after it passed barrier B of this step —
-// which this rank reaches after phase 1.  Receive buffers are rewritten after the next barrier A, gradients / bag scales after
-// the next barrier B, the reduced slices after the next barrier G: each time every reader of the old contents has arrived.
+// run `fn` on the side stream of sparse list `w` (its scratch set), as api.cu does for the replicated lists
+template <typename F>
+static int on_side(WdModel* m, int w, F fn) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->sstream[w]; m->scratch_sel = 1 + w;
+    int rc = fn();
+    m->stream = main_stream; m->scratch_sel = 0;
+    return rc;
+}
+
+// The whole step of one rank of a multi-process job.  Main stream: ids, routing, serve, combine, towers, dense all-reduce and
+// optimizers, with flag barriers A (ids delivered), B (pooled sums delivered), G (gradient arenas final), R (slices reduced) and
+// END.  Side stream of each table space: the owner-side grouping of the received rows (needs only ids: runs beside the towers)
+// and, once every rank's dlogit / dX0 exists (barriers Cw / Ce, on the side streams), the owners' pulled gradient sums and
+// optimizer — hidden behind the remaining weight gradients, the dense all-reduce and the dense optimizer.
+// Buffer hazards: within a step every producer / consumer pair is separated by one of the barriers; the END barrier keeps a fast
+// rank from starting the next step's sends while a slow owner still pulls this step's gradients and bag scales.
 int shard_step_ipc(WdModel* m, bool train) {
+    ShardState& S = m->shard;
     int rc;
     if ((rc = shard_phase0(m, train))) return rc;
     if ((rc = barrier(m, BAR_A))) return rc;
-    if ((rc = shard_phase1(m, train))) return rc;
+    for (int s = 0; s < 2; ++s) if ((rc = shard_serve(m, s))) return rc;
+    if (train) {
+        WD_CUDA(cudaEventRecord(S.ev_a, m->stream));
+        for (int s = 0; s < 2; ++s) {
+            if (!S.sp[s].on) continue;
+            if (m->side_pending[s]) {
+                WD_CUDA(cudaStreamWaitEvent(m->sstream[s], S.ev_a, 0));
+                if ((rc = on_side(m, s, [&] { return shard_owner_group(m, s); }))) return rc;
+            } else if ((rc = shard_owner_group(m, s))) return rc;
+        }
+    }
     if ((rc = barrier(m, BAR_B))) return rc;
-    if ((rc = shard_phase2(m, train))) return rc;
-    if (!train) { m->shard.step++; return WD_OK; }
-    if ((rc = barrier(m, BAR_G))) return rc;                    // every rank's dX0 / dlogit / gradient arena is final
-    if ((rc = shard_phase3(m))) return rc;
+    if ((rc = shard_phase2(m, train))) return rc;               // combine, towers forward (+ backward, replicated lists, dense gradient arena)
+    if (!train) { S.step++; return barrier(m, BAR_END); }
+    for (int s = 1; s >= 0; --s) {
+        if (!S.sp[s].on) continue;
+        auto owner = [&]() -> int { int r = barrier(m, s == 1 ? BAR_CW : BAR_CE); return r ? r : shard_owner_reduce_apply(m, s); };
+        if (m->side_active[s]) { if ((rc = on_side(m, s, owner))) return rc; }
+        else if ((rc = owner())) return rc;
+    }
+    if ((rc = barrier(m, BAR_G))) return rc;                    // every rank's gradient arena (dense + small-table block) is final
+    if ((rc = shard_ar_reduce(m))) return rc;
     if ((rc = barrier(m, BAR_R))) return rc;
-    return shard_phase4(m);
+    if ((rc = shard_phase4(m))) return rc;                      // gather the reduced slices, dense optimizers, join the side streams
+    return barrier(m, BAR_END);
 }
 
 }  // namespace wd
