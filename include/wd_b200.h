@@ -120,6 +120,11 @@ typedef struct WdPlanDesc {
     const uint8_t *col_wide_sharded;    /* [n_columns] */
     int64_t shard_capacity;
     float shard_slack;
+    /* dnn_dropout (reference python/lib/dnn.py:111-112: tf.layers.dropout(rate, training=True) after every hidden layer's
+     * activation, TRAIN mode only).  The keep mask is a counter-based function of (dropout_seed, step, layer, row, column) — see
+     * csrc/gemm.cuh — so runs are reproducible and the oracle can apply the same mask; 0 = no dropout. */
+    float dropout_rate;
+    uint64_t dropout_seed;
 } WdPlanDesc;
 
 /* One batch in HOST memory (pinned for async copies).  Replaces the feature dict produced by input_fn

@@ -103,6 +103,31 @@ def act_bwd(name, z, a):
     raise ValueError(name)
 
 
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x):
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return x ^ (x >> np.uint64(31))
+
+
+def drop_keep(seed, step, layer_id, rows, cols, rate):
+    """Keep mask [rows, cols] (bool) of the dropout after hidden layer `layer_id` (= tower * 64 + layer) in train step `step`:
+    element (m, n) is kept iff u(m, n) >= rate, u = top 24 bits of splitmix64(key ^ (m * 65536 + n)) / 2^24,
+    key = splitmix64(seed ^ step * 0x9E3779B97F4A7C15 ^ layer_id << 48).  (tf.layers.dropout keeps an element iff its uniform
+    draw >= rate and scales the kept ones by 1 / (1 - rate); the draw itself is TensorFlow's stream, replaced by this one.)"""
+    with np.errstate(over="ignore"):
+        key = _splitmix64(np.uint64(seed) ^ ((np.uint64(step) * np.uint64(0x9E3779B97F4A7C15)) & _M64) ^ (np.uint64(layer_id) << np.uint64(48)))
+        m = np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(65536)
+        n = np.arange(cols, dtype=np.uint64)[None, :]
+        r = _splitmix64(key ^ (m + n))
+    u = (r >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return u >= np.float32(rate)
+
+
 def layer_sources(mode, L):
     """Concat order of every hidden layer's input and of the logits layer's input.
     -> list of L+1 lists whose items are 'x' or int j (output of hidden layer j)."""
@@ -153,8 +178,11 @@ class OracleModel(object):
         self.use_deep = model_type != "wide"
         self.act = model_conf.get("dnn_activation_function") or "relu"
         self.bn = bool(model_conf.get("dnn_batch_normalization"))
-        if model_conf.get("dnn_dropout"):
-            raise NotImplementedError("dropout is random in the reference; the oracle covers dnn_dropout: (empty)")
+        # tf.layers.dropout(net, rate, training=True) after every hidden layer's activation, TRAIN mode only (reference dnn.py:
+        # 111-112 and the sibling blocks).  TensorFlow's random stream cannot be reproduced, so the keep mask is DEFINED here by a
+        # counter-based generator (drop_keep) that the CUDA path implements bit for bit: same mask, same scaling by 1 / (1 - rate).
+        self.dropout = float(model_conf.get("dnn_dropout") or 0.0)
+        self.dropout_seed = 0x5EED0006
         hu = model_conf["dnn_hidden_units"]
         self.towers = [list(h) for h in hu] if hu and isinstance(hu[0], (list, tuple)) else [list(hu)]
         cm = model_conf.get("dnn_connected_mode") or "simple"
@@ -249,7 +277,7 @@ class OracleModel(object):
                 out[c.name] = c.ids(batch, tf_compat_pad=self.tf_compat_pad)
         return out
 
-    def forward(self, batch, ids=None):
+    def forward(self, batch, ids=None, train=False):
         A = self.acc
         ids = ids if ids is not None else self.transform(batch)
         B = len(next(iter(ids.values()))[0]) - 1 if ids else len(next(iter(batch.values())))
@@ -280,7 +308,7 @@ class OracleModel(object):
             dl = np.zeros(B, dtype=A)
             cache["towers"] = []
             for t in range(len(self.towers)):
-                tc = self._tower_fwd(t, X)
+                tc = self._tower_fwd(t, X, train)
                 cache["towers"].append(tc)
                 dl += tc["logit"]
             cache["deep_logit"] = dl
@@ -288,10 +316,10 @@ class OracleModel(object):
         cache["logits"] = logits
         return logits.astype(np.float32), cache
 
-    def _tower_fwd(self, t, X):
+    def _tower_fwd(self, t, X, train=False):
         A, hu = self.acc, self.towers[t]
         srcs = layer_sources(self.modes[t], len(hu))
-        H, Z, Aact, INP = [], [], [], []
+        H, Z, Aact, INP, D = [], [], [], [], []
         pick = lambda s: X if s == "x" else H[s]
         inv = 1.0 / np.sqrt(1.0 + BN_EPS)
         for l in range(len(hu)):
@@ -299,17 +327,24 @@ class OracleModel(object):
             inp = np.concatenate([pick(s) for s in srcs[l]], axis=1)
             z = inp @ self.params[scope + "/kernel"].astype(A, copy=False) + self.params[scope + "/bias"].astype(A, copy=False)
             a = act_fwd(self.act, z)
+            D.append(None)
+            if train and self.dropout > 0:
+                D[-1] = drop_keep(self.dropout_seed, self.global_step, t * 64 + l, a.shape[0], a.shape[1], self.dropout).astype(A) \
+                    * A(1.0 / (1.0 - np.float32(self.dropout)))
+                a_in = a * D[-1]
+            else:
+                a_in = a
             if self.bn:   # A.8: always inference mode, moving mean 0 / var 1 (quirk Q4)
-                h = a * (self.params[scope + "/batch_normalization/gamma"].astype(A, copy=False) * inv) \
+                h = a_in * (self.params[scope + "/batch_normalization/gamma"].astype(A, copy=False) * inv) \
                     + self.params[scope + "/batch_normalization/beta"].astype(A, copy=False)
             else:
-                h = a
+                h = a_in
             INP.append(inp); Z.append(z); Aact.append(a); H.append(h)
         scope = "dnn/dnn_%d/logits" % (t + 1)
         inp = np.concatenate([pick(s) for s in srcs[-1]], axis=1)
         logit = (inp @ self.params[scope + "/kernel"].astype(A, copy=False) + self.params[scope + "/bias"].astype(A, copy=False))[:, 0]
         INP.append(inp)
-        return dict(H=H, Z=Z, A=Aact, INP=INP, logit=logit, srcs=srcs)
+        return dict(H=H, Z=Z, A=Aact, INP=INP, D=D, logit=logit, srcs=srcs)
 
     # ---- loss
     @staticmethod
@@ -379,11 +414,14 @@ class OracleModel(object):
             dh = dH[l]
             if self.bn:
                 gam = self.params[scope + "/batch_normalization/gamma"].astype(A, copy=False)
-                grads[scope + "/batch_normalization/gamma"] = (dh * tc["A"][l]).sum(0) * inv
+                a_drop = tc["A"][l] if tc["D"][l] is None else tc["A"][l] * tc["D"][l]
+                grads[scope + "/batch_normalization/gamma"] = (dh * a_drop).sum(0) * inv
                 grads[scope + "/batch_normalization/beta"] = dh.sum(0)
                 da = dh * (gam * inv)
             else:
                 da = dh
+            if tc["D"][l] is not None:
+                da = da * tc["D"][l]                                  # d(dropout) = mask / keep_prob
             dz = da * act_bwd(self.act, tc["Z"][l], tc["A"][l])
             grads[scope + "/kernel"] = tc["INP"][l].T @ dz
             grads[scope + "/bias"] = dz.sum(0)
@@ -447,7 +485,7 @@ class OracleModel(object):
         self.global_step += 1
 
     def train_step(self, batch, labels, weights=None):
-        logits, cache = self.forward(batch)
+        logits, cache = self.forward(batch, train=True)
         loss = self.loss(cache["logits"], labels, weights)
         self.apply(self.backward(cache, labels, weights))
         return loss, logits

@@ -451,3 +451,37 @@ def test_wide_only_hashed_crosses_ftrl():
             exp = om.params[name] if key is None else om.slots[name][key]
             sc = max(float(np.abs(exp).max()), 1e-3)
             assert np.max(np.abs(got - exp)) <= 5e-4 * sc, "%s slot %d: %g (scale %g)" % (name, slot, np.max(np.abs(got - exp)), sc)
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tc3x", "bf16x3"])
+@pytest.mark.parametrize("mode,bn", [("simple", 1), ("dense", 0)])
+def test_dropout_train_parity(engine, mode, bn):
+    """dnn_dropout (reference dnn.py:111-112: tf.layers.dropout after every hidden layer's activation, TRAIN only): the keep mask
+    is the counter-based one both sides define (oracle.model.drop_keep / csrc/gemm.cuh), so losses and trained parameters must
+    agree like without dropout; the mask changes every step (device-side step counter) and evaluation applies no dropout."""
+    fc, cross, model = small_conf(hidden=(128, 64), mode=mode, bn=bn)
+    model["dnn_dropout"] = 0.25
+    B = 256
+    om = OM.OracleModel(fc, cross, model, "wide_deep").init(91)
+    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64, max_keys=B * 64, gemm_engine=engine)
+    pm = WideDeepModel(plan)
+    copy_params_to_product(om, pm)
+    rng = np.random.default_rng(93)
+    tol = 1 if engine != "bf16x3" else 5
+    for step in range(3):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        batch = to_product_batch(plan, raw, label)
+        if step == 1:                                    # evaluation in between: no dropout, and it must not advance the mask counter
+            logits, _ = pm.forward(batch)
+            _, cache = om.forward(raw)
+            np.testing.assert_array_less(np.abs(logits - cache["logits"]), tol * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+        loss = pm.train_step(batch)
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= tol * RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    ptol = 2e-4 if engine != "bf16x3" else 2e-3
+    for name in pm.tensor_names():
+        got, exp = pm.get_tensor(name), om.params[name]
+        scale = max(float(np.abs(exp).max()), 1e-3)
+        bad = np.abs(got - exp) > ptol * scale
+        assert bad.mean() <= (0.0 if engine != "bf16x3" else 2e-2), "%s: %g of the tensor off, max %g (scale %g)" % (name, bad.mean(), np.max(np.abs(got - exp)), scale)

@@ -29,7 +29,7 @@ def conf(mode="simple", act="relu", bn=1, hidden=(16, 8)):
     return fc, cross, model
 
 
-def torch_forward(om, raw, P):
+def torch_forward(om, raw, P, drop_step=None):
     """Re-implementation with torch ops, parameters P (dict name -> torch tensor requiring grad)."""
     ids = om.transform(raw)
     B = len(next(iter(ids.values()))[0]) - 1
@@ -70,6 +70,9 @@ def torch_forward(om, raw, P):
                 sc = "dnn/dnn_%d/hiddenlayer_%d" % (t + 1, l)
                 inp = torch.cat([pick(s) for s in srcs[l]], 1)
                 a = act(inp @ P[sc + "/kernel"] + P[sc + "/bias"])
+                if drop_step is not None and om.dropout > 0:      # tf.layers.dropout, the oracle's counter-based keep mask
+                    keep = OM.drop_keep(om.dropout_seed, drop_step, t * 64 + l, a.shape[0], a.shape[1], om.dropout)
+                    a = a * torch.from_numpy(keep.astype(np.float64) / (1.0 - float(np.float32(om.dropout))))
                 if om.bn:
                     a = a * (P[sc + "/batch_normalization/gamma"] / np.sqrt(1 + 1e-3)) + P[sc + "/batch_normalization/beta"]
                 H.append(a)
@@ -169,3 +172,33 @@ def test_eval_metrics_against_sklearn():
     assert abs(r["accuracy_baseline"] - max(lm, 1 - lm)) < 1e-12
     assert set(r) == {"accuracy", "accuracy_baseline", "auc", "auc_precision_recall", "average_loss", "label/mean", "loss",
                       "precision", "prediction/mean", "recall"}
+
+
+def test_dropout_forward_and_grads_match_torch_autograd():
+    """dnn_dropout: the keep mask comes from oracle.model.drop_keep (counter-based, what the CUDA path reproduces); scaling by
+    1 / (1 - rate), applied after the activation and before batch norm, TRAIN only (reference dnn.py:111-112)."""
+    fc, cross, model = conf("dense", "relu")
+    model["dnn_dropout"] = 0.3
+    rng = np.random.default_rng(8)
+    om = OM.OracleModel(fc, cross, model, "wide_deep").init(4)
+    om.global_step = 5
+    B = 40
+    raw = random_raw_batch(fc, B, rng)
+    label = (rng.random(B) < 0.4).astype(np.float32)
+    P = {k: torch.tensor(v.astype(np.float64), requires_grad=True) for k, v in om.params.items()}
+    logit = torch_forward(om, raw, P, drop_step=5)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, torch.from_numpy(label.astype(np.float64)), reduction="sum")
+    loss.backward()
+    logits, cache = om.forward(raw, train=True)
+    np.testing.assert_allclose(cache["logits"], logit.detach().numpy(), rtol=1e-6, atol=1e-6)
+    ev, _ = om.forward(raw)                                         # eval / predict: no dropout
+    assert np.abs(ev - logits).max() > 1e-3
+    grads = om.backward(cache, label)
+    for name, g in grads.items():
+        ref = P[name].grad.numpy()
+        if isinstance(g, tuple):
+            rows, gr = g
+            dense = np.zeros_like(ref).reshape(ref.shape[0], -1)
+            dense[rows] = np.asarray(gr).reshape(len(rows), -1)
+            g = dense.reshape(ref.shape)
+        np.testing.assert_allclose(np.asarray(g).reshape(ref.shape), ref, rtol=1e-5, atol=1e-7, err_msg=name)

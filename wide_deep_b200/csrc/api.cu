@@ -166,6 +166,8 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     m->n_numeric = d->n_numeric;
     m->d0_phys = d->d0_phys; m->wide_rows = d->wide_rows;
     m->activation = d->activation; m->batch_norm = d->batch_norm;
+    m->dropout_rate = d->dropout_rate; m->dropout_seed = d->dropout_seed;
+    if (!(m->dropout_rate >= 0.f && m->dropout_rate < 1.f)) { set_error("dnn_dropout %g outside [0, 1)", m->dropout_rate); return WD_EINVAL; }
     m->lin_opt = d->lin_opt; m->dnn_opt = d->dnn_opt;
     m->max_batch = d->max_batch; m->max_batch_pad = pad_to(d->max_batch, 128);
     m->ldt = m->max_batch_pad;
@@ -246,6 +248,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if ((rc = dev_alloc(m, &m->d_loss_part, 512))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_head_counter, 4))) return rc;
+    if ((rc = dev_alloc(m, &m->d_step, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_bpow, 4))) return rc;
     {
         const float bp[4] = {m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2};     // beta^1: state before the first step
@@ -428,7 +431,8 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                     }
                     const int64_t n = (int64_t)m->max_batch_pad * L.N_phys;
                     if ((rc = dev_alloc(m, &L.H, n))) return rc;
-                    if (m->batch_norm) { if ((rc = dev_alloc(m, &L.A, n))) return rc; } else L.A = L.H;
+                    // post-activation values are kept apart from the layer output whenever something sits between them (BN affine, dropout)
+                    if (m->batch_norm || m->dropout_rate > 0.f) { if ((rc = dev_alloc(m, &L.A, n))) return rc; } else L.A = L.H;
                     if ((rc = dev_alloc(m, &L.HT, n))) return rc;
                     if ((rc = dev_alloc(m, &L.dH, n))) return rc;
                     if ((rc = dev_alloc(m, &L.dZ, n))) return rc;
@@ -952,6 +956,7 @@ static int apply_core(WdModel* m) {
     if ((rc = dense_apply(m))) return rc;
     if ((rc = small_apply(m))) return rc;
     mark(m, "dense_apply");
+    if (m->dropout_rate > 0.f && (rc = step_tick(m))) return rc;          // the dropout counter advances once per train step
     if (m->lin_opt.kind == WD_OPT_ADAM || m->dnn_opt.kind == WD_OPT_ADAM) {
         // AdamOptimizer._finish: beta powers advance once per step, after every variable of the optimizer has been updated (the
         // sparse lists may still be running on their side streams and read the powers: join them first)

@@ -366,6 +366,9 @@ struct WdModel {
     int64_t eval_batches = 0;
 
     int64_t launches = 0;
+    float dropout_rate = 0.f;               // dnn_dropout: tf.layers.dropout after every hidden layer's activation, train steps only
+    unsigned long long dropout_seed = 0;
+    unsigned int* d_step = nullptr;         // device: train steps completed (dropout counter; advances at the end of every step)
     bool fuse_dense = false;                // whole local step (train_eager): dense gradient reduction fused into the optimizer kernel
     int64_t gemm_fallbacks = 0;            // tensor-core engine GEMMs that ran on the FFMA kernel instead (tests assert 0)
     int cur_slot = 0;
@@ -396,6 +399,7 @@ int dense_reduce_grads(WdModel* m);                              // mlp.cu
 int dense_apply(WdModel* m);                                     // mlp.cu
 int loss_forward(WdModel* m, bool need_grad);                    // mlp.cu: logits = wide + deep, loss, dlogit
 int model_init_params(WdModel* m, uint64_t seed);                // init.cu
+int step_tick(WdModel* m);                                       // misc.cu: train-step counter on the device (dropout)
 int adam_tick(WdModel* m);                                       // misc.cu: beta powers advance (after every optimizer of the step)
 int metrics_accumulate(WdModel* m);                              // metrics.cu
 int metrics_finish(WdModel* m, double* out10);

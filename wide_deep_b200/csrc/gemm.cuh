@@ -61,6 +61,27 @@ struct Epi {
     __nv_bfloat16 *Hs_hi, *Hs_lo;
 };
 
+// ---- dropout (tf.layers.dropout after a hidden layer's activation, TRAIN only; reference dnn.py:111-112).  TensorFlow's random
+// stream cannot be reproduced, so the keep mask is DEFINED by a counter-based generator shared bit for bit with the oracle
+// (oracle/model.py drop_keep): element (m, n) of layer `layer_id` in train step `step` is kept iff
+//   u >= rate,  u = top 24 bits of splitmix64(key ^ (m * 65536 + n)) / 2^24,  key = splitmix64(seed ^ step * GOLDEN ^ layer_id << 48)
+// and kept elements are scaled by 1 / (1 - rate).  Nothing is stored: the backward regenerates the mask.
+struct DropArgs { float rate; unsigned long long seed; const unsigned int* step; int layer_id; };
+__device__ __forceinline__ unsigned long long splitmix64_dev(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long drop_key(const DropArgs& d) {
+    return splitmix64_dev(d.seed ^ ((unsigned long long)(*d.step) * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)d.layer_id << 48));
+}
+__device__ __forceinline__ float drop_mult(unsigned long long key, unsigned int m, unsigned int n, float rate, float inv_keep) {
+    const unsigned long long r = splitmix64_dev(key ^ ((unsigned long long)m * 65536ULL + n));
+    const float u = (float)(unsigned int)(r >> 40) * (1.f / 16777216.f);
+    return u >= rate ? inv_keep : 0.f;
+}
+
 // hi = bf16(x) (round to nearest), lo = bf16(x - hi): x = hi + lo up to 2^-17 relative; the product a*b is rebuilt as
 // a_lo*b_hi + a_hi*b_lo + a_hi*b_hi on the bf16 tensor pipe with fp32 accumulation (dropped term ~2^-18)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {

@@ -174,6 +174,13 @@ __global__ void adam_tick_kernel(float* bpow, float lb1, float lb2, float db1, f
         if (dnn) { bpow[2] *= db1; bpow[3] *= db2; }
     }
 }
+__global__ void step_tick_kernel(unsigned int* step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1u; }
+int step_tick(WdModel* m) {
+    step_tick_kernel<<<1, 32, 0, m->stream>>>(m->d_step);
+    m->launches++;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
 int adam_tick(WdModel* m) {
     adam_tick_kernel<<<1, 32, 0, m->stream>>>(m->d_bpow, m->lin_opt.beta1, m->lin_opt.beta2, m->dnn_opt.beta1, m->dnn_opt.beta2,
                                              m->lin_opt.kind == WD_OPT_ADAM, m->dnn_opt.kind == WD_OPT_ADAM);
@@ -192,6 +199,8 @@ extern "C" int wd_set_opt_step(WdModel* m, int64_t steps) {
     for (int64_t s = 0; s < steps && s < 100000000; ++s)
         for (int i = 0; i < 4; ++i) bp[i] *= b[i];
     WD_CUDA(cudaMemcpyAsync(m->d_bpow, bp, sizeof(bp), cudaMemcpyHostToDevice, m->stream));
+    const unsigned int st = (unsigned int)steps;                   // dropout counter
+    WD_CUDA(cudaMemcpyAsync(m->d_step, &st, sizeof(st), cudaMemcpyHostToDevice, m->stream));
     WD_CUDA(cudaStreamSynchronize(m->stream));
     return WD_OK;
 }

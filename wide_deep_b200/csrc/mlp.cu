@@ -222,6 +222,32 @@ __global__ void x0_split_kernel(const float* __restrict__ in, int64_t n4, __nv_b
     }
 }
 
+// dropout of a hidden layer (rare path, unfused): the forward GEMM's epilogue left the post-activation values A; this kernel
+// rebuilds the layer output from them with the keep mask: H = [BN affine](A * mask / keep) and its bf16 hi / lo or transposed copies
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(int B, int N, int n_logical, const float* __restrict__ A, int ld,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta, int bn,
+                                                         float* __restrict__ H, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo,
+                                                         float* __restrict__ HT, int ldt, DropArgs dr) {
+    const unsigned long long key = drop_key(dr);
+    const float inv_keep = 1.f / (1.f - dr.rate);
+    const int64_t total = (int64_t)B * N;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int mrow = (int)(t / N), n = (int)(t % N);
+        float h = 0.f;
+        if (n < n_logical) {
+            const float a = A[(int64_t)mrow * ld + n] * drop_mult(key, (unsigned)mrow, (unsigned)n, dr.rate, inv_keep);
+            h = bn ? a * (gamma[n] * 0.99950037468777f) + beta[n] : a;
+        }
+        if (H) H[(int64_t)mrow * ld + n] = h;
+        if (q_hi) {
+            __nv_bfloat16 hh, hl;
+            split_bf16(h, hh, hl);
+            q_hi[(int64_t)mrow * ld + n] = hh; q_lo[(int64_t)mrow * ld + n] = hl;
+        }
+        if (HT) HT[(int64_t)n * ldt + mrow] = h;
+    }
+}
+
 // logits layer forward: one warp per example, dot over the concatenated sources
 struct GemvSegs { int n; const float* ptr[kMaxSegs]; int ld[kMaxSegs]; int k[kMaxSegs]; int koff[kMaxSegs]; };
 __global__ void __launch_bounds__(256) logits_fwd_kernel(GemvSegs S, const float* __restrict__ kernel, const float* __restrict__ bias,
@@ -439,8 +465,10 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
                                                         int ld, const float* __restrict__ gamma, int act, int bn,
                                                         float* __restrict__ dZ, float* __restrict__ dZT, int ldt,
                                                         float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
-                                                        int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo) {
+                                                        int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo, DropArgs dr) {
     __shared__ float tile[32][33];
+    const unsigned long long dkey = dr.rate > 0.f ? drop_key(dr) : 0ull;
+    const float inv_keep = dr.rate > 0.f ? 1.f / (1.f - dr.rate) : 1.f;
     __shared__ float red[3][8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
     const int n = blockIdx.x * 32 + tx, rt = blockIdx.y;
@@ -455,8 +483,9 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
             float dz = 0.f;
             if (mm < B && n < n_logical) {
                 float dh = dH[(int64_t)mm * ld + n], a = Aact[(int64_t)mm * ld + n];
-                dz = dh * gsc * act_bwd(act, a);
-                sb += dz; sg += dh * a * inv; sbe += dh;
+                const float dm = dr.rate > 0.f ? drop_mult(dkey, (unsigned)mm, (unsigned)n, dr.rate, inv_keep) : 1.f;
+                dz = dh * gsc * dm * act_bwd(act, a);
+                sb += dz; sg += dh * (a * dm) * inv; sbe += dh;
             }
             if (q_hi) {                                           // 3xBF16 engine: the GEMMs read bf16 hi / lo copies only
                 if (mm < B && n < N) {
@@ -492,8 +521,10 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
 __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_logical, const float* __restrict__ dH, const float* __restrict__ Aact,
                                                           int ld, const float* __restrict__ gamma, int act, int bn,
                                                           float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
-                                                          int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo) {
+                                                          int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo, DropArgs dr) {
     __shared__ float red[3][8][128];
+    const unsigned long long dkey = dr.rate > 0.f ? drop_key(dr) : 0ull;
+    const float inv_keep = dr.rate > 0.f ? 1.f / (1.f - dr.rate) : 1.f;
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int n0 = blockIdx.x * 128 + cx * 4, rt = blockIdx.y;
     const float inv = 0.99950037468777f;
@@ -521,8 +552,9 @@ __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_l
             for (int j = 0; j < 4; ++j) {
                 dz[j] = 0.f;
                 if (n0 + j < n_logical) {
-                    dz[j] = dh[j] * gsc[j] * act_bwd(act, a[j]);
-                    sb[j] += dz[j]; sg[j] += dh[j] * a[j] * inv; sbe[j] += dh[j];
+                    const float dm = dr.rate > 0.f ? drop_mult(dkey, (unsigned)mm, (unsigned)(n0 + j), dr.rate, inv_keep) : 1.f;
+                    dz[j] = dh[j] * gsc[j] * dm * act_bwd(act, a[j]);
+                    sb[j] += dz[j]; sg[j] += dh[j] * (a[j] * dm) * inv; sbe[j] += dh[j];
                 }
             }
             __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
@@ -819,6 +851,12 @@ int mlp_forward(WdModel* m, bool train) {
             int rc = run_gemm(m, EPI_FWD, A, Wt, q ? L.N_phys : L.K_phys, B, L.N_phys, ep, 1, 0, m->d_Wsplit + 2 * m->wt_count + wo,
                               m->d_Wsplit + 3 * m->wt_count + wo, Wq + wo, Wq + m->wt_count + wo);
             if (rc) return rc;
+            if (train && m->dropout_rate > 0.f) {              // tf.layers.dropout(training=True): TRAIN steps only (dnn.py:111-112)
+                const DropArgs dr{m->dropout_rate, m->dropout_seed, m->d_step, (int)(&tw - &m->towers[0]) * 64 + l};
+                dropout_fwd_kernel<<<grid_for((int64_t)B * L.N_phys, 256), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.A, L.N_phys, ep.gamma, ep.beta, m->batch_norm,
+                    (!q || L.h_fp32) ? L.H : nullptr, q ? L.Hs[0] : nullptr, q ? L.Hs[1] : nullptr, ep.HT, m->ldt, dr);
+                m->launches++;
+            }
         }
         Layer& LL = tw.layers[tw.n_hidden];
         GemvSegs S{};
@@ -924,15 +962,16 @@ int mlp_backward(WdModel* m) {
                 WD_CUDA(cudaMemsetAsync(L.dH, 0, (size_t)m->max_batch_pad * L.N_phys * sizeof(float), m->stream));
             }
             dim3 g((L.N_phys + 31) / 32, rts);
+            const DropArgs dr{m->dropout_rate, m->dropout_seed, m->d_step, (int)(&tw - &m->towers[0]) * 64 + l};
             if (q)
                 act_bn_bwd_q_kernel<<<dim3((L.N_phys + 127) / 128, rts), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                     L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation, m->batch_norm, pb, pg, pbe,
-                    m->dense[L.t_bias].gstride, L.dZs[0], L.dZs[1]);
+                    m->dense[L.t_bias].gstride, L.dZs[0], L.dZs[1], dr);
             else
             act_bn_bwd_kernel<<<g, 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                                                        L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
                                                        m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride,
-                                                       q ? L.dZs[0] : nullptr, q ? L.dZs[1] : nullptr);
+                                                       q ? L.dZs[0] : nullptr, q ? L.dZs[1] : nullptr, dr);
             m->launches++;
             // data gradients first: the deep-input gradient dX0 is what the embedding backward waits for, so it is
             // produced before this layer's weight gradients (which then overlap the sparse backward on the side stream)

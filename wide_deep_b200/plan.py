@@ -117,6 +117,7 @@ class PlanDescC(ctypes.Structure):
         ("shard_world", ctypes.c_int32), ("shard_rank", ctypes.c_int32),
         ("table_sharded", _P), ("col_wide_sharded", _P),
         ("shard_capacity", ctypes.c_int64), ("shard_slack", ctypes.c_float),
+        ("dropout_rate", ctypes.c_float), ("dropout_seed", ctypes.c_uint64),
     ]
 
 
@@ -321,8 +322,11 @@ class Plan(object):
             raise ValueError("Unsupported activation name: {}. Supported names are: {}".format(act, tuple(sorted(ACTS))))
         self.activation = act
         self.batch_norm = 1 if model_conf.get("dnn_batch_normalization") else 0
-        if model_conf.get("dnn_dropout"):
-            raise ValueError("dnn_dropout is not supported by the B200 path yet (conf default is empty)")
+        # dnn_dropout: tf.layers.dropout(rate) after every hidden layer's activation in TRAIN mode (reference dnn.py:111-112)
+        self.dropout = float(model_conf.get("dnn_dropout") or 0.0)
+        if not 0.0 <= self.dropout < 1.0:
+            raise ValueError("dnn_dropout must be in [0, 1), found {}".format(self.dropout))
+        self.dropout_seed = 0x5EED0006
         # constant learning rates (quirk Q1: the reference's decay never advances, joint.py:145 vs 227)
         self.lin_opt = parse_optimizer(model_conf.get("linear_optimizer") or "Ftrl",
                                        model_conf.get("linear_initial_learning_rate") or 0.005)
@@ -502,6 +506,7 @@ class Plan(object):
         d.table_sharded = arr([1 if t["sharded"] else 0 for t in self.tables], np.uint8)
         d.col_wide_sharded = arr([1 if x else 0 for x in self.wide_sharded], np.uint8)
         d.shard_capacity, d.shard_slack = self.shard_capacity, self.shard_slack
+        d.dropout_rate, d.dropout_seed = self.dropout, self.dropout_seed
         d.wide_small_base = self.wide_small_base if self.wide_small_base is not None else self.wide_rows
         return d, keep
 
