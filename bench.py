@@ -525,6 +525,35 @@ def main():
         if rank == 0:
             sys.stderr.write("dp phases (ms from step start): %s\n" % json.dumps({k: round(v, 3) for k, v in prof.items()}))
 
+    if trainer and exchange == "sharded" and os.environ.get("WD_SHARD_TRACE"):
+        # flag-barrier timeline of one replayed step per rank (globaltimer, us from that rank's step start): enter / leave of the
+        # barriers A (ids delivered), B (pooled sums delivered), Cw / Ce (dlogit / dX0 exist; side streams), G (gradient arenas
+        # final), R (slices reduced), END; "work" = step start -> last kernel before END
+        import ctypes
+        for i in range(3):
+            step_resident(i)
+        tr = np.zeros(16, dtype=np.uint64)
+        model._lib.wd_debug_shard_trace(model._h, tr.ctypes.data_as(ctypes.c_void_p))
+        t0 = int(tr[14])
+        names = ["A", "B", "Cw", "Ce", "G", "R", "END"]
+        mine = {n: [round((int(tr[2 * k]) - t0) / 1e3, 1), round((int(tr[2 * k + 1]) - t0) / 1e3, 1)] for k, n in enumerate(names)}
+        mine["work_end"] = round((int(tr[15]) - t0) / 1e3, 1)
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        if rank == 0:
+            sys.stderr.write("shard barrier timeline (us, [enter, leave]): %s\n" % json.dumps(allr))
+
+    if not trainer and os.environ.get("WD_STEP_TRACE"):
+        # stream timeline of one replayed step (globaltimer stamps inside the step's CUDA graph; us from the step's start)
+        import ctypes
+        for i in range(3):
+            step_resident(i)
+        tr = np.zeros(16, dtype=np.uint64)
+        model._lib.wd_debug_step_trace(model._h, tr.ctypes.data_as(ctypes.c_void_p))
+        names = ["start", "ids", "gather", "head", "towers_bwd", "main_end", "group_emb_end", "group_wide_end", "reduce_emb_beg",
+                 "reduce_emb_end", "reduce_wide_beg", "reduce_wide_end", "apply_emb_end", "apply_wide_end"]
+        sys.stderr.write("step timeline (us): %s\n" % json.dumps({n: round((int(tr[k]) - int(tr[0])) / 1e3, 1) for k, n in enumerate(names)}))
+
     # per-kernel timings (CUDA events between stages on the model stream), a few profiled steps
     phases = {}
     if not trainer:

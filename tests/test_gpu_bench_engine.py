@@ -120,3 +120,39 @@ def test_bench_shape_50_step_drift_from_init_is_within_the_fp32_envelope():
             engine, worst, worst / max(floor_loss, 1e-12), err, err / max(floor_err, 1e-12)))
         assert worst <= max(1e-4, 10.0 * floor_loss), (engine, worst, floor_loss)
         assert err <= max(5e-4, 10.0 * floor_err), (engine, err, floor_err)
+
+
+def test_bench_shape_parameters_after_two_steps():
+    """Every trained tensor of the bf16x3 engine on the benchmark towers (B = 2048: the CTA-pair kernel with the activation /
+    batch-norm backward fused into the data-gradient epilogues, EPI_DACT) against the oracle: bias / gamma / beta gradients come
+    from the epilogue's column partials, so a wrong partial shows up here at once."""
+    om = _oracle(23, warm=3)
+    pm = _product(om, "bf16x3")
+    for step in range(2):
+        raw, label, b = _batch(step)
+        loss = pm.train_step(b)
+        ref, _ = om.train_step(raw, label)
+        assert abs(loss - ref) <= 1e-4 * max(abs(ref), 1.0), (step, loss, ref)
+    worst = ("", 0.0)
+    for name in pm.tensor_names():
+        got, exp = pm.get_tensor(name), om.params[name]
+        scale = max(float(np.abs(exp).max()), 1e-3)
+        err = float(np.max(np.abs(got - exp))) / scale
+        if err > worst[1]:
+            worst = (name, err)
+        assert err <= 2e-3, "%s: %g of scale %g" % (name, err, scale)
+    print("worst tensor after 2 steps: %s, %.3g of its scale" % worst)
+    assert pm.gemm_fallback_count() == 0
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_pair_kernel_on_a_ragged_batch(fuse):
+    """The CTA-pair kernel forced onto a small ragged problem (B = 700: the last pair's second CTA holds 60 valid rows), with and
+    without the fused activation-backward epilogue: the environment switches are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, WD_TC_FORCE_WIDE="1", WD_FUSE_DACT=fuse)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(os.path.dirname(__file__), "test_gpu_parity.py"),
+                        "-k", "bf16x3 and (wide_tiles or engine_train_parity)"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

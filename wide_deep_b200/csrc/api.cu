@@ -248,6 +248,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if ((rc = dev_alloc(m, &m->d_loss_part, 512))) return rc;
     if ((rc = dev_alloc(m, &m->d_loss, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_head_counter, 4))) return rc;
+    if (getenv("WD_STEP_TRACE") && (rc = dev_alloc(m, &m->d_step_trace, 16))) return rc;
     if ((rc = dev_alloc(m, &m->d_step, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_bpow, 4))) return rc;
     {
@@ -870,13 +871,22 @@ static int on_side(WdModel* m, int which, F fn) {
 }
 
 // launch the id-only grouping of both sparse lists on their side streams (overlaps forward + backward of the towers)
+// WD_STEP_TRACE=1: stamp i of the step timeline on whatever stream is current (captured into the step's graph like any kernel)
+__global__ void step_stamp_kernel(unsigned long long* t) { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); *t = v; }
+enum { ST_START = 0, ST_IDS, ST_GATHER, ST_HEAD, ST_BWD, ST_MAIN_END, ST_G0, ST_G1, ST_R0_BEG, ST_R0_END, ST_R1_BEG, ST_R1_END, ST_A0_END, ST_A1_END };
+static void stamp(WdModel* m, int i) {
+    if (!m->d_step_trace) return;
+    step_stamp_kernel<<<1, 1, 0, m->stream>>>(m->d_step_trace + i);
+    m->launches++;
+}
+
 static int group_async(WdModel* m) {
     if (m->timer.enabled) return WD_OK;                      // profiling: keep everything on one stream (done before the reduce)
     WD_CUDA(cudaEventRecord(m->ev_ids, m->stream));
     for (int w = 0; w < 2; ++w) {
         if (!list_present(m, w)) continue;
         WD_CUDA(cudaStreamWaitEvent(m->sstream[w], m->ev_ids, 0));
-        int rc = on_side(m, w, [&] { return sparse_group_which(m, w); });
+        int rc = on_side(m, w, [&] { int r = sparse_group_which(m, w); stamp(m, ST_G0 + w); return r; });
         if (rc) return rc;
         WD_CUDA(cudaEventRecord(m->ev_grouped[w], m->sstream[w]));
         m->side_pending[w] = true;
@@ -886,14 +896,18 @@ static int group_async(WdModel* m) {
 
 static int forward_core(WdModel* m, bool train) {
     int rc;
+    stamp(m, ST_START);
     if ((rc = ids_prepare(m))) return rc;
     mark(m, "ids");
+    stamp(m, ST_IDS);
     if (train && (rc = group_async(m))) return rc;
     if ((rc = sparse_forward(m))) return rc;
+    stamp(m, ST_GATHER);
     if ((rc = mlp_forward(m, train))) return rc;
     mark(m, "mlp_other");
     if ((rc = loss_forward(m, train))) return rc;
     mark(m, "head");
+    stamp(m, ST_HEAD);
     if (train && (m->side_pending[0] || m->side_pending[1])) WD_CUDA(cudaEventRecord(m->ev_head, m->stream));
     return WD_OK;
 }
@@ -908,7 +922,7 @@ static int backward_core(WdModel* m) {
     if (m->side_pending[1]) {
         if (m->gs_count > 0) { WD_CUDA(cudaEventRecord(m->ev_head, m->stream)); }     // (re-recorded: also orders the memset above)
         WD_CUDA(cudaStreamWaitEvent(m->sstream[1], m->ev_head, 0));
-        if ((rc = on_side(m, 1, [&] { int r = sparse_reduce_wide(m); return r ? r : small_scatter(m, 1); }))) return rc;
+        if ((rc = on_side(m, 1, [&] { stamp(m, ST_R1_BEG); int r = sparse_reduce_wide(m); if (!r) r = small_scatter(m, 1); stamp(m, ST_R1_END); return r; }))) return rc;
         m->side_active[1] = true;
     }
     m->record_dx0 = m->side_pending[0];
@@ -916,9 +930,10 @@ static int backward_core(WdModel* m) {
     if ((rc = mlp_backward(m))) return rc;
     m->record_dx0 = false;
     mark(m, "mlp_other");
+    stamp(m, ST_BWD);
     if (m->side_pending[0] && m->dx0_recorded) {
         WD_CUDA(cudaStreamWaitEvent(m->sstream[0], m->ev_dx0, 0));
-        if ((rc = on_side(m, 0, [&] { int r = sparse_reduce_emb(m); return r ? r : small_scatter(m, 0); }))) return rc;
+        if ((rc = on_side(m, 0, [&] { stamp(m, ST_R0_BEG); int r = sparse_reduce_emb(m); if (!r) r = small_scatter(m, 0); stamp(m, ST_R0_END); return r; }))) return rc;
         m->side_active[0] = true;
     }
     if ((rc = wide_bias_grad(m))) return rc;
@@ -948,7 +963,7 @@ static int apply_core(WdModel* m) {
     int rc;
     for (int w = 0; w < 2; ++w) {
         if (m->side_active[w]) {
-            if ((rc = on_side(m, w, [&] { return sparse_apply_which(m, w); }))) return rc;
+            if ((rc = on_side(m, w, [&] { int r = sparse_apply_which(m, w); stamp(m, ST_A0_END + w); return r; }))) return rc;
             WD_CUDA(cudaEventRecord(m->ev_done[w], m->sstream[w]));
         } else if ((rc = sparse_apply_which(m, w))) return rc;
     }
@@ -956,6 +971,7 @@ static int apply_core(WdModel* m) {
     if ((rc = dense_apply(m))) return rc;
     if ((rc = small_apply(m))) return rc;
     mark(m, "dense_apply");
+    stamp(m, ST_MAIN_END);
     if (m->dropout_rate > 0.f && (rc = step_tick(m))) return rc;          // the dropout counter advances once per train step
     if (m->lin_opt.kind == WD_OPT_ADAM || m->dnn_opt.kind == WD_OPT_ADAM) {
         // AdamOptimizer._finish: beta powers advance once per step, after every variable of the optimizer has been updated (the
@@ -1450,4 +1466,13 @@ extern "C" int wd_sync(WdModel* m) {
     if (rc) return rc;
     WD_CUDA(cudaStreamSynchronize(m->stream));
     return WD_OK;
+}
+
+// debugging aid (not part of the public header): stamps of the last train step's timeline (ns, globaltimer), WD_STEP_TRACE=1:
+// [start, ids, gather, head, towers' backward, main stream end, grouping 0 / 1 end, reduce 0 begin / end, reduce 1 begin / end,
+// apply 0 / 1 end] (0 = embedding rows, 1 = wide rows; side streams)
+extern "C" int wd_debug_step_trace(WdModel* m, unsigned long long* out) {
+    if (!m || !m->d_step_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, m->d_step_trace, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }

@@ -217,6 +217,7 @@ struct ShardState {
     int64_t off_flags = 0, off_gred = 0, off_G = 0;
     uint32_t** d_peer_flags = nullptr;  // [G] device array of peers' flag blocks
     uint32_t* d_epoch = nullptr;        // [kBarriers] local epoch counters
+    unsigned long long* d_trace = nullptr;   // WD_SHARD_TRACE=1: [kBarriers][2] enter / leave stamps of the last step's barriers
     float** d_peer_G = nullptr;         // [G] peers' dense gradient arenas
     float** d_peer_gred = nullptr;      // [G] peers' reduced slices
     float* gred = nullptr;              // this rank's reduced slice buffer (whole-arena sized; only the own slice is written)
@@ -337,6 +338,7 @@ struct WdModel {
     float* d_dlogit = nullptr;               // [max_batch]
     float* d_loss_part = nullptr;            // per-block partials
     float* d_loss = nullptr;                 // scalar
+    unsigned long long* d_step_trace = nullptr;   // WD_STEP_TRACE=1: globaltimer stamps of the last step (wd_debug_step_trace)
     int32_t* d_head_counter = nullptr;       // blocks of the fused head kernel that have finished (last one sums the loss)
     float* d_bpow = nullptr;                 // Adam: {linear beta1^t, linear beta2^t, dnn beta1^t, dnn beta2^t}, multiplied in fp32 after every step (AdamOptimizer._finish)
     float* h_loss_pinned = nullptr;

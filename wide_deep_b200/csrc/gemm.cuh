@@ -47,7 +47,10 @@ struct GemmA {                         // A operand: up to kMaxSegs K-contiguous
     const __nv_bfloat16* hi[kMaxSegs]; // 3xBF16 engine: the same segments pre-split into bf16 hi / lo copies (same ld)
     const __nv_bfloat16* lo[kMaxSegs];
 };
-enum { EPI_FWD = 0, EPI_STORE = 1, EPI_WGRAD = 2 };
+// EPI_DACT (3xBF16 pair kernel only): a data-gradient GEMM whose epilogue is the activation / batch-norm backward of the layer
+// it feeds — dH never reaches memory: dZ = dH * gamma' * act'(A) leaves as bf16 hi / lo copies and the 128-row column partials of
+// the bias / gamma / beta gradients go to the partial arena (what act_bn_bwd_q_kernel does in a separate pass otherwise)
+enum { EPI_FWD = 0, EPI_STORE = 1, EPI_WGRAD = 2, EPI_DACT = 3 };
 struct Epi {
     float* C; int ldc;                 // STORE / WGRAD target
     int accumulate;                    // STORE: C += acc
@@ -59,6 +62,11 @@ struct Epi {
     int64_t split_stride;              // WGRAD: floats between split partials
     // 3xBF16 engine, FWD: the layer output leaves as bf16 hi / lo copies, row-major [M, ldh] (H_out may then be NULL)
     __nv_bfloat16 *Hs_hi, *Hs_lo;
+    // EPI_DACT: stored post-activation values of the fed layer [M, ldh], its partial arenas ([128-row tile][pstride]); dZ hi / lo
+    // copies go to Hs_hi / Hs_lo (row-major [M, ldh]); gamma / act / bn / n_logical as in FWD
+    const float* Aact;
+    float *p_bias, *p_gamma, *p_beta;
+    int64_t pstride;
 };
 
 // ---- dropout (tf.layers.dropout after a hidden layer's activation, TRAIN only; reference dnn.py:111-112).  TensorFlow's random

@@ -385,6 +385,22 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {          // ar
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// Sum of x[j] over the 32 lanes for every j, transposed: lane j returns the sum of column j.  Five exchange rounds that halve
+// the live values (16 + 8 + 4 + 2 + 1 shuffles), fixed order.
+__device__ __forceinline__ float colsum32(float (&x)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = up ? x[i + o] : x[i];
+            const float send = up ? x[i] : x[i + o];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return x[0];
+}
+
 constexpr bool kPairDefault = true;  // validated on B200 (tests green, +7 % on the layer-0 GEMMs); WD_GEMM_2CTA=0 selects the single-CTA kernel
 constexpr int P_TBN = 256;           // tile columns of the pair (each CTA stages 128 of them)
 constexpr int P_NST = 3;
@@ -395,7 +411,7 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr bool A_MN = MODE == EPI_WGRAD;
-    constexpr bool B_MN = MODE != EPI_STORE;
+    constexpr bool B_MN = MODE == EPI_FWD || MODE == EPI_WGRAD;
     constexpr int A_BYTES = QBM * 128, B_BYTES = (P_TBN / 2) * 128;          // per CTA: 128 rows of A, 128 columns of B, 64 k each
     constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);                     // 64 KB
     auto a_hi = [&](int s) { return base + s * STAGE_BYTES; };
@@ -408,6 +424,7 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
     uint64_t* tmem_full = bars + 2 * P_NST; uint64_t* tmem_empty = bars + 2 * P_NST + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_NST + 4);
     float* epi_params = reinterpret_cast<float*>(bars + 16);
+    float* colsum = epi_params + 8 * 96;                           // EPI_DACT: [8 epilogue warps][3 sums][128 columns]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -563,6 +580,29 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
             put64(x); flush64(d, ld * 4, mw, accumulate);
             put64(x + 16); flush64(d + 64, ld * 4, mw, accumulate);
         };
+        // the reverse path (EPI_DACT): rows [mw, mw + 32) x 64 bytes of a row-major matrix, fetched with whole-sector loads (8 rows x
+        // 64 B per instruction), staged, and handed out one row per lane
+        auto fetch64 = [&](const uint8_t* __restrict__ src, int64_t ld_bytes, int mw, uint4 (&r)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = min(mw + i * 8 + (lane >> 2), M - 1);
+                r[i] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(rr - mw) * ld_bytes + (lane & 3) * 16));
+            }
+        };
+        auto take64 = [&](const uint4 (&r)[4], float* x) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + (lane >> 2), c = lane & 3;
+                *reinterpret_cast<uint4*>(stg + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4)) = r[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 t = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4));
+                x[4 * c] = __uint_as_float(t.x); x[4 * c + 1] = __uint_as_float(t.y); x[4 * c + 2] = __uint_as_float(t.z); x[4 * c + 3] = __uint_as_float(t.w);
+            }
+        };
         const uint32_t lead_empty[2] = {map_to_cta(smem_u32(&tmem_empty[0]), 0), map_to_cta(smem_u32(&tmem_empty[1]), 0)};
         for (int tile = pair; tile < ntiles; tile += npairs) {
             int m0, n0, z, kbeg, nkb;
@@ -575,11 +615,11 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
             auto load_params = [&](int nbx, float& b_, float& g_, float& e_) {
                 const int gn = nbx + lane;
                 const bool in = gn < ep.n_logical;
-                b_ = in ? ep.bias[gn] : 0.f;
+                b_ = (in && MODE == EPI_FWD) ? ep.bias[gn] : 0.f;
                 g_ = (in && ep.bn) ? ep.gamma[gn] * 0.99950037468777f : 1.f;
-                e_ = (in && ep.bn) ? ep.beta[gn] : 0.f;
+                e_ = (in && ep.bn && MODE == EPI_FWD) ? ep.beta[gn] : 0.f;
             };
-            if (MODE == EPI_FWD && n0 + c_beg * 32 < N) load_params(n0 + c_beg * 32, pb, pg, pe);
+            if ((MODE == EPI_FWD || MODE == EPI_DACT) && n0 + c_beg * 32 < N) load_params(n0 + c_beg * 32, pb, pg, pe);
             if (nkb > 0) {
                 mbar_wait_wd(&tmem_full[a], au & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -589,7 +629,13 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;
                 float qb = 0.f, qg = 1.f, qe = 0.f;
-                if (MODE == EPI_FWD && c + 1 < c_end && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
+                if ((MODE == EPI_FWD || MODE == EPI_DACT) && c + 1 < c_end && nb + 32 < N) load_params(nb + 32, qb, qg, qe);
+                uint4 ar0[4], ar1[4];                                  // EPI_DACT: the fed layer's activations of this chunk, in flight
+                if (MODE == EPI_DACT) {
+                    const uint8_t* asrc = reinterpret_cast<const uint8_t*>(ep.Aact + (int64_t)mw * ep.ldh + nb);
+                    fetch64(asrc, (int64_t)ep.ldh * 4, mw, ar0);
+                    fetch64(asrc + 64, (int64_t)ep.ldh * 4, mw, ar1);
+                }
                 uint32_t v[32];
                 if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P_TBN + c * 32), v);
                 else {
@@ -649,6 +695,51 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                     uint8_t* dl = reinterpret_cast<uint8_t*>(ep.Hs_lo + (int64_t)mw * ep.ldh + nb);
                     put64(hh); flush64(dh, (int64_t)ep.ldh * 2, mw, false);
                     put64(hl); flush64(dl, (int64_t)ep.ldh * 2, mw, false);
+                } else if (MODE == EPI_DACT) {
+                    // v = dH of the fed layer (row m, columns nb .. nb + 31); never stored
+                    float* wp = epi_params + ew * 96;
+                    __syncwarp();
+                    wp[lane] = pg;                                    // gamma * 1/sqrt(1 + eps) of column nb + lane (1 without batch norm)
+                    pg = qg;
+                    __syncwarp();
+                    const bool rv = m < M;
+                    float av[32], dz[32];
+                    take64(ar0, av);
+                    take64(ar1, av + 16);
+                    const bool relu = ep.act == WD_ACT_RELU;
+                    float te[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool ok = rv && (nb + j) < ep.n_logical;
+                        const float dh = ok ? __uint_as_float(v[j]) : 0.f;
+                        const float aj = ok ? av[j] : 0.f;
+                        dz[j] = relu ? (aj > 0.f ? dh * wp[j] : 0.f) : dh * wp[j] * act_bwd(ep.act, aj);
+                        av[j] = dh * aj * 0.99950037468777f;           // gamma-gradient term
+                        te[j] = dh;                                   // beta-gradient term
+                    }
+                    // column sums over the warp's 32 rows (fixed butterfly order): lane j ends with the sum of column nb + j
+                    float* cs = colsum + ew * 384 + (c - c_beg) * 32 + lane;
+                    if (ep.bn) {
+                        cs[128] = colsum32(av, lane);
+                        cs[256] = colsum32(te, lane);
+                    }
+                    {
+                        uint32_t hh[16], hl[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x0 = dz[2 * j], x1 = dz[2 * j + 1];
+                            const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+                            const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xFFFF0000u));
+                            hh[j] = hb;
+                            hl[j] = *reinterpret_cast<const uint32_t*>(&lp);
+                        }
+                        uint8_t* dh_ = reinterpret_cast<uint8_t*>(ep.Hs_hi + (int64_t)mw * ep.ldh + nb);
+                        uint8_t* dl_ = reinterpret_cast<uint8_t*>(ep.Hs_lo + (int64_t)mw * ep.ldh + nb);
+                        put64(hh); flush64(dh_, (int64_t)ep.ldh * 2, mw, false);
+                        put64(hl); flush64(dl_, (int64_t)ep.ldh * 2, mw, false);
+                    }
+                    cs[0] = colsum32(dz, lane);
                 } else {
                     store_f32(ep.C + (MODE == EPI_WGRAD ? (int64_t)z * ep.split_stride : 0), ep.ldc, mw, nb, v, MODE == EPI_STORE && ep.accumulate);
                 }
@@ -658,6 +749,25 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(lead_empty[a]);          // this warp is done with accumulator buffer a (of its CTA)
                 ++use;
+            }
+            if (MODE == EPI_DACT) {
+                // 128-row partials of this CTA's row tile: the four lane quarters summed in quarter order, one column per thread
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int t = threadIdx.x - 64, hcol = t >> 7, col = t & 127;
+                const int n = n0 + hcol * 128 + col;
+                if (n < N && m0 < M) {
+                    float sb = 0.f, sg = 0.f, se = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const float* src = colsum + (hcol * 4 + ((qq + 2) & 3)) * 384 + col;      // warp 2 + 4 h + i serves quarter (i + 2) & 3
+                        sb += src[0];
+                        if (ep.bn) { sg += src[128]; se += src[256]; }
+                    }
+                    const int64_t o = (int64_t)(m0 / QBM) * ep.pstride + n;
+                    ep.p_bias[o] = sb;
+                    if (ep.bn) { ep.p_gamma[o] = sg; ep.p_beta[o] = se; }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -669,7 +779,7 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
 
 template <int MODE>
 int launch_pair(WdModel* m, const QMaps& maps, const QSegs& segs, int M, int N, int ktot, int splits, int ksplit_len, const Epi& ep) {
-    constexpr int smem = P_NST * 2 * (QBM * 128 + (P_TBN / 2) * 128) + 16384 + 1024 + 128 + 3072;
+    constexpr int smem = P_NST * 2 * (QBM * 128 + (P_TBN / 2) * 128) + 16384 + 1024 + 128 + 3072 + (MODE == EPI_DACT ? 8 * 384 * 4 : 0);
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
@@ -732,6 +842,12 @@ bool tc_bf16_wide_tile(int mode, int M, int N, int splits, int num_sms) {
     return c256 < c128;
 }
 
+// whether this problem runs on the CTA-pair kernel (cta_group::2): WD_GEMM_2CTA=0 keeps the single-CTA kernel everywhere
+bool tc_bf16_uses_pair(int mode, int M, int N, int splits, int num_sms) {
+    static const bool pair_on = getenv("WD_GEMM_2CTA") ? atoi(getenv("WD_GEMM_2CTA")) != 0 : kPairDefault;
+    return pair_on && M >= 256 && tc_bf16_wide_tile(mode == EPI_DACT ? EPI_STORE : mode, M, N, splits, num_sms);
+}
+
 int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, int M, int N,
                  const Epi& ep, int splits, int ksplit_len) {
     if (N % 32 != 0 || A.n > kMaxSegs || !B_hi || !B_lo) { set_error("bf16 GEMM engine: unsupported operands"); return WD_EUNSUPPORTED; }
@@ -741,7 +857,7 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
     QSegs segs{};
     segs.n = A.n;
     int rc, ktot = 0;
-    const bool a_mn = mode == EPI_WGRAD, b_mn = mode != EPI_STORE;
+    const bool a_mn = mode == EPI_WGRAD, b_mn = mode == EPI_FWD || mode == EPI_WGRAD;
     for (int s = 0; s < A.n; ++s) {
         if (!A.hi[s] || !A.lo[s]) { set_error("bf16 GEMM engine: operand without hi/lo copies"); return WD_EINVAL; }
         // K-major: [M rows][k contiguous], box 64 k x 128 rows.  MN-major: [k rows][M contiguous], box 64 columns x 64 k-rows
@@ -757,9 +873,8 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
     }
     for (int s = A.n; s < kMaxSegs; ++s) { maps.a_hi[s] = maps.a_hi[0]; maps.a_lo[s] = maps.a_lo[0]; }
     const bool wide = tc_bf16_wide_tile(mode, M, N, splits, num_sms);
-    // CTA pairs (cta_group::2) for the wide tiles: WD_GEMM_2CTA=0 keeps the single-CTA kernel
-    static const bool pair_on = getenv("WD_GEMM_2CTA") ? atoi(getenv("WD_GEMM_2CTA")) != 0 : kPairDefault;
-    const bool pair = wide && pair_on && M >= 256;
+    const bool pair = tc_bf16_uses_pair(mode, M, N, splits, num_sms);
+    if (mode == EPI_DACT && !pair) { set_error("bf16 GEMM engine: the fused activation-backward epilogue exists only in the pair kernel"); return WD_EUNSUPPORTED; }
     const int tbn = wide ? 256 : 128;
     if (!b_mn) {
         if ((rc = tc_make_map_bf16(&maps.b_hi, B_hi, N, ktot, ldb, pair ? 128 : tbn))) return rc;      // a pair's CTA stages half of the tile's columns
@@ -775,6 +890,7 @@ int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi
     return wide ? launch_q<256, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep) : launch_q<128, MODE_>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep)
     if (mode == EPI_FWD) { WD_Q_LAUNCH(EPI_FWD); }
     if (mode == EPI_STORE) { WD_Q_LAUNCH(EPI_STORE); }
+    if (mode == EPI_DACT) return launch_pair<EPI_DACT>(m, maps, segs, M, N, ktot, splits, ksplit_len, ep);
     WD_Q_LAUNCH(EPI_WGRAD);
 #undef WD_Q_LAUNCH
 }

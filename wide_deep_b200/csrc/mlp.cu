@@ -162,6 +162,7 @@ static void launch_gemm(WdModel* m, int mode, const GemmA& A, const float* B, in
 int tc_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ldb, int M, int N, const Epi& ep, int splits, int ksplit_len,
             const float* B_hi, const float* B_lo);
 // 3xBF16 tcgen05 engine (gemm_bf16.cu): operands are the bf16 hi / lo copies (GemmA::hi/lo, Bq_hi/Bq_lo)
+bool tc_bf16_uses_pair(int mode, int M, int N, int splits, int num_sms);
 int tc_gemm_bf16(WdModel* m, int mode, const GemmA& A, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, int M, int N,
                  const Epi& ep, int splits, int ksplit_len);
 
@@ -175,7 +176,7 @@ static int run_gemm(WdModel* m, int mode, const GemmA& A, const float* B, int ld
     mark(m, "mlp_other");
     if (m->gemm_engine == WD_GEMM_BF16X3) {
         int rc = tc_gemm_bf16(m, mode, A, Bq_hi, Bq_lo, ldb, M, N, ep, splits, ksplit_len);
-        mark(m, kNames[mode]);
+        mark(m, kNames[mode == EPI_DACT ? EPI_STORE : mode]);
         return rc;
     }
     if (m->gemm_engine == WD_GEMM_TC3X || m->gemm_engine == WD_GEMM_TC1X) {
@@ -361,30 +362,47 @@ __global__ void __launch_bounds__(256) logits_head_kernel(HeadIn in, int B, cons
                                                         float* __restrict__ loss_part, int32_t* __restrict__ counter, float* __restrict__ loss_out) {
     __shared__ float red[8];
     __shared__ bool is_last;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // eight lanes per example, four examples per warp: a lane's loads (up to four 16-byte loads per segment round) are all in
+    // flight before the first one is used
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     float lsum = 0.f;
-    for (int b = warp; b < B; b += nw) {
-        float x = wide_logit ? wide_logit[b] : 0.f;
+    for (int b0 = warp * 4; b0 < B; b0 += nw * 4) {
+        const int b = b0 + grp;
+        const bool live = b < B;
+        float x = (live && wide_logit) ? wide_logit[b] : 0.f;
         for (int t = 0; t < in.n; ++t) {
             const GemvSegs& S = in.S[t];
             float acc = 0.f;
-            for (int s = 0; s < S.n; ++s) {
-                const float* row = S.ptr[s] + (int64_t)b * S.ld[s];
-                const float* kw = in.kernel[t] + S.koff[s];
-                for (int k = lane * 4; k < S.k[s]; k += 128) {
-                    float4 xv = *reinterpret_cast<const float4*>(row + k);
-                    float4 w = *reinterpret_cast<const float4*>(kw + k);
-                    acc = fmaf(xv.x, w.x, acc); acc = fmaf(xv.y, w.y, acc); acc = fmaf(xv.z, w.z, acc); acc = fmaf(xv.w, w.w, acc);
+            if (live) {
+                for (int s = 0; s < S.n; ++s) {
+                    const float* row = S.ptr[s] + (int64_t)b * S.ld[s];
+                    const float* kw = in.kernel[t] + S.koff[s];
+                    const int K = S.k[s];
+                    int k = lig * 4;
+                    for (; k + 96 < K; k += 128) {
+                        float4 xv[4], w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { xv[u] = *reinterpret_cast<const float4*>(row + k + 32 * u); w[u] = *reinterpret_cast<const float4*>(kw + k + 32 * u); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            acc = fmaf(xv[u].x, w[u].x, acc); acc = fmaf(xv[u].y, w[u].y, acc); acc = fmaf(xv[u].z, w[u].z, acc); acc = fmaf(xv[u].w, w[u].w, acc);
+                        }
+                    }
+                    for (; k < K; k += 32) {
+                        const float4 xv = *reinterpret_cast<const float4*>(row + k);
+                        const float4 w = *reinterpret_cast<const float4*>(kw + k);
+                        acc = fmaf(xv.x, w.x, acc); acc = fmaf(xv.y, w.y, acc); acc = fmaf(xv.z, w.z, acc); acc = fmaf(xv.w, w.w, acc);
+                    }
                 }
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            for (int d = 4; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
             const float tl = acc + in.bias[t][0];
-            if (lane == 0) in.tower_logit[t][b] = tl;
+            if (lig == 0 && live) in.tower_logit[t][b] = tl;
             x += tl;
         }
-        if (lane == 0) {
+        if (lig == 0 && live) {
             logits[b] = x;
             if (label) {
                 const float y = label[b], w = weight ? weight[b] : 1.f;
@@ -393,6 +411,8 @@ __global__ void __launch_bounds__(256) logits_head_kernel(HeadIn in, int B, cons
             }
         }
     }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);                     // the warp's four examples, fixed order
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
     if (lane == 0) red[threadIdx.x >> 5] = lsum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -896,7 +916,7 @@ int loss_forward(WdModel* m, bool need_grad) {
             in.bias[t] = m->d_P + m->dense[LL.t_bias].off;
             in.tower_logit[t] = tw.logit;
         }
-        const int blocks = grid_for((int64_t)B * 32, 256, 512);          // (loss_part holds 512 block partials)
+        const int blocks = grid_for((int64_t)B * 8, 256, 512);           // eight lanes per example (loss_part holds 512 block partials)
         logits_head_kernel<<<blocks, 256, 0, m->stream>>>(in, B, m->use_wide ? m->d_wide_logit : nullptr, m->batch_has_label ? m->d_label : nullptr,
                                                          m->dbatch.weight, m->d_logits, need_grad ? m->d_dlogit : nullptr, m->d_loss_part,
                                                          m->d_head_counter, m->d_loss);
@@ -925,8 +945,19 @@ int mlp_backward(WdModel* m) {
     const bool need_dx0 = !m->tables.empty();
     const bool q = m->gemm_engine == WD_GEMM_BF16X3;
     const __nv_bfloat16* Wq = reinterpret_cast<const __nv_bfloat16*>(m->d_Wsplit);
+    // 3xBF16 engine: a hidden layer read by exactly one later HIDDEN layer (every layer but the last of `simple` towers) gets its
+    // activation / batch-norm backward inside the epilogue of that consumer's data-gradient GEMM (EPI_DACT): its dH is never
+    // stored and act_bn_bwd_q_kernel is not launched for it.  WD_FUSE_DACT=0 keeps the separate pass.
+    static const bool fuse_dact_on = getenv("WD_FUSE_DACT") ? atoi(getenv("WD_FUSE_DACT")) != 0 : true;
+    static int num_sms = 0;
+    if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, m->device);
     for (auto& tw : m->towers) {
         std::vector<char> written(tw.n_hidden, 0);
+        std::vector<int> readers(tw.n_hidden, 0);
+        std::vector<char> fused(tw.n_hidden, 0);
+        for (int l = 0; l <= tw.n_hidden; ++l)
+            for (int s = 0; s < tw.layers[l].n_in_segs; ++s)
+                if (tw.layers[l].segs[s].src >= 0) readers[tw.layers[l].segs[s].src] += (l == tw.n_hidden ? 2 : 1);   // the logits layer's kernel is not a GEMM
         auto grad_dst = [&](int src, float** p, int* ld, int* acc) {
             if (src < 0) { *p = m->d_dX0; *ld = m->d0_phys; *acc = dx0_written ? 1 : 0; dx0_written = true; }
             else { *p = tw.layers[src].dH; *ld = tw.layers[src].N_phys; *acc = written[src] ? 1 : 0; written[src] = 1; }
@@ -958,12 +989,14 @@ int mlp_backward(WdModel* m) {
             float* pb = m->d_gpart + m->dense[L.t_bias].gpart_off;
             float* pg = L.t_gamma >= 0 ? m->d_gpart + m->dense[L.t_gamma].gpart_off : nullptr;
             float* pbe = L.t_beta >= 0 ? m->d_gpart + m->dense[L.t_beta].gpart_off : nullptr;
-            if (!written[l]) {                                        // layer output unused downstream (cannot happen for valid modes)
+            if (!written[l] && !fused[l]) {                           // layer output unused downstream (cannot happen for valid modes)
                 WD_CUDA(cudaMemsetAsync(L.dH, 0, (size_t)m->max_batch_pad * L.N_phys * sizeof(float), m->stream));
             }
             dim3 g((L.N_phys + 31) / 32, rts);
             const DropArgs dr{m->dropout_rate, m->dropout_seed, m->d_step, (int)(&tw - &m->towers[0]) * 64 + l};
-            if (q)
+            if (fused[l]) {
+                // dZ and the partials of this layer were written by the data-gradient GEMM of the layer above
+            } else if (q)
                 act_bn_bwd_q_kernel<<<dim3((L.N_phys + 127) / 128, rts), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                     L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation, m->batch_norm, pb, pg, pbe,
                     m->dense[L.t_bias].gstride, L.dZs[0], L.dZs[1], dr);
@@ -972,7 +1005,7 @@ int mlp_backward(WdModel* m) {
                                                        L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation,
                                                        m->batch_norm, L.dZ, L.dZT, m->ldt, pb, pg, pbe, m->dense[L.t_bias].gstride,
                                                        q ? L.dZs[0] : nullptr, q ? L.dZs[1] : nullptr, dr);
-            m->launches++;
+            if (!fused[l]) m->launches++;
             // data gradients first: the deep-input gradient dX0 is what the embedding backward waits for, so it is
             // produced before this layer's weight gradients (which then overlap the sparse backward on the side stream)
             for (int s = 0; s < L.n_in_segs; ++s) {
@@ -985,8 +1018,22 @@ int mlp_backward(WdModel* m) {
                 A2.hi[0] = L.dZs[0]; A2.lo[0] = L.dZs[1];
                 Epi e2{};
                 e2.C = dst; e2.ldc = dld; e2.accumulate = acc;
+                int mode2 = EPI_STORE;
+                if (q && fuse_dact_on && sg.src >= 0 && readers[sg.src] == 1 && m->dropout_rate <= 0.f && sg.width_phys == tw.layers[sg.src].N_phys &&
+                    tc_bf16_uses_pair(EPI_DACT, B, sg.width_phys, 1, num_sms)) {
+                    Layer& S = tw.layers[sg.src];
+                    mode2 = EPI_DACT;
+                    fused[sg.src] = 1;
+                    e2.Aact = S.A; e2.ldh = S.N_phys; e2.Hs_hi = S.dZs[0]; e2.Hs_lo = S.dZs[1];
+                    e2.gamma = S.t_gamma >= 0 ? m->d_P + m->dense[S.t_gamma].off : nullptr;
+                    e2.n_logical = S.N; e2.act = m->activation; e2.bn = m->batch_norm;
+                    e2.p_bias = m->d_gpart + m->dense[S.t_bias].gpart_off;
+                    e2.p_gamma = S.t_gamma >= 0 ? m->d_gpart + m->dense[S.t_gamma].gpart_off : nullptr;
+                    e2.p_beta = S.t_beta >= 0 ? m->d_gpart + m->dense[S.t_beta].gpart_off : nullptr;
+                    e2.pstride = m->dense[S.t_bias].gstride;
+                }
                 const int64_t woff = tkn.wt_off + (int64_t)sg.k_off * L.N_phys;
-                int rc = run_gemm(m, EPI_STORE, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
+                int rc = run_gemm(m, mode2, A2, m->d_P + tkn.off + (int64_t)sg.k_off * L.N_phys, L.N_phys, B, sg.width_phys, e2, 1, 0,
                                   m->d_Wsplit + woff, m->d_Wsplit + m->wt_count + woff, Wq + woff, Wq + m->wt_count + woff);
                 if (rc) return rc;
             }

@@ -51,10 +51,11 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // One warp: lane r signals rank r ("rank `me` reached barrier k for the e-th time") and waits for rank r's signal.  The epoch
 // lives in device memory so the kernel can be replayed from a CUDA graph.  A rank that never arrives trips a 20 s timeout that
 // raises an error flag instead of hanging the device.
+// `trace` (optional): [kBarriers][2] globaltimer stamps {barrier entered, barrier left} of the last step (wd_debug_shard_trace).
 __global__ void shard_barrier_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t* __restrict__ my_flags, uint32_t* __restrict__ epoch,
-                                     int k, int G, int me, int32_t* __restrict__ err) {
+                                     int k, int G, int me, int32_t* __restrict__ err, unsigned long long* __restrict__ trace) {
     __shared__ uint32_t e_sh;
-    if (threadIdx.x == 0) { e_sh = epoch[k] + 1u; epoch[k] = e_sh; }
+    if (threadIdx.x == 0) { e_sh = epoch[k] + 1u; epoch[k] = e_sh; if (trace) trace[2 * k] = gtimer_ns(); }
     __syncthreads();
     const uint32_t e = e_sh;
     const int r = threadIdx.x;
@@ -68,7 +69,11 @@ __global__ void shard_barrier_kernel(uint32_t* const* __restrict__ peer_flags, u
         }
     }
     __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0 && trace) trace[2 * k + 1] = gtimer_ns();
 }
+
+__global__ void shard_stamp_kernel(unsigned long long* __restrict__ t) { *t = gtimer_ns(); }
 
 // --------------------------------------------------------------------------------------------- requester: route + send
 // starts[o] = first position of owner o in the owner-sorted key list (keys >= G are "not a sharded column"), o = 0 .. G
@@ -487,6 +492,7 @@ int shard_build(WdModel* m, const WdPlanDesc* d) {
     S.gred = reinterpret_cast<float*>(S.seg + S.off_gred);
     if ((rc = dev_alloc(m, &S.d_peer_flags, kMaxRanks))) return rc;
     if ((rc = dev_alloc(m, &S.d_epoch, kBarriers))) return rc;
+    if (getenv("WD_SHARD_TRACE") && (rc = dev_alloc(m, &S.d_trace, 2 * kBarriers))) return rc;
     if ((rc = dev_alloc(m, &S.d_peer_G, kMaxRanks))) return rc;
     if ((rc = dev_alloc(m, &S.d_peer_gred, kMaxRanks))) return rc;
     WD_CUDA(cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming));
@@ -531,7 +537,7 @@ static int barrier(WdModel* m, int k) {
     ShardState& S = m->shard;
     if (!S.ipc) return WD_OK;                                  // ranks of one process: the caller orders the phases with events
     shard_barrier_kernel<<<1, 32, 0, m->stream>>>(S.d_peer_flags, reinterpret_cast<uint32_t*>(S.seg + S.off_flags), S.d_epoch, k, S.world, S.rank,
-                                                  m->d_flags);
+                                                  m->d_flags, S.d_trace);
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
@@ -724,6 +730,7 @@ static int on_side(WdModel* m, int w, F fn) {
 int shard_step_ipc(WdModel* m, bool train) {
     ShardState& S = m->shard;
     int rc;
+    if (S.d_trace) { shard_stamp_kernel<<<1, 1, 0, m->stream>>>(S.d_trace + 2 * (kBarriers - 1)); m->launches++; }   // step start
     if ((rc = shard_phase0(m, train))) return rc;
     if ((rc = barrier(m, BAR_A))) return rc;
     for (int s = 0; s < 2; ++s) if ((rc = shard_serve(m, s))) return rc;
@@ -750,6 +757,7 @@ int shard_step_ipc(WdModel* m, bool train) {
     if ((rc = shard_ar_reduce(m))) return rc;
     if ((rc = barrier(m, BAR_R))) return rc;
     if ((rc = shard_phase4(m))) return rc;                      // gather the reduced slices, dense optimizers, join the side streams
+    if (S.d_trace) { shard_stamp_kernel<<<1, 1, 0, m->stream>>>(S.d_trace + 2 * (kBarriers - 1) + 1); m->launches++; }   // before END
     return barrier(m, BAR_END);
 }
 
@@ -764,6 +772,13 @@ extern "C" int wd_shard_info(WdModel* m, int32_t* world, int32_t* rank, int64_t*
     if (rank) *rank = m->shard.rank;
     if (seg_bytes) *seg_bytes = m->shard.seg_bytes;
     return WD_OK;
+}
+
+// debugging aid (not part of the public header): enter / leave stamps (ns, globaltimer) of the last step's flag barriers, WD_SHARD_TRACE=1
+extern "C" int wd_debug_shard_trace(WdModel* m, unsigned long long* out) {
+    if (!m || !m->shard.d_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, m->shard.d_trace, sizeof(unsigned long long) * 2 * kBarriers, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 
 extern "C" int wd_shard_ipc_handle(WdModel* m, void* handle_out64) {
