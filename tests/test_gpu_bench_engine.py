@@ -123,9 +123,10 @@ def test_bench_shape_50_step_drift_from_init_is_within_the_fp32_envelope():
 
 
 def test_bench_shape_parameters_after_two_steps():
-    """Every trained tensor of the bf16x3 engine on the benchmark towers (B = 2048: the CTA-pair kernel with the activation /
-    batch-norm backward fused into the data-gradient epilogues, EPI_DACT) against the oracle: bias / gamma / beta gradients come
-    from the epilogue's column partials, so a wrong partial shows up here at once."""
+    """Every trained tensor of the bf16x3 engine on the benchmark towers (B = 2048: the CTA-pair kernel, the fused logits-layer /
+    activation backward and — in the WD_FUSE_DACT=1 subprocess of the next test — the activation / batch-norm backward fused into
+    the data-gradient epilogues) against the oracle: bias / gamma / beta gradients come from column partials, so a wrong partial
+    shows up here at once."""
     om = _oracle(23, warm=3)
     pm = _product(om, "bf16x3")
     for step in range(2):
@@ -152,7 +153,13 @@ def test_pair_kernel_on_a_ragged_batch(fuse):
     import os
     import subprocess
     import sys
+    here = os.path.dirname(__file__)
     env = dict(os.environ, WD_TC_FORCE_WIDE="1", WD_FUSE_DACT=fuse)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(os.path.dirname(__file__), "test_gpu_parity.py"),
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_gpu_parity.py"),
                         "-k", "bf16x3 and (wide_tiles or engine_train_parity)"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    if fuse == "1":                                      # and the benchmark towers with the fused epilogue (opt-in)
+        env = dict(os.environ, WD_FUSE_DACT="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_gpu_bench_engine.py"),
+                            "-k", "parameters_after_two_steps or logits_at_the_bar"], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

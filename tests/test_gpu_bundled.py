@@ -138,3 +138,25 @@ def test_device_fingerprint64_bit_exact(native_lib):
     out = np.zeros(len(strs), dtype=np.uint64)
     assert native_lib.wd_fingerprint64_device(buf.ctypes.data, offs.ctypes.data, len(strs), out.ctypes.data) == 0
     assert [int(v) for v in out] == [int(v["hash"]) for v in kat]
+
+
+def test_checkpoint_cadence_by_steps(tmp_path):
+    """RunConfig's save_checkpoints_steps (reference conf/train.yaml:80-98): a checkpoint every N global steps during train() plus
+    the final one; keep_checkpoint_max bounds what stays on disk; giving both cadences is the same error TensorFlow raises."""
+    from wide_deep_b200.config import Config
+    from wide_deep_b200.dataset import input_fn
+    from wide_deep_b200.estimator import build_custom_estimator
+    cfg = Config()
+    run = cfg.runconfig                                  # (cached dict of this Config instance)
+    run["save_checkpoints_steps"], run["save_checkpoints_secs"], run["keep_checkpoint_max"] = 20, None, 3
+    data = os.path.join(ROOT, "data", "eval", "eval1")   # 5000 rows -> 79 batches of 64
+    est = build_custom_estimator(str(tmp_path / "m"), "wide_deep", config=cfg, max_batch=64)
+    est.train(input_fn=lambda: input_fn(data, None, "train", 64, config=cfg, plan=est.plan))
+    have = sorted(int(f[len("model.ckpt-"):-4]) for f in os.listdir(str(tmp_path / "m")) if f.endswith(".npz"))
+    assert have == [40, 60, 79], have                    # 20 was rotated out by keep_checkpoint_max = 3
+    est2 = build_custom_estimator(str(tmp_path / "m"), "wide_deep", config=cfg, max_batch=64)
+    assert est2._ensure_model().global_step == 79
+    run["save_checkpoints_secs"] = 5
+    est3 = build_custom_estimator(str(tmp_path / "m3"), "wide_deep", config=cfg, max_batch=64)
+    with pytest.raises(ValueError):
+        est3.train(input_fn=lambda: input_fn(data, None, "train", 64, config=cfg, plan=est3.plan))

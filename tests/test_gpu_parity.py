@@ -107,6 +107,26 @@ def test_forward_logits(mode, model_type):
             np.testing.assert_allclose(X[:, po:po + w], cache["X"][:, lo:lo + w], rtol=1e-5, atol=1e-6, err_msg=name)
 
 
+def test_log_normaliser():
+    """`transform: log` of a continuous feature (reference build_estimator.py:67-68: tf.log(x), natural log, fp32): the deep
+    input column and — through its bucketized twin in the wide part — the logits, against the oracle on positive inputs."""
+    fc, cross, model = small_conf(hidden=(64, 32))
+    fc["x4"] = dict(type="continuous", transform="log", parameter=dict(normalization=[0, 1], boundaries=[0.5, 1.0, 2.0, 3.0, 4.0, 5.0]))   # (the reference needs a list here too: tuple(normalization), build_estimator.py:126)
+    rng = np.random.default_rng(5)
+    B = 128
+    om, plan, pm = build_pair(fc, cross, model, "wide_deep", B=B, seed=9)
+    for c in om.wide_cols:
+        om.params[om.wname(c)][:] = rng.standard_normal(c.num_buckets).astype(np.float32) * 0.1
+    copy_params_to_product(om, pm)
+    raw = random_raw_batch(fc, B, rng)
+    raw["x4"] = np.exp(rng.uniform(-1.0, 6.0, size=B)).astype(np.float32)           # positive, three decades
+    logits, _ = pm.forward(to_product_batch(plan, raw, (rng.random(B) < 0.3).astype(np.float32)))
+    _, cache = om.forward(raw)
+    np.testing.assert_array_less(np.abs(logits - cache["logits"]), RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+    lo, po, w = plan.deep_layout["x4"]
+    np.testing.assert_allclose(pm.deep_input(B)[:, po:po + w], cache["X"][:, lo:lo + w], rtol=2e-6, atol=1e-6)   # logf vs np.log: <= 2 ulp
+
+
 @pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", "elu", "selu", "softplus", "softsign", "leaky_relu", "relu6"])
 def test_activations_train(act):
     fc, cross, model = small_conf(hidden=(32, 32), act=act)

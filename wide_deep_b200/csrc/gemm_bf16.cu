@@ -38,6 +38,24 @@ int tc_make_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 
 namespace {
 
+// explicit shared-window accesses: the staging tiles are carved out of the dynamic shared memory through integer arithmetic, so
+// the compiler cannot prove the address space and would emit generic LD / ST (long-scoreboard, slower) for them
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+
 constexpr int QBM = 128;         // UMMA M
 constexpr int QBK = 64;          // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int Q_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -201,13 +219,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
         // fire-and-forget.  (A TMA-store epilogue was measured no faster; the epilogue is bound by its instruction count, hence
         // eight warps, packed bf16 conversions and a predicate-free relu path.)
         const int ew = warp - 2, q = warp & 3, half = ew >> 2;
-        uint8_t* stg = stage_out + ew * 2048;
+        const uint32_t stg_s = smem_u32(stage_out + ew * 2048);
         int use = 0;
         auto put64 = [&](const uint32_t* x) {                         // 16 words per lane -> [32 rows][64 B], 64-byte swizzle
             __syncwarp();                                             // earlier readers of the staging tile are done
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                sts128(stg_s + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
             __syncwarp();
         };
         // rows [mw, mw + 32) of a row-major matrix, 64 bytes per row starting at dst (byte pointer of row mw); accumulate: fp32 +=
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = i * 8 + (lane >> 2), c = lane & 3;
-                uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                uint4 v4 = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
                 if (mw + r < M) {
                     uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
                     if (accumulate) {
@@ -268,9 +286,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
                 if (MODE == EPI_FWD) {
-                    float* wp = epi_params + ew * 96;
+                    const uint32_t wp = smem_u32(epi_params + ew * 96);
                     __syncwarp();
-                    wp[lane] = pb; wp[32 + lane] = pg; wp[64 + lane] = pe;
+                    sts32f(wp + 4 * lane, pb); sts32f(wp + 4 * (32 + lane), pg); sts32f(wp + 4 * (64 + lane), pe);
                     pb = qb; pg = qg; pe = qe;
                     __syncwarp();
                     uint32_t h[32];
@@ -280,9 +298,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
                         // shift 0, and relu(0) = 0 keeps them zero
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(wp + 4 * j4);
-                            const float4 g4 = *reinterpret_cast<const float4*>(wp + 32 + 4 * j4);
-                            const float4 e4 = *reinterpret_cast<const float4*>(wp + 64 + 4 * j4);
+                            const float4 b4 = lds128f(wp + 16 * j4);
+                            const float4 g4 = lds128f(wp + 128 + 16 * j4);
+                            const float4 e4 = lds128f(wp + 256 + 16 * j4);
                             const float a0 = fmaxf(__uint_as_float(v[4 * j4]) + b4.x, 0.f), a1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b4.y, 0.f);
                             const float a2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f), a3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
                             v[4 * j4] = __float_as_uint(a0); v[4 * j4 + 1] = __float_as_uint(a1); v[4 * j4 + 2] = __float_as_uint(a2); v[4 * j4 + 3] = __float_as_uint(a3);
@@ -297,9 +315,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const bool ok = (nb + j) < ep.n_logical;
-                            const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + wp[j]) : 0.f;
+                            const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + lds32f(wp + 4 * j)) : 0.f;
                             v[j] = __float_as_uint(av);
-                            h[j] = __float_as_uint(ok ? fmaf(av, wp[32 + j], wp[64 + j]) : 0.f);
+                            h[j] = __float_as_uint(ok ? fmaf(av, lds32f(wp + 4 * (32 + j)), lds32f(wp + 4 * (64 + j))) : 0.f);
                         }
                     }
                     if (!rv) {                                        // rows past the batch: zeros (only in the last row tile)
@@ -550,20 +568,20 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
     } else {
         // ------------------------------------------------------------------ epilogue: warps 2..9 of both CTAs (own TMEM half)
         const int ew = warp - 2, q = warp & 3, half = ew >> 2;
-        uint8_t* stg = stage_out + ew * 2048;
+        const uint32_t stg_s = smem_u32(stage_out + ew * 2048);
         int use = 0;
         auto put64 = [&](const uint32_t* x) {
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                sts128(stg_s + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
             __syncwarp();
         };
         auto flush64 = [&](uint8_t* __restrict__ dst, int64_t ld_bytes, int mw, bool accumulate) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = i * 8 + (lane >> 2), c = lane & 3;
-                uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+                uint4 v4 = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
                 if (mw + r < M) {
                     uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
                     if (accumulate) {
@@ -594,12 +612,12 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int rr = i * 8 + (lane >> 2), c = lane & 3;
-                *reinterpret_cast<uint4*>(stg + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4)) = r[i];
+                sts128(stg_s + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4), r[i].x, r[i].y, r[i].z, r[i].w);
             }
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const uint4 t = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4));
+                const uint4 t = lds128(stg_s + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4));
                 x[4 * c] = __uint_as_float(t.x); x[4 * c + 1] = __uint_as_float(t.y); x[4 * c + 2] = __uint_as_float(t.z); x[4 * c + 3] = __uint_as_float(t.w);
             }
         };
@@ -643,9 +661,9 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
                 if (MODE == EPI_FWD) {
-                    float* wp = epi_params + ew * 96;
+                    const uint32_t wp = smem_u32(epi_params + ew * 96);
                     __syncwarp();
-                    wp[lane] = pb; wp[32 + lane] = pg; wp[64 + lane] = pe;
+                    sts32f(wp + 4 * lane, pb); sts32f(wp + 4 * (32 + lane), pg); sts32f(wp + 4 * (64 + lane), pe);
                     pb = qb; pg = qg; pe = qe;
                     __syncwarp();
                     uint32_t h[32];
@@ -653,9 +671,9 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                     if (ep.act == WD_ACT_RELU) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(wp + 4 * j4);
-                            const float4 g4 = *reinterpret_cast<const float4*>(wp + 32 + 4 * j4);
-                            const float4 e4 = *reinterpret_cast<const float4*>(wp + 64 + 4 * j4);
+                            const float4 b4 = lds128f(wp + 16 * j4);
+                            const float4 g4 = lds128f(wp + 128 + 16 * j4);
+                            const float4 e4 = lds128f(wp + 256 + 16 * j4);
                             const float a0 = fmaxf(__uint_as_float(v[4 * j4]) + b4.x, 0.f), a1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b4.y, 0.f);
                             const float a2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b4.z, 0.f), a3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b4.w, 0.f);
                             v[4 * j4] = __float_as_uint(a0); v[4 * j4 + 1] = __float_as_uint(a1); v[4 * j4 + 2] = __float_as_uint(a2); v[4 * j4 + 3] = __float_as_uint(a3);
@@ -670,9 +688,9 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const bool ok = (nb + j) < ep.n_logical;
-                            const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + wp[j]) : 0.f;
+                            const float av = ok ? act_fwd(ep.act, __uint_as_float(v[j]) + lds32f(wp + 4 * j)) : 0.f;
                             v[j] = __float_as_uint(av);
-                            h[j] = __float_as_uint(ok ? fmaf(av, wp[32 + j], wp[64 + j]) : 0.f);
+                            h[j] = __float_as_uint(ok ? fmaf(av, lds32f(wp + 4 * (32 + j)), lds32f(wp + 4 * (64 + j))) : 0.f);
                         }
                     }
                     if (!rv) {
@@ -697,11 +715,17 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                     put64(hl); flush64(dl, (int64_t)ep.ldh * 2, mw, false);
                 } else if (MODE == EPI_DACT) {
                     // v = dH of the fed layer (row m, columns nb .. nb + 31); never stored
-                    float* wp = epi_params + ew * 96;
+                    const uint32_t wp = smem_u32(epi_params + ew * 96);
                     __syncwarp();
-                    wp[lane] = pg;                                    // gamma * 1/sqrt(1 + eps) of column nb + lane (1 without batch norm)
+                    sts32f(wp + 4 * lane, pg);                        // gamma * 1/sqrt(1 + eps) of column nb + lane (1 without batch norm)
                     pg = qg;
                     __syncwarp();
+                    float gs[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 t = lds128f(wp + 16 * j4);
+                        gs[4 * j4] = t.x; gs[4 * j4 + 1] = t.y; gs[4 * j4 + 2] = t.z; gs[4 * j4 + 3] = t.w;
+                    }
                     const bool rv = m < M;
                     float av[32], dz[32];
                     take64(ar0, av);
@@ -713,15 +737,15 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                         const bool ok = rv && (nb + j) < ep.n_logical;
                         const float dh = ok ? __uint_as_float(v[j]) : 0.f;
                         const float aj = ok ? av[j] : 0.f;
-                        dz[j] = relu ? (aj > 0.f ? dh * wp[j] : 0.f) : dh * wp[j] * act_bwd(ep.act, aj);
+                        dz[j] = relu ? (aj > 0.f ? dh * gs[j] : 0.f) : dh * gs[j] * act_bwd(ep.act, aj);
                         av[j] = dh * aj * 0.99950037468777f;           // gamma-gradient term
                         te[j] = dh;                                   // beta-gradient term
                     }
                     // column sums over the warp's 32 rows (fixed butterfly order): lane j ends with the sum of column nb + j
-                    float* cs = colsum + ew * 384 + (c - c_beg) * 32 + lane;
+                    const uint32_t cs = smem_u32(colsum + ew * 384 + (c - c_beg) * 32 + lane);
                     if (ep.bn) {
-                        cs[128] = colsum32(av, lane);
-                        cs[256] = colsum32(te, lane);
+                        sts32f(cs + 512, colsum32(av, lane));
+                        sts32f(cs + 1024, colsum32(te, lane));
                     }
                     {
                         uint32_t hh[16], hl[16];
@@ -739,7 +763,7 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                         put64(hh); flush64(dh_, (int64_t)ep.ldh * 2, mw, false);
                         put64(hl); flush64(dl_, (int64_t)ep.ldh * 2, mw, false);
                     }
-                    cs[0] = colsum32(dz, lane);
+                    sts32f(cs, colsum32(dz, lane));
                 } else {
                     store_f32(ep.C + (MODE == EPI_WGRAD ? (int64_t)z * ep.split_stride : 0), ep.ldc, mw, nb, v, MODE == EPI_STORE && ep.accumulate);
                 }
@@ -759,9 +783,9 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
                     float sb = 0.f, sg = 0.f, se = 0.f;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
-                        const float* src = colsum + (hcol * 4 + ((qq + 2) & 3)) * 384 + col;      // warp 2 + 4 h + i serves quarter (i + 2) & 3
-                        sb += src[0];
-                        if (ep.bn) { sg += src[128]; se += src[256]; }
+                        const uint32_t src = smem_u32(colsum + (hcol * 4 + ((qq + 2) & 3)) * 384 + col);   // warp 2 + 4 h + i serves quarter (i + 2) & 3
+                        sb += lds32f(src);
+                        if (ep.bn) { sg += lds32f(src + 512); se += lds32f(src + 1024); }
                     }
                     const int64_t o = (int64_t)(m0 / QBM) * ep.pstride + n;
                     ep.p_bias[o] = sb;

@@ -535,38 +535,35 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(int B, int N, int n_log
     }
 }
 
-// The same for the 3xBF16 engine (dZ leaves as bf16 hi / lo copies only, no transposed copy), vectorised: a block covers one
-// 128-row tile x 128 columns; a thread owns 4 consecutive columns (16-byte loads of dH and A, 8-byte stores of the bf16 copies)
-// and every 8th row; the column partial sums go through shared memory in a fixed order.
+// The same for the 3xBF16 engine (dZ leaves as bf16 hi / lo copies only, no transposed copy): a block covers one 128-row tile x
+// 64 columns; a thread owns 4 consecutive columns and every 16th row, and issues all sixteen 16-byte loads (dH and A of its 8
+// rows) before the first use; 8-byte stores of the bf16 copies; the column partial sums go through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_logical, const float* __restrict__ dH, const float* __restrict__ Aact,
                                                           int ld, const float* __restrict__ gamma, int act, int bn,
                                                           float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta,
                                                           int64_t pstride, __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo, DropArgs dr) {
-    __shared__ float red[3][8][128];
+    __shared__ float red[3][16][64];
     const unsigned long long dkey = dr.rate > 0.f ? drop_key(dr) : 0ull;
     const float inv_keep = dr.rate > 0.f ? 1.f / (1.f - dr.rate) : 1.f;
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int n0 = blockIdx.x * 128 + cx * 4, rt = blockIdx.y;
+    const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+    const int n0 = blockIdx.x * 64 + cx * 4, rt = blockIdx.y, b0 = rt * 128;
     const float inv = 0.99950037468777f;
     float gsc[4], sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sbe[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) gsc[j] = (bn && n0 + j < n_logical) ? gamma[n0 + j] * inv : 1.f;
     if (n0 < N) {
-      for (int i0 = 0; i0 < 16; i0 += 4) {
-        // the loads of four rows are issued before anything depends on them (rows past the batch re-read the last valid row)
-        float4 dhv[4], av[4];
+        float4 dhv[8], av[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int mr = min(rt * 128 + (i0 + u) * 8 + ry, B - 1);
+        for (int u = 0; u < 8; ++u) {                                  // rows past the batch re-read the last valid row
+            const int mr = min(b0 + u * 16 + ry, B - 1);
             dhv[u] = *reinterpret_cast<const float4*>(dH + (int64_t)mr * ld + n0);
             av[u] = *reinterpret_cast<const float4*>(Aact + (int64_t)mr * ld + n0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int mm = rt * 128 + (i0 + u) * 8 + ry;
+        for (int u = 0; u < 8; ++u) {
+            const int mm = b0 + u * 16 + ry;
             if (mm >= B) continue;
-            const float4 dh4 = dhv[u], a4 = av[u];
-            const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float dh[4] = {dhv[u].x, dhv[u].y, dhv[u].z, dhv[u].w}, a[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
             float dz[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -587,19 +584,100 @@ __global__ void __launch_bounds__(256) act_bn_bwd_q_kernel(int B, int N, int n_l
             *reinterpret_cast<uint2*>(q_hi + (int64_t)mm * ld + n0) = ph;
             *reinterpret_cast<uint2*>(q_lo + (int64_t)mm * ld + n0) = pl;
         }
-      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red[0][ry][cx * 4 + j] = sb[j]; red[1][ry][cx * 4 + j] = sg[j]; red[2][ry][cx * 4 + j] = sbe[j]; }
     __syncthreads();
-    if (threadIdx.x < 128) {
-        const int n = blockIdx.x * 128 + threadIdx.x;
-        if (n < N) {
-            float x = 0.f, y = 0.f, z = 0.f;
-            for (int i = 0; i < 8; ++i) { x += red[0][i][threadIdx.x]; y += red[1][i][threadIdx.x]; z += red[2][i][threadIdx.x]; }
-            p_bias[(int64_t)rt * pstride + n] = x;
-            if (bn) { p_gamma[(int64_t)rt * pstride + n] = y; p_beta[(int64_t)rt * pstride + n] = z; }
+    if (threadIdx.x < 192) {
+        const int which = threadIdx.x >> 6, c = threadIdx.x & 63, n = blockIdx.x * 64 + c;
+        if (n < N && (which == 0 || bn)) {
+            float x = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x += red[which][i][c];
+            (which == 0 ? p_bias : which == 1 ? p_gamma : p_beta)[(int64_t)rt * pstride + n] = x;
         }
+    }
+}
+
+// 3xBF16 engine, last hidden layer of a tower whose only reader is the logits layer: the logits layer's backward (kernel / bias
+// gradient partials, dH = dlogit x w) and the layer's own activation / batch-norm backward in ONE pass — dH never exists.
+// Block = 128 rows x 64 columns, thread = 4 columns x 8 rows with all sixteen 16-byte loads (H and A) in flight before the first use;
+// column partials through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) logits_act_bwd_q_kernel(int B, int N, int n_logical, const float* __restrict__ H, int ldh,
+                                                              const float* __restrict__ Aact, int ld, const float* __restrict__ dlogit,
+                                                              const float* __restrict__ kw, const float* __restrict__ gamma, int act, int bn,
+                                                              float* __restrict__ p_kw, int64_t kw_stride, float* __restrict__ p_lbias, int64_t lbias_stride,
+                                                              float* __restrict__ p_wbias, int64_t wbias_stride,
+                                                              float* __restrict__ p_bias, float* __restrict__ p_gamma, float* __restrict__ p_beta, int64_t pstride,
+                                                              __nv_bfloat16* __restrict__ q_hi, __nv_bfloat16* __restrict__ q_lo) {
+    __shared__ float red[4][16][64];
+    __shared__ float dl[128];
+    const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+    const int n0 = blockIdx.x * 64 + cx * 4, rt = blockIdx.y, b0 = rt * 128;
+    const float inv = 0.99950037468777f;
+    if (threadIdx.x < 128) dl[threadIdx.x] = (b0 + threadIdx.x < B) ? dlogit[b0 + threadIdx.x] : 0.f;
+    float gsc[4], w[4], sk[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sbe[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gsc[j] = (bn && n0 + j < n_logical) ? gamma[n0 + j] * inv : 1.f;
+        w[j] = n0 + j < N ? kw[n0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (n0 < N) {
+        float4 hv[8], av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                                  // rows past the batch re-read the last valid row
+            const int mr = min(b0 + u * 16 + ry, B - 1);
+            hv[u] = *reinterpret_cast<const float4*>(H + (int64_t)mr * ldh + n0);
+            av[u] = *reinterpret_cast<const float4*>(Aact + (int64_t)mr * ld + n0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int mm = b0 + u * 16 + ry;
+            if (mm >= B) continue;
+            const float g = dl[u * 16 + ry];
+            const float h[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w}, a[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+            float dz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sk[j] = fmaf(h[j], g, sk[j]);
+                dz[j] = 0.f;
+                if (n0 + j < n_logical) {
+                    const float dh = g * w[j];
+                    dz[j] = dh * gsc[j] * act_bwd(act, a[j]);
+                    sb[j] += dz[j]; sg[j] += dh * a[j] * inv; sbe[j] += dh;
+                }
+            }
+            __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+            split_bf16(dz[0], h0, l0); split_bf16(dz[1], h1, l1); split_bf16(dz[2], h2, l2); split_bf16(dz[3], h3, l3);
+            uint2 ph, pl;
+            ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+            *reinterpret_cast<uint2*>(q_hi + (int64_t)mm * ld + n0) = ph;
+            *reinterpret_cast<uint2*>(q_lo + (int64_t)mm * ld + n0) = pl;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][ry][cx * 4 + j] = sk[j]; red[1][ry][cx * 4 + j] = sb[j]; red[2][ry][cx * 4 + j] = sg[j]; red[3][ry][cx * 4 + j] = sbe[j]; }
+    __syncthreads();
+    {
+        const int which = threadIdx.x >> 6, c = threadIdx.x & 63, n = blockIdx.x * 64 + c;      // 4 quantities x 64 columns
+        if (n < N) {
+            float x = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x += red[which][i][c];
+            if (which == 0) p_kw[(int64_t)rt * kw_stride + n] = x;
+            else if (which == 1) p_bias[(int64_t)rt * pstride + n] = x;
+            else if (bn) (which == 2 ? p_gamma : p_beta)[(int64_t)rt * pstride + n] = x;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (p_lbias || p_wbias)) {
+        float s = 0.f;
+        for (int i = 0; i < 128; ++i) s += dl[i];
+        if (p_lbias) p_lbias[(int64_t)rt * lbias_stride] = s;
+        if (p_wbias) p_wbias[(int64_t)rt * wbias_stride] = s;
     }
 }
 
@@ -947,8 +1025,11 @@ int mlp_backward(WdModel* m) {
     const __nv_bfloat16* Wq = reinterpret_cast<const __nv_bfloat16*>(m->d_Wsplit);
     // 3xBF16 engine: a hidden layer read by exactly one later HIDDEN layer (every layer but the last of `simple` towers) gets its
     // activation / batch-norm backward inside the epilogue of that consumer's data-gradient GEMM (EPI_DACT): its dH is never
-    // stored and act_bn_bwd_q_kernel is not launched for it.  WD_FUSE_DACT=0 keeps the separate pass.
-    static const bool fuse_dact_on = getenv("WD_FUSE_DACT") ? atoi(getenv("WD_FUSE_DACT")) != 0 : true;
+    // stored and act_bn_bwd_q_kernel is not launched for it.  Opt-in (WD_FUSE_DACT=1): measured on B200 the fused epilogue
+    // (1400 instructions per 32 x 32 chunk on eight epilogue warps) costs more than the separate pass saves (0.534 vs 0.520 ms per
+    // step, profiles/r2_*); the logits-layer fusion below (logits_act_bwd_q_kernel) is always on.
+    static const bool fuse_dact_on = getenv("WD_FUSE_DACT") ? atoi(getenv("WD_FUSE_DACT")) != 0 : false;
+    static const bool fuse_logits_on = getenv("WD_FUSE_LOGITS_BWD") ? atoi(getenv("WD_FUSE_LOGITS_BWD")) != 0 : true;
     static int num_sms = 0;
     if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, m->device);
     for (auto& tw : m->towers) {
@@ -975,6 +1056,19 @@ int mlp_backward(WdModel* m) {
             if (!(sg.src < 0 && !need_dx0)) grad_dst(sg.src, &dst, &dld, &acc);
             // (the first segment of the first tower also leaves the wide bias's gradient partials: both are tile sums of dlogit)
             const bool wb = m->use_wide && s == 0 && &tw == &m->towers.front();
+            if (q && fuse_logits_on && LL.n_in_segs == 1 && sg.src >= 0 && readers[sg.src] == 2 && m->dropout_rate <= 0.f &&
+                sg.width_phys == tw.layers[sg.src].N_phys) {
+                Layer& S = tw.layers[sg.src];
+                logits_act_bwd_q_kernel<<<dim3((S.N_phys + 63) / 64, rts), 256, 0, m->stream>>>(B, S.N_phys, S.N, src, ld, S.A, S.N_phys, m->d_dlogit,
+                    m->d_P + tk.off + sg.k_off, S.t_gamma >= 0 ? m->d_P + m->dense[S.t_gamma].off : nullptr, m->activation, m->batch_norm,
+                    m->d_gpart + tk.gpart_off + sg.k_off, tk.gstride, m->d_gpart + tb.gpart_off, tb.gstride,
+                    wb ? m->d_gpart + m->dense[0].gpart_off : nullptr, wb ? m->dense[0].gstride : 0,
+                    m->d_gpart + m->dense[S.t_bias].gpart_off, S.t_gamma >= 0 ? m->d_gpart + m->dense[S.t_gamma].gpart_off : nullptr,
+                    S.t_beta >= 0 ? m->d_gpart + m->dense[S.t_beta].gpart_off : nullptr, m->dense[S.t_bias].gstride, S.dZs[0], S.dZs[1]);
+                m->launches++;
+                fused[sg.src] = 1;
+                continue;
+            }
             logits_bwd_kernel<<<g, 256, 0, m->stream>>>(B, sg.width_phys, src, ld, m->d_dlogit, m->d_P + tk.off + sg.k_off,
                                                        m->d_gpart + tk.gpart_off + sg.k_off, tk.gstride,
                                                        s == 0 ? m->d_gpart + tb.gpart_off : nullptr, tb.gstride,
@@ -997,7 +1091,7 @@ int mlp_backward(WdModel* m) {
             if (fused[l]) {
                 // dZ and the partials of this layer were written by the data-gradient GEMM of the layer above
             } else if (q)
-                act_bn_bwd_q_kernel<<<dim3((L.N_phys + 127) / 128, rts), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
+                act_bn_bwd_q_kernel<<<dim3((L.N_phys + 63) / 64, rts), 256, 0, m->stream>>>(B, L.N_phys, L.N, L.dH, L.A, L.N_phys,
                     L.t_gamma >= 0 ? m->d_P + m->dense[L.t_gamma].off : nullptr, m->activation, m->batch_norm, pb, pg, pbe,
                     m->dense[L.t_bias].gstride, L.dZs[0], L.dZs[1], dr);
             else
@@ -1041,6 +1135,14 @@ int mlp_backward(WdModel* m) {
                 WD_CUDA(cudaEventRecord(m->ev_dx0, m->stream));        // dX0 is complete from here on
                 m->dx0_recorded = true;
             }
+        }
+        // ---- weight gradients, after EVERY data gradient of the tower: dX0 exists as early as the dependency chain allows, and
+        // the embedding backward on its side stream (sums + row updates, the longest tail of the step) runs under all of the
+        // tower's weight-gradient GEMMs and the dense optimizer instead of under the last one only
+        for (int l = tw.n_hidden - 1; l >= 0; --l) {
+            Layer& L = tw.layers[l];
+            m->cur_layer = l;
+            const DenseTensor& tkn = m->dense[L.t_kernel];
             for (int s = 0; s < L.n_in_segs; ++s) {
                 const Seg& sg = L.segs[s];
                 // weight gradient of the rows fed by this segment: [width_phys, N] = srcT * dZT^T, split over the batch

@@ -133,7 +133,17 @@ class WideAndDeepClassifier(object):
         restoring the latest checkpoint first and saving one at the end."""
         m = self._ensure_model()
         n, t0, loss = 0, time.time(), float("nan")
-        log_every = (self.config.runconfig or {}).get("log_step_count_steps") or 1000
+        run = self.config.runconfig or {}
+        log_every = run.get("log_step_count_steps") or 1000
+        # checkpoint cadence of tf.estimator.RunConfig (reference conf/train.yaml:80-98): every `save_checkpoints_steps` global
+        # steps, else every `save_checkpoints_secs` seconds (600 when neither is set); the step-count test is deterministic, so
+        # in a multi-GPU job every rank takes the collective save() at the same step; the timer of rank 0 decides for all ranks
+        ck_steps, ck_secs = run.get("save_checkpoints_steps"), run.get("save_checkpoints_secs")
+        if ck_steps and ck_secs:
+            raise ValueError("Can not provide both save_checkpoints_steps and save_checkpoints_secs.")      # RunConfig's message
+        if not ck_steps and not ck_secs:
+            ck_secs = 600
+        last_save = time.time()
         # one batch of look-ahead, as the reference's input_fn prefetches (python/lib/dataset.py:181-184): while step i runs on the
         # GPU, batch i+1 is parsed and its host->device copy issued (wd_batch_prefetch_slot, two alternating slots)
         from .dataset import Prefetcher
@@ -156,10 +166,26 @@ class WideAndDeepClassifier(object):
                 print("INFO: global_step %d: loss = %.6g (%.1f steps/sec)" % (m.global_step, loss, n / (time.time() - t0)))
             if (steps and n >= steps) or (max_steps and m.global_step >= max_steps):
                 break
+            if nxt is not None and self._checkpoint_due(m.global_step, ck_steps, ck_secs, last_save):
+                self.save()
+                last_save = time.time()
             cur, slot = nxt, 1 - slot
         print("INFO: Loss for final step: %s." % loss)
         self.save()
         return self
+
+    def _checkpoint_due(self, global_step, ck_steps, ck_secs, last_save):
+        if ck_steps:
+            return global_step % int(ck_steps) == 0
+        due = (time.time() - last_save) >= float(ck_secs)
+        if self.shard_world > 1:                              # save() is a collective: rank 0's clock decides for everyone
+            import torch
+            import torch.distributed as dist
+            dev = torch.device("cuda", self.device) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+            flag = torch.tensor([1 if due else 0], dtype=torch.int32, device=dev)
+            dist.broadcast(flag, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            due = bool(int(flag.item()))
+        return due
 
     def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
         if self.shard_world > 1:
