@@ -224,6 +224,7 @@ struct ShardState {
     int64_t ar_count = 0;               // floats all-reduced per step (dense gradients + small-table block)
     uint64_t step = 0;                  // steps issued (inbox double buffering)
     cudaEvent_t ev_a = nullptr;         // after barrier A on the main stream (owner-side grouping may start)
+    cudaEvent_t ev_ids2 = nullptr, ev_routed1 = nullptr, ev_served1 = nullptr;   // wide space routed / served on its side stream
     cudaGraphExec_t graph[64] = {};     // whole sharded step per batch slot
     DevBatch graph_view[64];
     int64_t graph_launches[64] = {};

@@ -496,6 +496,9 @@ int shard_build(WdModel* m, const WdPlanDesc* d) {
     if ((rc = dev_alloc(m, &S.d_peer_G, kMaxRanks))) return rc;
     if ((rc = dev_alloc(m, &S.d_peer_gred, kMaxRanks))) return rc;
     WD_CUDA(cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming));
+    WD_CUDA(cudaEventCreateWithFlags(&S.ev_ids2, cudaEventDisableTiming));
+    WD_CUDA(cudaEventCreateWithFlags(&S.ev_routed1, cudaEventDisableTiming));
+    WD_CUDA(cudaEventCreateWithFlags(&S.ev_served1, cudaEventDisableTiming));
     return WD_OK;
 }
 
@@ -669,18 +672,60 @@ int shard_backward_local(WdModel* m, bool overlap);     // api.cu: towers' backw
 int shard_apply_local(WdModel* m);                     // api.cu: dense optimizer + small-table block + joins
 int shard_group_async(WdModel* m);                     // api.cu: replicated lists' grouping on the side streams
 
+// run `fn` on the side stream of sparse list `w` (its scratch set), as api.cu does for the replicated lists
+template <typename F>
+static int on_side(WdModel* m, int w, F fn) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->sstream[w]; m->scratch_sel = 1 + w;
+    int rc = fn();
+    m->stream = main_stream; m->scratch_sel = 0;
+    return rc;
+}
+
+// The two table spaces (0 = embedding rows, 1 = wide rows) are independent until the towers need both results, and each one's
+// routing (sort by owner, starts, send) and serving is a chain of small latency-bound launches: the wide space's chain runs on
+// side stream 1, concurrently with the embedding space's on the main stream, and joins it before the next barrier.
+static bool wide_on_side(WdModel* m) { return m->shard.sp[0].on && m->shard.sp[1].on; }
+
 // phase 0: ids, routing, local gathers
 int shard_phase0(WdModel* m, bool train) {
+    ShardState& S = m->shard;
     int rc;
     if ((rc = ids_prepare(m))) return rc;
+    const bool split = wide_on_side(m);
+    if (split) {                                                // ahead of the replicated lists' grouping on that stream
+        WD_CUDA(cudaEventRecord(S.ev_ids2, m->stream));
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], S.ev_ids2, 0));
+        if ((rc = on_side(m, 1, [&] { return shard_route_send(m, 1); }))) return rc;
+        WD_CUDA(cudaEventRecord(S.ev_routed1, m->sstream[1]));
+    }
     if (train && (rc = shard_group_async(m))) return rc;
-    for (int s = 0; s < 2; ++s) if ((rc = shard_route_send(m, s))) return rc;
-    return sparse_forward(m);                                   // replicated tables (and the wide bias) while the peers route
+    if ((rc = shard_route_send(m, 0))) return rc;
+    if (!split && (rc = shard_route_send(m, 1))) return rc;
+    if ((rc = sparse_forward(m))) return rc;                    // replicated tables (and the wide bias) while the peers route
+    if (split) WD_CUDA(cudaStreamWaitEvent(m->stream, S.ev_routed1, 0));
+    return WD_OK;
+}
+// serve both spaces (after barrier A); the wide space on its side stream when both exist
+static int shard_serve_both(WdModel* m) {
+    ShardState& S = m->shard;
+    int rc;
+    const bool split = wide_on_side(m);
+    if (split) {
+        WD_CUDA(cudaEventRecord(S.ev_a, m->stream));
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], S.ev_a, 0));
+        if ((rc = on_side(m, 1, [&] { return shard_serve(m, 1); }))) return rc;
+        WD_CUDA(cudaEventRecord(S.ev_served1, m->sstream[1]));
+    }
+    if ((rc = shard_serve(m, 0))) return rc;
+    if (!split && (rc = shard_serve(m, 1))) return rc;
+    if (split) WD_CUDA(cudaStreamWaitEvent(m->stream, S.ev_served1, 0));
+    return WD_OK;
 }
 // phase 1: serve the peers; sort what was received
 int shard_phase1(WdModel* m, bool train) {
     int rc;
-    for (int s = 0; s < 2; ++s) if ((rc = shard_serve(m, s))) return rc;
+    if ((rc = shard_serve_both(m))) return rc;
     if (train)
         for (int s = 0; s < 2; ++s) if ((rc = shard_owner_group(m, s))) return rc;
     return WD_OK;
@@ -710,16 +755,6 @@ int shard_phase4(WdModel* m) {
     return WD_OK;
 }
 
-// run `fn` on the side stream of sparse list `w` (its scratch set), as api.cu does for the replicated lists
-template <typename F>
-static int on_side(WdModel* m, int w, F fn) {
-    cudaStream_t main_stream = m->stream;
-    m->stream = m->sstream[w]; m->scratch_sel = 1 + w;
-    int rc = fn();
-    m->stream = main_stream; m->scratch_sel = 0;
-    return rc;
-}
-
 // The whole step of one rank of a multi-process job.  Main stream: ids, routing, serve, combine, towers, dense all-reduce and
 // optimizers, with flag barriers A (ids delivered), B (pooled sums delivered), G (gradient arenas final), R (slices reduced) and
 // END.  Side stream of each table space: the owner-side grouping of the received rows (needs only ids: runs beside the towers)
@@ -733,7 +768,7 @@ int shard_step_ipc(WdModel* m, bool train) {
     if (S.d_trace) { shard_stamp_kernel<<<1, 1, 0, m->stream>>>(S.d_trace + 2 * (kBarriers - 1)); m->launches++; }   // step start
     if ((rc = shard_phase0(m, train))) return rc;
     if ((rc = barrier(m, BAR_A))) return rc;
-    for (int s = 0; s < 2; ++s) if ((rc = shard_serve(m, s))) return rc;
+    if ((rc = shard_serve_both(m))) return rc;
     if (train) {
         WD_CUDA(cudaEventRecord(S.ev_a, m->stream));
         for (int s = 0; s < 2; ++s) {

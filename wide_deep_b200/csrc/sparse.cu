@@ -96,20 +96,29 @@ __global__ void __launch_bounds__(256) emb_pool_fwd_kernel(int B, int C, int nta
             const int stride = tab_stride[t];
             const int64_t rb = tab_row_base[t];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int j = s + grp;
-            for (; j + 3 * GROUPS < e; j += 4 * GROUPS) {
-                float4 v0 = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
-                float4 v1 = ldg_nc_f4(base + (int64_t)(e_emb[j + GROUPS] - rb) * stride);
-                float4 v2 = ldg_nc_f4(base + (int64_t)(e_emb[j + 2 * GROUPS] - rb) * stride);
-                float4 v3 = ldg_nc_f4(base + (int64_t)(e_emb[j + 3 * GROUPS] - rb) * stride);
-                acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-                acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
-                acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
-                acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
-            }
-            for (; j < e; j += GROUPS) {
-                float4 v = ldg_nc_f4(base + (int64_t)(e_emb[j] - rb) * stride);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            // 32 ids of the bag per round trip (one per lane), then ALL rows of the chunk that belong to this lane group back to
+            // back (up to sixteen 16-byte loads in flight per lane): the chain offsets -> ids -> rows is three dependent round trips
+            // per 32 ids instead of one per four rows.  Group grp still sums rows grp, grp + GROUPS, ... in that order (the result
+            // is bit-identical to the sequential walk).
+            constexpr int STEPS = 32 / GROUPS, RND = STEPS < 16 ? STEPS : 16;
+            for (int j0 = s; j0 < e; j0 += 32) {
+                const int cnt = min(32, e - j0);
+                const uint32_t my = lane < cnt ? e_emb[j0 + lane] : 0u;
+#pragma unroll
+                for (int k0 = 0; k0 < STEPS; k0 += RND) {
+                    if (k0 * GROUPS >= cnt) break;
+                    float4 v[RND];
+#pragma unroll
+                    for (int u = 0; u < RND; ++u) {
+                        const int r = (k0 + u) * GROUPS + grp;
+                        const uint32_t id = __shfl_sync(0xffffffffu, my, r & 31);
+                        v[u] = r < cnt ? ldg_nc_f4(base + (int64_t)(id - rb) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < RND; ++u) {
+                        if ((k0 + u) * GROUPS + grp < cnt) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                    }
+                }
             }
 #pragma unroll
             for (int d = G; d < 32; d <<= 1) {                  // segmented (per lane-in-group) shuffle reduction
