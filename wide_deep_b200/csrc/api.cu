@@ -121,6 +121,8 @@ extern "C" int wd_model_destroy(WdModel* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_loss_pinned) cudaFreeHost(m->h_loss_pinned);
     for (auto& e : m->timer.ev) if (e) cudaEventDestroy(e);
+    if (m->shard.aux) { cudaStreamSynchronize(m->shard.aux); cudaStreamDestroy(m->shard.aux); }
+    for (cudaEvent_t ev : {m->shard.ev_a, m->shard.ev_ids2, m->shard.ev_routed1, m->shard.ev_a2, m->shard.ev_aux_done}) if (ev) cudaEventDestroy(ev);
     for (int w = 0; w < 2; ++w) {
         if (m->sstream[w]) { cudaStreamSynchronize(m->sstream[w]); cudaStreamDestroy(m->sstream[w]); }
         if (m->ev_grouped[w]) cudaEventDestroy(m->ev_grouped[w]);
@@ -234,10 +236,10 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     if ((rc = dev_alloc(m, &m->d_e_id, m->max_nnz))) return rc;
     if ((rc = dev_alloc(m, &m->d_nnz, 4))) return rc;
     if ((rc = dev_alloc(m, &m->d_flags, 4))) return rc;
-    for (int k = 0; k < 3; ++k) if ((rc = dev_alloc(m, &m->d_sort_counter_s[k], 4))) return rc;
+    for (int k = 0; k < 4; ++k) if ((rc = dev_alloc(m, &m->d_sort_counter_s[k], 4))) return rc;
     {
         int64_t n = std::max<int64_t>(Bm * std::max(C, 1) + 2, m->max_nnz + 2);
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 4; ++k) {
             int32_t* t;
             if ((rc = dev_alloc(m, &t, n / 4096 + 8))) return rc;
             m->d_scan_tmp_s[k] = t;
@@ -502,7 +504,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
         m->sparse_cap[w] = m->max_nnz;
     }
     m->sort_hist_cap = 1024 * ((m->max_nnz + kSortTile - 1) / kSortTile + 1) + 4 * 1024 + 64;
-    for (int k = 0; k < 3; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
+    for (int k = 0; k < 4; ++k) if ((rc = dev_alloc(m, &m->d_sort_hist_s[k], m->sort_hist_cap))) return rc;
     if (G > 1) {
         if ((rc = shard_build(m, d))) return rc;
         DevPlan& dp = m->dplan;

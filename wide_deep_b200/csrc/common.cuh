@@ -224,7 +224,8 @@ struct ShardState {
     int64_t ar_count = 0;               // floats all-reduced per step (dense gradients + small-table block)
     uint64_t step = 0;                  // steps issued (inbox double buffering)
     cudaEvent_t ev_a = nullptr;         // after barrier A on the main stream (owner-side grouping may start)
-    cudaEvent_t ev_ids2 = nullptr, ev_routed1 = nullptr, ev_served1 = nullptr;   // wide space routed / served on its side stream
+    cudaStream_t aux = nullptr;         // the wide space's routing / serving and the local gathers, beside the embedding space's chain
+    cudaEvent_t ev_ids2 = nullptr, ev_routed1 = nullptr, ev_a2 = nullptr, ev_aux_done = nullptr;
     cudaGraphExec_t graph[64] = {};     // whole sharded step per batch slot
     DevBatch graph_view[64];
     int64_t graph_launches[64] = {};
@@ -300,7 +301,7 @@ struct WdModel {
     int32_t* d_e_id = nullptr;               // [max_nnz] column-local id (debug / parity)
     int32_t* d_nnz = nullptr;                // device scalar: entries this step
     int32_t* d_flags = nullptr;              // device error flags [4]
-    void* d_scan_tmp_s[3] = {nullptr, nullptr, nullptr};   // scan / sort scratch, one set per stream (0 main, 1 + list for the side streams)
+    void* d_scan_tmp_s[4] = {nullptr, nullptr, nullptr, nullptr};   // scan / sort scratch, one set per stream (0 main, 1 + list for the side streams, 3 aux)
     int scratch_sel = 0;
 
     // ---- wide part: record {w, n, z, 0} per row
@@ -347,9 +348,9 @@ struct WdModel {
     // ---- sparse backward scratch (two sorts: 0 = embedding rows, 1 = wide rows)
     uint32_t *d_sk[wd::kLists] = {}, *d_sv[wd::kLists] = {};     // ping-pong keys / values
     uint32_t *d_sk2[wd::kLists] = {}, *d_sv2[wd::kLists] = {};
-    int32_t* d_sort_hist_s[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_sort_hist_s[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t sort_hist_cap = 0;
-    int32_t* d_sort_counter_s[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_sort_counter_s[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t* d_urow[wd::kLists] = {};   // unique rows
     int32_t* d_ustart[wd::kLists] = {};  // segment starts in the sorted list (+1 sentinel)
     float* d_ugrad[wd::kLists] = {};     // [cap, width]

@@ -498,7 +498,9 @@ int shard_build(WdModel* m, const WdPlanDesc* d) {
     WD_CUDA(cudaEventCreateWithFlags(&S.ev_a, cudaEventDisableTiming));
     WD_CUDA(cudaEventCreateWithFlags(&S.ev_ids2, cudaEventDisableTiming));
     WD_CUDA(cudaEventCreateWithFlags(&S.ev_routed1, cudaEventDisableTiming));
-    WD_CUDA(cudaEventCreateWithFlags(&S.ev_served1, cudaEventDisableTiming));
+    WD_CUDA(cudaEventCreateWithFlags(&S.ev_a2, cudaEventDisableTiming));
+    WD_CUDA(cudaEventCreateWithFlags(&S.ev_aux_done, cudaEventDisableTiming));
+    WD_CUDA(cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking));
     return WD_OK;
 }
 
@@ -682,47 +684,59 @@ static int on_side(WdModel* m, int w, F fn) {
     return rc;
 }
 
-// The two table spaces (0 = embedding rows, 1 = wide rows) are independent until the towers need both results, and each one's
-// routing (sort by owner, starts, send) and serving is a chain of small latency-bound launches: the wide space's chain runs on
-// side stream 1, concurrently with the embedding space's on the main stream, and joins it before the next barrier.
-static bool wide_on_side(WdModel* m) { return m->shard.sp[0].on && m->shard.sp[1].on; }
+// run `fn` on the auxiliary stream (scratch set 3)
+template <typename F>
+static int on_aux(WdModel* m, F fn) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->shard.aux; m->scratch_sel = 3;
+    int rc = fn();
+    m->stream = main_stream; m->scratch_sel = 0;
+    return rc;
+}
 
-// phase 0: ids, routing, local gathers
+// The critical chain in front of the towers is   ids -> route + send (embedding space) -> [A] -> serve (embedding space) -> [B].
+// Everything else that must exist before the towers — the wide space's routing, its serve, and this rank's local gathers
+// (replicated tables, wide bias) — is independent of that chain, so it runs beside it on an auxiliary stream: routing right after
+// the ids, serving + local gathers once barrier A has passed, joined before barrier B.  (The two side streams cannot take it: they
+// already hold the grouping of the replicated lists, ~100 us of sort launches enqueued before barrier A.)
+static bool aux_split(WdModel* m) { return m->shard.sp[0].on && m->shard.sp[1].on; }
+
+// phase 0: ids, routing
 int shard_phase0(WdModel* m, bool train) {
     ShardState& S = m->shard;
     int rc;
     if ((rc = ids_prepare(m))) return rc;
-    const bool split = wide_on_side(m);
-    if (split) {                                                // ahead of the replicated lists' grouping on that stream
+    const bool split = aux_split(m);
+    if (split) {
         WD_CUDA(cudaEventRecord(S.ev_ids2, m->stream));
-        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], S.ev_ids2, 0));
-        if ((rc = on_side(m, 1, [&] { return shard_route_send(m, 1); }))) return rc;
-        WD_CUDA(cudaEventRecord(S.ev_routed1, m->sstream[1]));
+        WD_CUDA(cudaStreamWaitEvent(S.aux, S.ev_ids2, 0));
+        if ((rc = on_aux(m, [&] { return shard_route_send(m, 1); }))) return rc;
+        WD_CUDA(cudaEventRecord(S.ev_routed1, S.aux));
     }
     if (train && (rc = shard_group_async(m))) return rc;
     if ((rc = shard_route_send(m, 0))) return rc;
     if (!split && (rc = shard_route_send(m, 1))) return rc;
-    if ((rc = sparse_forward(m))) return rc;                    // replicated tables (and the wide bias) while the peers route
     if (split) WD_CUDA(cudaStreamWaitEvent(m->stream, S.ev_routed1, 0));
     return WD_OK;
 }
-// serve both spaces (after barrier A); the wide space on its side stream when both exist
+// after barrier A: serve both spaces and run the local part of the forward (needed only by this rank's towers, while every peer's
+// barrier B waits for the serves)
 static int shard_serve_both(WdModel* m) {
     ShardState& S = m->shard;
     int rc;
-    const bool split = wide_on_side(m);
-    if (split) {
-        WD_CUDA(cudaEventRecord(S.ev_a, m->stream));
-        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], S.ev_a, 0));
-        if ((rc = on_side(m, 1, [&] { return shard_serve(m, 1); }))) return rc;
-        WD_CUDA(cudaEventRecord(S.ev_served1, m->sstream[1]));
+    if (aux_split(m)) {
+        WD_CUDA(cudaEventRecord(S.ev_a2, m->stream));
+        WD_CUDA(cudaStreamWaitEvent(S.aux, S.ev_a2, 0));
+        if ((rc = on_aux(m, [&] { int r = shard_serve(m, 1); return r ? r : sparse_forward(m); }))) return rc;
+        WD_CUDA(cudaEventRecord(S.ev_aux_done, S.aux));
+        if ((rc = shard_serve(m, 0))) return rc;
+        WD_CUDA(cudaStreamWaitEvent(m->stream, S.ev_aux_done, 0));
+        return WD_OK;
     }
-    if ((rc = shard_serve(m, 0))) return rc;
-    if (!split && (rc = shard_serve(m, 1))) return rc;
-    if (split) WD_CUDA(cudaStreamWaitEvent(m->stream, S.ev_served1, 0));
-    return WD_OK;
+    for (int s = 0; s < 2; ++s) if ((rc = shard_serve(m, s))) return rc;
+    return sparse_forward(m);
 }
-// phase 1: serve the peers; sort what was received
+// phase 1: serve the peers, local gathers; sort what was received
 int shard_phase1(WdModel* m, bool train) {
     int rc;
     if ((rc = shard_serve_both(m))) return rc;
@@ -878,7 +892,8 @@ extern "C" int wd_shard_local_sync(WdModel** models, int32_t n_ranks) {
     for (int r = 0; r < n_ranks; ++r) {
         WdModel* m = models[r];
         WD_CUDA(cudaSetDevice(m->device));
-        for (cudaStream_t st : {m->stream, m->sstream[0], m->sstream[1]}) {
+        for (cudaStream_t st : {m->stream, m->sstream[0], m->sstream[1], m->shard.aux}) {
+            if (!st) continue;
             cudaEvent_t ev;
             WD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             WD_CUDA(cudaEventRecord(ev, st));
@@ -888,8 +903,8 @@ extern "C" int wd_shard_local_sync(WdModel** models, int32_t n_ranks) {
     for (int r = 0; r < n_ranks; ++r) {
         WdModel* m = models[r];
         WD_CUDA(cudaSetDevice(m->device));
-        for (cudaStream_t st : {m->stream, m->sstream[0], m->sstream[1]})
-            for (cudaEvent_t ev : evs) WD_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        for (cudaStream_t st : {m->stream, m->sstream[0], m->sstream[1], m->shard.aux})
+            if (st) for (cudaEvent_t ev : evs) WD_CUDA(cudaStreamWaitEvent(st, ev, 0));
     }
     for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
     return WD_OK;
