@@ -129,6 +129,7 @@ extern "C" int wd_model_destroy(WdModel* m) {
         if (m->ev_done[w]) cudaEventDestroy(m->ev_done[w]);
     }
     if (m->ev_ids) cudaEventDestroy(m->ev_ids);
+    if (m->ev_wide_fwd) cudaEventDestroy(m->ev_wide_fwd);
     if (m->ev_head) cudaEventDestroy(m->ev_head);
     if (m->ev_dx0) cudaEventDestroy(m->ev_dx0);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -547,6 +548,7 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_done[w], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide_fwd, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_dx0, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_bwd_done, cudaEventDisableTiming);
@@ -902,11 +904,21 @@ static int forward_core(WdModel* m, bool train) {
     if ((rc = ids_prepare(m))) return rc;
     mark(m, "ids");
     stamp(m, ST_IDS);
+    // training: the wide logit is needed only by the head, so it is computed on side stream 1, ahead of that stream's grouping work
+    const bool wide_aside = train && !m->timer.enabled && m->use_wide && m->use_deep && list_present(m, 1);
+    if (wide_aside) {
+        WD_CUDA(cudaEventRecord(m->ev_ids, m->stream));
+        WD_CUDA(cudaStreamWaitEvent(m->sstream[1], m->ev_ids, 0));
+        if ((rc = on_side(m, 1, [&] { return sparse_forward_wide(m); }))) return rc;
+        WD_CUDA(cudaEventRecord(m->ev_wide_fwd, m->sstream[1]));
+    }
     if (train && (rc = group_async(m))) return rc;
-    if ((rc = sparse_forward(m))) return rc;
+    if (!wide_aside && (rc = sparse_forward_wide(m))) return rc;
+    if ((rc = sparse_forward_emb(m))) return rc;
     stamp(m, ST_GATHER);
     if ((rc = mlp_forward(m, train))) return rc;
     mark(m, "mlp_other");
+    if (wide_aside) WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_wide_fwd, 0));
     if ((rc = loss_forward(m, train))) return rc;
     mark(m, "head");
     stamp(m, ST_HEAD);

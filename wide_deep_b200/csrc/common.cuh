@@ -257,7 +257,7 @@ struct WdModel {
     // the data-parallel merge and the row updates of a list all run there, overlapping the towers on the main stream
     cudaStream_t sstream[2] = {nullptr, nullptr};
     cudaStream_t stream_up = nullptr;        // host->device refills of batch slots (wd_batch_prefetch_slot), overlapping the running step
-    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr;
+    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr, ev_wide_fwd = nullptr;
     cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool side_pending[2] = {false, false};   // the list's grouping of this step was issued on its side stream
     bool side_active[2] = {false, false};    // the list's sums live on its side stream (merge / apply follow there)
@@ -388,6 +388,8 @@ namespace wd {
 // ---- kernels / stages implemented in the .cu files (all enqueue on m->stream)
 int ids_prepare(WdModel* m);                                     // ids.cu
 int sparse_forward(WdModel* m);                                  // sparse.cu: wide logit + embedding pooling + numerics
+int sparse_forward_wide(WdModel* m);                             //   the wide half alone
+int sparse_forward_emb(WdModel* m);                              //   the deep half alone
 int sparse_group(WdModel* m);                                    // sparse.cu: sort (row, occurrence) pairs, unique rows, chunks
 int sparse_reduce_emb(WdModel* m);                               // sparse.cu: per-row gradient sums (needs dX0)
 int sparse_reduce_wide(WdModel* m);                              // sparse.cu: per-row gradient sums (needs dlogit only)

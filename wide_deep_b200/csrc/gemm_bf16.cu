@@ -230,19 +230,32 @@ __global__ void __launch_bounds__(Q_THREADS, 1) tc_gemm_bf16_kernel(const __grid
         };
         // rows [mw, mw + 32) of a row-major matrix, 64 bytes per row starting at dst (byte pointer of row mw); accumulate: fp32 +=
         auto flush64 = [&](uint8_t* __restrict__ dst, int64_t ld_bytes, int mw, bool accumulate) {
+            // all four staged pieces (and, when accumulating, the four previous values) are fetched into DISTINCT registers before
+            // the first store: a store holds its source registers until the data has left for L1, so re-using one register quad per
+            // piece (what a load-store-load-store order compiles to) serialises the warp on that hand-off
+            const int c = lane & 3, r0 = lane >> 2;
+            uint4 v[4], p[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + (lane >> 2), c = lane & 3;
-                uint4 v4 = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-                if (mw + r < M) {
-                    uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
-                    if (accumulate) {
-                        const uint4 p = *g;
-                        v4.x = __float_as_uint(__uint_as_float(v4.x) + __uint_as_float(p.x)); v4.y = __float_as_uint(__uint_as_float(v4.y) + __uint_as_float(p.y));
-                        v4.z = __float_as_uint(__uint_as_float(v4.z) + __uint_as_float(p.z)); v4.w = __float_as_uint(__uint_as_float(v4.w) + __uint_as_float(p.w));
-                    }
-                    *g = v4;
+                const int r = i * 8 + r0;
+                v[i] = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+            }
+            if (accumulate) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + r0;
+                    p[i] = *reinterpret_cast<const uint4*>(dst + (int64_t)min(r, M - 1 - mw < 0 ? 0 : M - 1 - mw) * ld_bytes + c * 16);
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[i].x = __float_as_uint(__uint_as_float(v[i].x) + __uint_as_float(p[i].x)); v[i].y = __float_as_uint(__uint_as_float(v[i].y) + __uint_as_float(p[i].y));
+                    v[i].z = __float_as_uint(__uint_as_float(v[i].z) + __uint_as_float(p[i].z)); v[i].w = __float_as_uint(__uint_as_float(v[i].w) + __uint_as_float(p[i].w));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + r0;
+                if (mw + r < M) *reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16) = v[i];
             }
         };
         auto store_f32 = [&](float* __restrict__ dst, int64_t ld, int mw, int nb, const uint32_t* x, bool accumulate) {   // 32 x 32 fp32
@@ -578,19 +591,32 @@ tc_gemm_bf16_pair_kernel(const __grid_constant__ QMaps maps, const QSegs segs, i
             __syncwarp();
         };
         auto flush64 = [&](uint8_t* __restrict__ dst, int64_t ld_bytes, int mw, bool accumulate) {
+            // all four staged pieces (and, when accumulating, the four previous values) are fetched into DISTINCT registers before
+            // the first store: a store holds its source registers until the data has left for L1, so re-using one register quad per
+            // piece (what a load-store-load-store order compiles to) serialises the warp on that hand-off
+            const int c = lane & 3, r0 = lane >> 2;
+            uint4 v[4], p[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + (lane >> 2), c = lane & 3;
-                uint4 v4 = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-                if (mw + r < M) {
-                    uint4* g = reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16);
-                    if (accumulate) {
-                        const uint4 p = *g;
-                        v4.x = __float_as_uint(__uint_as_float(v4.x) + __uint_as_float(p.x)); v4.y = __float_as_uint(__uint_as_float(v4.y) + __uint_as_float(p.y));
-                        v4.z = __float_as_uint(__uint_as_float(v4.z) + __uint_as_float(p.z)); v4.w = __float_as_uint(__uint_as_float(v4.w) + __uint_as_float(p.w));
-                    }
-                    *g = v4;
+                const int r = i * 8 + r0;
+                v[i] = lds128(stg_s + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+            }
+            if (accumulate) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + r0;
+                    p[i] = *reinterpret_cast<const uint4*>(dst + (int64_t)min(r, M - 1 - mw < 0 ? 0 : M - 1 - mw) * ld_bytes + c * 16);
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[i].x = __float_as_uint(__uint_as_float(v[i].x) + __uint_as_float(p[i].x)); v[i].y = __float_as_uint(__uint_as_float(v[i].y) + __uint_as_float(p[i].y));
+                    v[i].z = __float_as_uint(__uint_as_float(v[i].z) + __uint_as_float(p[i].z)); v[i].w = __float_as_uint(__uint_as_float(v[i].w) + __uint_as_float(p[i].w));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + r0;
+                if (mw + r < M) *reinterpret_cast<uint4*>(dst + (int64_t)r * ld_bytes + c * 16) = v[i];
             }
         };
         auto store_f32 = [&](float* __restrict__ dst, int64_t ld, int mw, int nb, const uint32_t* x, bool accumulate) {

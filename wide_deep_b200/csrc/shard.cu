@@ -334,11 +334,15 @@ __global__ void __launch_bounds__(256) shard_ar_reduce_kernel(float* const* __re
                                                               int G, int me) {
     const int64_t lo = (int64_t)me * slice4, hi = min(n4, lo + slice4);
     for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < G; ++r) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(peer_G[r]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+        // every rank's value in flight before the first add (a peer load is ~2 us: one round trip instead of G), summed in rank order
+        float4 v[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+            v[r] = r < G ? __ldcg(reinterpret_cast<const float4*>(peer_G[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < kMaxRanks; ++r)
+            if (r < G) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
         reinterpret_cast<float4*>(gred)[i] = acc;
     }
 }

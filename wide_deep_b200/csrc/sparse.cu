@@ -370,7 +370,8 @@ static void launch_emb_fwd(WdModel* m, int di, bool widebag) {
     m->launches++;
 }
 
-int sparse_forward(WdModel* m) {
+// the wide half of the forward (independent of the deep half until the head adds the logits)
+int sparse_forward_wide(WdModel* m) {
     const int B = m->dbatch.B;
     if (m->use_wide) {
         wide_fwd_kernel<<<grid_for((int64_t)B * 32, 256), 256, 0, m->stream>>>(B, m->n_columns, m->d_col_offs, m->d_e_wide,
@@ -378,6 +379,15 @@ int sparse_forward(WdModel* m) {
         m->launches++;
         mark(m, "wide_fwd");
     }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+int sparse_forward_emb(WdModel* m);
+int sparse_forward(WdModel* m) {
+    int rc = sparse_forward_wide(m);
+    return rc ? rc : sparse_forward_emb(m);
+}
+int sparse_forward_emb(WdModel* m) {
     if (m->use_deep) {
         // heuristic: average bag length from the key count of the batch decides narrow vs full-warp bags
         bool widebag = m->max_nnz > 0 && (m->keys_cap / (int64_t)(m->max_batch * (m->n_cat_fields > 0 ? m->n_cat_fields : 1))) >= 8;
