@@ -846,6 +846,11 @@ static int finish_step(WdModel* m, float* loss_out, float* logits_out) {
         set_error("row-sharded exchange capacity exceeded (a rank received more than %lld ids): raise shard_slack / shard_capacity", (long long)m->max_nnz);
         return WD_EINVAL;
     }
+    if (flags_host[0] & 8) {
+        cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
+        set_error("data-parallel list exchange: this rank touched more unique rows than the fixed list length it exchanges (wd_sparse_set_sorted list_len); raise fixed_rows");
+        return WD_EINVAL;
+    }
     if (flags_host[0] & 4) {
         cudaMemsetAsync(m->d_flags, 0, 16, m->stream);
         set_error("row-sharded exchange: a peer rank did not reach a barrier within 20 s (ranks out of step, or a rank failed)");

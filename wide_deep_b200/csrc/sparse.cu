@@ -744,10 +744,16 @@ __global__ void __launch_bounds__(256) merge_rank_kernel(const uint32_t* __restr
         vals[pos] = (uint32_t)e;
     }
 }
+// this rank touched more unique rows than the fixed exchange length: its tail was NOT exchanged -> fail the step loudly (flag 8)
+__global__ void list_len_check_kernel(const int32_t* __restrict__ d_nuniq, int64_t list_len, int32_t* __restrict__ flags) {
+    if ((int64_t)*d_nuniq > list_len) atomicOr(flags, 8);
+}
 int merge_sparse_sorted(WdModel* m, int which, const void* rows, const void* grads, int n_lists, int64_t list_len) {
     const int64_t n = (int64_t)n_lists * list_len;
     if (n_lists < 1 || list_len < 1 || list_len > 0x7fffffff) { set_error("merge: bad list shape"); return WD_EINVAL; }
     if (n > m->max_nnz) { set_error("merged sparse list has %lld rows, capacity %lld", (long long)n, (long long)m->max_nnz); return WD_EINVAL; }
+    list_len_check_kernel<<<1, 1, 0, m->stream>>>(m->d_nuniq[which], list_len, m->d_flags);   // (d_nuniq still holds the local count)
+    m->launches++;
     merge_rank_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>((const uint32_t*)rows, n_lists, (int)list_len, m->d_sk[which], m->d_sv[which], m->d_nvalid[which]);
     m->launches++;
     int rc = group_tail(m, which, m->d_nvalid[which]);
