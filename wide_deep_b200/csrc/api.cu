@@ -130,6 +130,7 @@ extern "C" int wd_model_destroy(WdModel* m) {
     }
     if (m->ev_ids) cudaEventDestroy(m->ev_ids);
     if (m->ev_wide_fwd) cudaEventDestroy(m->ev_wide_fwd);
+    if (m->ev_wgrad_rest) cudaEventDestroy(m->ev_wgrad_rest);
     if (m->ev_head) cudaEventDestroy(m->ev_head);
     if (m->ev_dx0) cudaEventDestroy(m->ev_dx0);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -549,6 +550,7 @@ extern "C" int wd_model_create(const WdPlanDesc* d, int device, WdModel** out) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ids, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wide_fwd, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_wgrad_rest, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_dx0, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_bwd_done, cudaEventDisableTiming);
@@ -946,8 +948,13 @@ static int backward_core(WdModel* m) {
     }
     m->record_dx0 = m->side_pending[0];
     m->dx0_recorded = false;
+    // single-GPU fused step with the wide list on its side stream: the dense optimizer of everything but the first layer's kernel
+    // runs there (after the wide rows' updates), under that kernel's weight-gradient GEMM
+    m->dense_split_tensor = -1;
+    m->record_wgrad_rest = m->fuse_dense && m->side_active[1] && m->gemm_engine == WD_GEMM_BF16X3 && !m->timer.enabled;
     if ((rc = mlp_backward(m))) return rc;
     m->record_dx0 = false;
+    m->record_wgrad_rest = false;
     mark(m, "mlp_other");
     stamp(m, ST_BWD);
     if (m->side_pending[0] && m->dx0_recorded) {
@@ -980,14 +987,28 @@ static int backward_core(WdModel* m) {
 // optimizer runs on the main stream meanwhile and the streams join at the end of the step.
 static int apply_core(WdModel* m) {
     int rc;
+    const bool split_dense = m->fuse_dense && m->dense_split_tensor >= 0 && m->side_active[1];
     for (int w = 0; w < 2; ++w) {
         if (m->side_active[w]) {
-            if ((rc = on_side(m, w, [&] { int r = sparse_apply_which(m, w); stamp(m, ST_A0_END + w); return r; }))) return rc;
+            if ((rc = on_side(m, w, [&]() -> int {
+                    int r = sparse_apply_which(m, w);
+                    stamp(m, ST_A0_END + w);
+                    if (!r && w == 1 && split_dense) {
+                        WD_CUDA(cudaStreamWaitEvent(m->stream, m->ev_wgrad_rest, 0));
+                        m->dense_part = 2;
+                        r = dense_apply(m);
+                        m->dense_part = 0;
+                    }
+                    return r;
+                }))) return rc;
             WD_CUDA(cudaEventRecord(m->ev_done[w], m->sstream[w]));
         } else if ((rc = sparse_apply_which(m, w))) return rc;
     }
     mark(m, "sparse_apply");
-    if ((rc = dense_apply(m))) return rc;
+    m->dense_part = split_dense ? 1 : 0;
+    rc = dense_apply(m);
+    m->dense_part = 0;
+    if (rc) return rc;
     if ((rc = small_apply(m))) return rc;
     mark(m, "dense_apply");
     stamp(m, ST_MAIN_END);

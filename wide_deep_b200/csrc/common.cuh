@@ -257,7 +257,9 @@ struct WdModel {
     // the data-parallel merge and the row updates of a list all run there, overlapping the towers on the main stream
     cudaStream_t sstream[2] = {nullptr, nullptr};
     cudaStream_t stream_up = nullptr;        // host->device refills of batch slots (wd_batch_prefetch_slot), overlapping the running step
-    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr, ev_wide_fwd = nullptr;
+    cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr, ev_wide_fwd = nullptr, ev_wgrad_rest = nullptr;
+    bool record_wgrad_rest = false;           // mlp_backward: record ev_wgrad_rest before the first layer's weight gradient
+    int dense_split_tensor = -1, dense_part = 0;   // dense_apply: see mlp.cu (single-GPU step, split dense optimizer)
     cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool side_pending[2] = {false, false};   // the list's grouping of this step was issued on its side stream
     bool side_active[2] = {false, false};    // the list's sums live on its side stream (merge / apply follow there)

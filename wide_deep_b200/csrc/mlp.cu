@@ -800,8 +800,11 @@ template <int MODE>
 __global__ void __launch_bounds__(256) dense_vec_kernel(const DenseTensor* __restrict__ T, int nt, int64_t total4, const float* __restrict__ gpart,
                                                         float* __restrict__ G, float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2,
                                                         float* __restrict__ Wsplit, int64_t wt_count, OptParamsD dnn, OptParamsD lin, int lin_tensor,
-                                                        int live_row_tiles) {
-    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+                                                        int live_row_tiles, int64_t begin4, int64_t hole_lo4, int64_t hole_hi4) {
+    // arena range [begin4, total4) minus the hole [hole_lo4, hole_hi4): the single-GPU step updates everything but the first
+    // layer's kernel on a side stream while that kernel's weight gradient is still being computed (dense_apply_split)
+    for (int64_t i4 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        if (i4 >= hole_lo4 && i4 < hole_hi4) continue;
         const int64_t i = i4 * 4;
         int lo = 0, hi = nt - 1;
         while (lo < hi) {
@@ -1143,6 +1146,11 @@ int mlp_backward(WdModel* m) {
             Layer& L = tw.layers[l];
             m->cur_layer = l;
             const DenseTensor& tkn = m->dense[L.t_kernel];
+            if (l == 0 && m->record_wgrad_rest && m->towers.size() == 1 && L.n_in_segs == 1) {
+                // every gradient partial except the first layer's kernel is final from here on
+                WD_CUDA(cudaEventRecord(m->ev_wgrad_rest, m->stream));
+                m->dense_split_tensor = L.t_kernel;
+            }
             for (int s = 0; s < L.n_in_segs; ++s) {
                 const Seg& sg = L.segs[s];
                 // weight gradient of the rows fed by this segment: [width_phys, N] = srcT * dZT^T, split over the batch
@@ -1173,7 +1181,7 @@ int dense_reduce_grads(WdModel* m) {
         if (m->fuse_dense) return WD_OK;                              // single-GPU step: reduced inside dense_apply's kernel
         OptParamsD z{};
         dense_vec_kernel<0><<<grid_for(m->dense_count / 4, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart,
-            m->d_G, nullptr, nullptr, nullptr, nullptr, 0, z, z, -1, rts);
+            m->d_G, nullptr, nullptr, nullptr, nullptr, 0, z, z, -1, rts, 0, 0, 0);
         m->launches++;
         WD_CUDA(cudaGetLastError());
         return WD_OK;
@@ -1193,12 +1201,19 @@ int dense_apply(WdModel* m) {
     if (m->gemm_engine == WD_GEMM_BF16X3) {
         const int rts = (m->dbatch.B + 127) / 128;
         const int g = grid_for(m->dense_count / 4, 256);
-        if (m->fuse_dense)
-            dense_vec_kernel<2><<<g, 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart, m->d_G, m->d_P, m->d_S1,
-                                                          m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts);
-        else
+        if (m->fuse_dense) {
+            // part: 0 = whole arena, 1 = only the first layer's kernel (the rest was updated on a side stream), 2 = all but that kernel
+            int64_t b4 = 0, e4 = m->dense_count / 4, hlo = 0, hhi = 0;
+            if (m->dense_part && m->dense_split_tensor >= 0) {
+                const DenseTensor& t = m->dense[m->dense_split_tensor];
+                const int64_t k0 = t.off / 4, k1 = (t.off + t.count + 3) / 4;
+                if (m->dense_part == 1) { b4 = k0; e4 = k1; } else { hlo = k0; hhi = k1; }
+            }
+            dense_vec_kernel<2><<<grid_for(e4 - b4, 256), 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), e4, m->d_gpart, m->d_G, m->d_P,
+                                                                                m->d_S1, m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts, b4, hlo, hhi);
+        } else
             dense_vec_kernel<1><<<g, 256, 0, m->stream>>>(m->d_dense_desc, (int)m->dense.size(), m->dense_count / 4, m->d_gpart, m->d_G, m->d_P, m->d_S1,
-                                                          m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts);
+                                                          m->d_S2, m->d_Wsplit, m->wt_count, d, l, lin_tensor, rts, 0, 0, 0);
         m->launches++;
         WD_CUDA(cudaGetLastError());
         return WD_OK;
