@@ -30,6 +30,9 @@ JSON keys beyond the base contract:
   dtype     arithmetic of the MLP GEMMs ("bf16x3" = fp32 operands split into bf16 hi + lo, three tensor-core products, fp32
             accumulation); `parity` re-checks the engine against the oracle in this run, `strict_engine` = the same step on tf32x3
   cpu_baseline  the optimised CPU restatement (oracle/fast.py) on the host cores, same workload, bounded sample
+Before the W warm-up steps every ring slot is visited three times untimed (two eager steps + the CUDA-graph capture of that slot), so
+the timed K steps replay graphs only.  WD_STEP_TRACE=1 (N = 1) / WD_SHARD_TRACE=1 (N > 1) print a stream / flag-barrier timeline of
+one replayed step to stderr (profiles/r2_step_timelines.md).
 """
 import argparse
 import json
