@@ -38,7 +38,10 @@ enum { WD_OPT_SGD = 0, WD_OPT_ADAGRAD = 1, WD_OPT_FTRL = 2,
        WD_OPT_RMSPROP = 4  /* tf.train.RMSPropOptimizer (not centered): slots rms (init 1), momentum; touched rows only */ };
 /* activations (reference python/lib/utils/model_util.py:28-59) */
 enum { WD_ACT_RELU = 0, WD_ACT_RELU6, WD_ACT_SIGMOID, WD_ACT_TANH, WD_ACT_LEAKY_RELU, WD_ACT_ELU, WD_ACT_SELU,
-       WD_ACT_SOFTPLUS, WD_ACT_SOFTSIGN };
+       WD_ACT_SOFTPLUS, WD_ACT_SOFTSIGN,
+       WD_ACT_CRELU   /* tf.nn.crelu = concat(relu(z), relu(-z)): a hidden layer of u units feeds 2u features to whatever follows it
+                       * (dropout, batch norm, the next layers).  The parameters keep the reference's shapes — kernel [in, u], bias [u]
+                       * (wd_tensor_io / wd_tensor_size), batch-norm gamma / beta [2u]. */ };
 /* dnn_connected_mode (reference python/lib/dnn.py:92-193) */
 enum { WD_MODE_SIMPLE = 0, WD_MODE_FIRST_DENSE, WD_MODE_LAST_DENSE, WD_MODE_DENSE, WD_MODE_RESNET };
 /* GEMM engine for the MLP */

@@ -32,6 +32,7 @@ _ACT = {
     "selu": F.selu,
     "softplus": F.softplus,
     "softsign": F.softsign,
+    "crelu": lambda z: torch.cat([torch.relu(z), torch.relu(-z)], 1),     # tf.nn.crelu
 }
 
 

@@ -76,6 +76,8 @@ def act_fwd(name, z):
         return np.logaddexp(z, 0)
     if name == "softsign":
         return z / (1 + np.abs(z))
+    if name == "crelu":          # tf.nn.crelu (reference model_util.py:45-50): concat([relu(z), relu(-z)], axis=-1)
+        return np.concatenate([np.maximum(z, 0), np.maximum(-z, 0)], axis=-1)
     raise ValueError("Unsupported activation name: {}".format(name))
 
 
@@ -209,8 +211,12 @@ class OracleModel(object):
     def layer_dims(self, t):
         """[(in_dim, out_dim)] for hidden layers then logits of tower t."""
         hu, srcs = self.towers[t], layer_sources(self.modes[t], len(self.towers[t]))
-        w = lambda s: self.D0 if s == "x" else hu[s]
+        w = lambda s: self.D0 if s == "x" else self.out_width(hu[s])
         return [(sum(w(s) for s in srcs[l]), hu[l] if l < len(hu) else 1) for l in range(len(hu) + 1)]
+
+    def out_width(self, units):
+        """Features a hidden layer of `units` units hands on: tf.nn.crelu doubles them."""
+        return 2 * units if self.act == "crelu" else units
 
     # ---- init (same distributions as TF: A.7 truncated normal, A.8 glorot uniform, zeros)
     def init(self, seed=0):
@@ -240,8 +246,8 @@ class OracleModel(object):
                     P[scope + "/kernel"] = rng.uniform(-lim, lim, size=(i, o)).astype(np.float32)
                     P[scope + "/bias"] = np.zeros(o, dtype=np.float32)
                     if self.bn and l < len(dims) - 1:
-                        P[scope + "/batch_normalization/gamma"] = np.ones(o, dtype=np.float32)
-                        P[scope + "/batch_normalization/beta"] = np.zeros(o, dtype=np.float32)
+                        P[scope + "/batch_normalization/gamma"] = np.ones(self.out_width(o), dtype=np.float32)
+                        P[scope + "/batch_normalization/beta"] = np.zeros(self.out_width(o), dtype=np.float32)
         self.reset_slots()
         return self
 
@@ -397,7 +403,7 @@ class OracleModel(object):
         def scatter(dinp, sources):
             o = 0
             for s in sources:
-                wd = dX.shape[1] if s == "x" else hu[s]
+                wd = dX.shape[1] if s == "x" else self.out_width(hu[s])
                 if s == "x":
                     dX[:, :] += dinp[:, o:o + wd]
                 else:
@@ -422,7 +428,11 @@ class OracleModel(object):
                 da = dh
             if tc["D"][l] is not None:
                 da = da * tc["D"][l]                                  # d(dropout) = mask / keep_prob
-            dz = da * act_bwd(self.act, tc["Z"][l], tc["A"][l])
+            if self.act == "crelu":                                   # da is [B, 2u]: d relu(z) on the first half, d relu(-z) = -1[z < 0] on the second
+                z, u = tc["Z"][l], tc["Z"][l].shape[1]
+                dz = da[:, :u] * (z > 0) - da[:, u:] * (z < 0)
+            else:
+                dz = da * act_bwd(self.act, tc["Z"][l], tc["A"][l])
             grads[scope + "/kernel"] = tc["INP"][l].T @ dz
             grads[scope + "/bias"] = dz.sum(0)
             scatter(dz @ self.params[scope + "/kernel"].astype(A, copy=False).T, srcs[l])

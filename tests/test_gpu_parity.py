@@ -127,10 +127,59 @@ def test_log_normaliser():
     np.testing.assert_allclose(pm.deep_input(B)[:, po:po + w], cache["X"][:, lo:lo + w], rtol=2e-6, atol=1e-6)   # logf vs np.log: <= 2 ulp
 
 
-@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", "elu", "selu", "softplus", "softsign", "leaky_relu", "relu6"])
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", "elu", "selu", "softplus", "softsign", "leaky_relu", "relu6", "crelu"])
 def test_activations_train(act):
     fc, cross, model = small_conf(hidden=(32, 32), act=act)
     _train_compare(fc, cross, model, "wide_deep", steps=2, seed=5)
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tc3x", "bf16x3"])
+@pytest.mark.parametrize("mode,bn,dnn_opt", [("simple", 1, "Adagrad"), ("dense", 0, "Adam"), ("first_dense", 1, "Ftrl")])
+def test_crelu_train_parity(engine, mode, bn, dnn_opt):
+    """dnn_activation_function crelu (reference model_util.py:45-50, tf.nn.crelu = concat(relu(z), relu(-z))): a layer of u units
+    hands 2u features to dropout / batch norm / the next layers; the variables keep the reference's shapes (kernel [in, u],
+    bias [u], gamma / beta [2u]).  Forward logits, per-step losses and the trained parameters + optimizer slots against the
+    oracle (which concatenates explicitly); Adam and Ftrl move weights under a zero gradient, which the tied half must not see."""
+    fc, cross, model = small_conf(hidden=(64, 48), mode=mode, act="crelu", bn=bn, dnn_opt=dnn_opt)
+    B = 256
+    om = OM.OracleModel(fc, cross, model, "wide_deep").init(21)
+    plan = Plan(fc, cross, model, "wide_deep", max_batch=B, max_nnz=B * 64, max_keys=B * 64, gemm_engine=engine)
+    pm = WideDeepModel(plan)
+    assert plan.tensor_names["dnn/dnn_1/hiddenlayer_1/kernel"][3] == ((128 if mode == "simple" else plan.d0 + 128), 48)
+    if bn:
+        assert plan.tensor_names["dnn/dnn_1/hiddenlayer_1/batch_normalization/gamma"][3] == (96,)
+    copy_params_to_product(om, pm)
+    rng = np.random.default_rng(23)
+    tol = 1 if engine != "bf16x3" else 5
+    for step in range(3):
+        raw = random_raw_batch(fc, B, rng)
+        label = (rng.random(B) < 0.3).astype(np.float32)
+        batch = to_product_batch(plan, raw, label)
+        if step == 0:
+            logits, _ = pm.forward(batch)
+            _, cache = om.forward(raw)
+            np.testing.assert_array_less(np.abs(logits - cache["logits"]), tol * RTOL * np.maximum(np.abs(cache["logits"]), 1.0))
+        loss = pm.train_step(batch)
+        ref_loss, _ = om.train_step(raw, label)
+        assert abs(loss - ref_loss) <= tol * RTOL * max(abs(ref_loss), 1.0), "step %d loss %g vs %g" % (step, loss, ref_loss)
+    ptol = 2e-4 if engine != "bf16x3" else 2e-3
+    slot_keys = {"adagrad": ["acc"], "ftrl": ["n", "z"], "adam": ["m", "v"]}[plan.dnn_opt["kind"]]
+    for name in pm.tensor_names():
+        checks = [(0, None)]
+        if name.startswith("dnn/dnn_1/"):
+            checks += [(i + 1, k) for i, k in enumerate(slot_keys)]
+        for slot, key in checks:
+            got = pm.get_tensor(name, slot=slot)
+            exp = om.params[name] if key is None else om.slots[name][key]
+            assert got.shape == exp.shape, name
+            scale = max(float(np.abs(exp).max()), 1e-3)
+            bad = np.abs(got - exp) > ptol * scale
+            assert bad.mean() <= (0.0 if engine != "bf16x3" else 2e-2), "%s slot %d: %g of the tensor off, max %g (scale %g)" % (
+                name, slot, bad.mean(), np.max(np.abs(got - exp)), scale)
+    # a fresh handle initialises the tied halves too: its first forward is finite and its kernels have the variable's shape
+    pm2 = WideDeepModel(plan).init(3)
+    assert pm2.get_tensor("dnn/dnn_1/hiddenlayer_0/kernel").shape == (plan.d0, 64)
+    assert np.isfinite(pm2.forward(batch)[0]).all()
 
 
 @pytest.mark.parametrize("mode", ["simple", "first_dense", "last_dense", "dense", "resnet"])

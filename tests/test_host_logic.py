@@ -78,6 +78,27 @@ def test_optimizer_parsing():
         parse_optimizer("tf.train.MomentumOptimizer(0.1, 0.9)", 0.1)
 
 
+def test_crelu_shapes_match_oracle_and_all_ten_activation_names_parse():
+    """The reference's ten activation names (model_util.py:28-59) are all accepted; crelu doubles what a layer hands on while its
+    kernel / bias keep the conf's units (tf.layers.dense(units=u, activation=tf.nn.crelu) + batch_normalization over 2u)."""
+    from oracle.model import OracleModel
+    from tests.test_gpu_parity import small_conf
+    from wide_deep_b200.plan import ACTS, Plan
+    assert sorted(ACTS) == sorted(["sigmoid", "tanh", "relu", "relu6", "leaky_relu", "crelu", "elu", "selu", "softplus", "softsign"])
+    for mode in ["simple", "first_dense", "last_dense", "dense", "resnet"]:
+        hidden = (32, 32, 32) if mode == "resnet" else (64, 48, 16)
+        fc, cross, model = small_conf(hidden=hidden, mode=mode, act="crelu", bn=1)
+        p = Plan(fc, cross, model, "wide_deep", max_batch=8)
+        om = OracleModel(fc, cross, model, "wide_deep").init(0)
+        shapes = {k: tuple(v[3]) for k, v in p.tensor_names.items() if k.startswith("dnn/dnn_1/")}
+        assert shapes == {k: v.shape for k, v in om.params.items() if k.startswith("dnn/dnn_1/")}, mode
+        assert shapes["dnn/dnn_1/hiddenlayer_0/kernel"] == (p.d0, hidden[0])
+        assert shapes["dnn/dnn_1/hiddenlayer_0/batch_normalization/gamma"] == (2 * hidden[0],)
+    with pytest.raises(ValueError):
+        small = small_conf(act="swish")
+        Plan(small[0], small[1], small[2], "wide_deep", max_batch=8)
+
+
 def test_layer_sources_match_oracle():
     from oracle.model import layer_sources as o_src
     from wide_deep_b200.plan import Plan

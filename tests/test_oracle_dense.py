@@ -65,7 +65,8 @@ def torch_forward(om, raw, P, drop_step=None):
             H = []
             pick = lambda s: x if s == "x" else H[s]
             act = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "elu": torch.nn.functional.elu,
-                   "softplus": torch.nn.functional.softplus}[om.act]
+                   "softplus": torch.nn.functional.softplus,
+                   "crelu": lambda z: torch.cat([torch.relu(z), torch.relu(-z)], 1)}[om.act]        # tf.nn.crelu
             for l in range(len(hu)):
                 sc = "dnn/dnn_%d/hiddenlayer_%d" % (t + 1, l)
                 inp = torch.cat([pick(s) for s in srcs[l]], 1)
@@ -83,7 +84,7 @@ def torch_forward(om, raw, P, drop_step=None):
 
 
 @pytest.mark.parametrize("mode,act", [("simple", "relu"), ("dense", "tanh"), ("resnet", "sigmoid"), ("first_dense", "elu"),
-                                      ("last_dense", "softplus")])
+                                      ("last_dense", "softplus"), ("simple", "crelu"), ("dense", "crelu")])
 def test_oracle_logits_and_grads_match_torch(mode, act):
     fc, cross, model = conf(mode, act)
     rng = np.random.default_rng(4)

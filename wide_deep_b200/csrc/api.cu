@@ -169,7 +169,10 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
     m->col_ind_off.assign(d->col_ind_off, d->col_ind_off + C);
     m->n_numeric = d->n_numeric;
     m->d0_phys = d->d0_phys; m->wide_rows = d->wide_rows;
-    m->activation = d->activation; m->batch_norm = d->batch_norm;
+    // crelu(z) = [relu(z) | relu(-z)]: the layer is built twice as wide with relu, its kernel / bias columns n + u tied to minus
+    // columns n (exact: every product and sum just changes sign); see crelu_fold / crelu_mirror in mlp.cu
+    m->crelu = d->activation == WD_ACT_CRELU;
+    m->activation = m->crelu ? WD_ACT_RELU : d->activation; m->batch_norm = d->batch_norm;
     m->dropout_rate = d->dropout_rate; m->dropout_seed = d->dropout_seed;
     if (!(m->dropout_rate >= 0.f && m->dropout_rate < 1.f)) { set_error("dnn_dropout %g outside [0, 1)", m->dropout_rate); return WD_EINVAL; }
     m->lin_opt = d->lin_opt; m->dnn_opt = d->dnn_opt;
@@ -393,6 +396,8 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
             tw.n_hidden = d->tower_nlayers[t]; tw.mode = d->tower_mode[t];
             std::vector<int> hu(d->hidden_units + hu_off, d->hidden_units + hu_off + tw.n_hidden);
             hu_off += tw.n_hidden;
+            const std::vector<int> units = hu;                         // the conf's units per layer
+            if (m->crelu) for (int& h : hu) h *= 2;                    // features a layer hands on
             auto srcs = layer_sources(tw.mode, tw.n_hidden);
             for (int l = 0; l <= tw.n_hidden; ++l) {
                 Layer L{};
@@ -413,6 +418,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                 const bool hidden = l < tw.n_hidden;
                 L.N = hidden ? hu[l] : 1;
                 L.N_phys = hidden ? pad_to(hu[l], 32) : 1;
+                L.N_param = hidden ? units[l] : 1;
                 L.t_gamma = L.t_beta = -1;
                 L.h_fp32 = false;
                 for (int src : srcs[tw.n_hidden]) if (src == l) L.h_fp32 = true;      // read by the logits layer
@@ -430,6 +436,7 @@ static int build_model(const WdPlanDesc* d, WdModel* m, WdModelExtra* x) {
                     }
                     L.t_kernel = add_dense(L.K_phys, L.N_phys, L.wgrad_splits, 0, (int64_t)L.K_phys * L.N_phys, true);
                     L.t_bias = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
+                    if (m->crelu) m->dense[L.t_kernel].mirror_u = m->dense[L.t_bias].mirror_u = L.N_param;
                     if (m->batch_norm) {
                         L.t_gamma = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
                         L.t_beta = add_dense(1, L.N_phys, m->row_tiles, 1, L.N_phys, false);
@@ -573,13 +580,17 @@ static int init_dense(WdModel* m, WdModelExtra* x, uint64_t seed) {
         for (int l = 0; l <= tw.n_hidden; ++l) {
             Layer& L = tw.layers[l];
             const DenseTensor& tk = m->dense[L.t_kernel];
-            const float lim = std::sqrt(6.f / (float)(L.K + L.N));
+            const float lim = std::sqrt(6.f / (float)(L.K + L.N_param));          // glorot_uniform over the variable's shape [K, N_param]
             for (int s = 0; s < L.n_in_segs; ++s) {
                 const Seg& sg = L.segs[s];
                 for (int j = 0; j < sg.width_phys; ++j) {
                     bool real = sg.src < 0 ? (x->x0_real[j] != 0) : (j < sg.width);
                     if (!real) continue;
-                    for (int n = 0; n < L.N; ++n) P[tk.off + (int64_t)(sg.k_off + j) * L.N_phys + n] = lim * U(rng);
+                    float* prow = &P[tk.off + (int64_t)(sg.k_off + j) * L.N_phys];
+                    for (int n = 0; n < L.N_param; ++n) {
+                        prow[n] = lim * U(rng);
+                        if (tk.mirror_u) prow[n + tk.mirror_u] = -prow[n];
+                    }
                 }
             }
             if (L.t_gamma >= 0) for (int n = 0; n < L.N; ++n) P[m->dense[L.t_gamma].off + n] = 1.f;
@@ -634,7 +645,7 @@ extern "C" int64_t wd_tensor_size(WdModel* m, int kind, int index, int sub) {
         int di;
         if (resolve_dense(m, x, index, sub, &di)) return WD_EINVAL;
         Layer& L = m->towers[x->did_tower[index]].layers[x->did_layer[index]];
-        return sub == WD_D_KERNEL ? (int64_t)L.K * L.N : L.N;
+        return sub == WD_D_KERNEL ? (int64_t)L.K * L.N_param : (sub == WD_D_BIAS ? L.N_param : L.N);
     }
     return WD_EINVAL;
 }
@@ -692,16 +703,25 @@ extern "C" int wd_tensor_io(WdModel* m, int kind, int index, int sub, int slot, 
             for (int j = 0; j < sg.width_phys; ++j) {
                 bool real = sg.src < 0 ? (x->x0_real[j] != 0) : (j < sg.width);
                 if (!real) continue;
-                for (int n = 0; n < L.N; ++n) {
+                for (int n = 0; n < L.N_param; ++n) {
                     float& pv = phys[(int64_t)(sg.k_off + j) * L.N_phys + n];
-                    if (to_device) pv = h[lk * L.N + n]; else h[lk * L.N + n] = pv;
+                    if (to_device) {
+                        pv = h[lk * L.N_param + n];
+                        if (t.mirror_u) (&pv)[t.mirror_u] = slot == 0 ? -pv : pv;       // tied half: minus the weight, same slot value
+                    } else h[lk * L.N_param + n] = pv;
                 }
                 ++lk;
             }
         }
         if (lk != L.K) { set_error("internal: logical K mismatch %lld vs %d", (long long)lk, L.K); return WD_ESTATE; }
     } else {
-        for (int n = 0; n < L.N; ++n) { if (to_device) phys[n] = h[n]; else h[n] = phys[n]; }
+        const int nn = sub == WD_D_BIAS ? L.N_param : L.N;
+        for (int n = 0; n < nn; ++n) {
+            if (to_device) {
+                phys[n] = h[n];
+                if (t.mirror_u) phys[n + t.mirror_u] = slot == 0 ? -h[n] : h[n];
+            } else h[n] = phys[n];
+        }
     }
     if (to_device) {
         // all copies go through the model stream: a pageable cudaMemcpy on the NULL stream may still be in flight when a
@@ -951,7 +971,7 @@ static int backward_core(WdModel* m) {
     // single-GPU fused step with the wide list on its side stream: the dense optimizer of everything but the first layer's kernel
     // runs there (after the wide rows' updates), under that kernel's weight-gradient GEMM
     m->dense_split_tensor = -1;
-    m->record_wgrad_rest = m->fuse_dense && m->side_active[1] && m->gemm_engine == WD_GEMM_BF16X3 && !m->timer.enabled;
+    m->record_wgrad_rest = m->fuse_dense && m->side_active[1] && m->gemm_engine == WD_GEMM_BF16X3 && !m->timer.enabled && !m->crelu;
     if ((rc = mlp_backward(m))) return rc;
     m->record_dx0 = false;
     m->record_wgrad_rest = false;

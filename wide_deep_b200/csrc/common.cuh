@@ -101,6 +101,7 @@ struct DenseTensor {         // one trainable dense tensor inside the dense aren
     int g_rowtiles;          // 1: partials are per 128-row batch tile (only the tiles of the current batch are live)
     int64_t gstride;
     int64_t wt_off;          // offset of the transposed copy in the wt buffer, -1 if none
+    int mirror_u;            // crelu layers (kernel, bias): column n + mirror_u holds minus column n, n < mirror_u (0: plain tensor)
 };
 
 struct Seg {                 // one source of a layer input
@@ -115,6 +116,7 @@ struct Layer {
     Seg segs[kMaxSegs];
     int K, K_phys;           // logical / physical input width
     int N, N_phys;           // logical / physical output width (1 for logits)
+    int N_param;             // logical columns of kernel / bias: N, or N / 2 for a crelu layer (the other half mirrors them)
     int t_kernel, t_bias, t_gamma, t_beta;   // indices into Model::dense (-1 if absent)
     int wgrad_splits;        // split-K factor of this layer's weight gradient (= gparts of its kernel tensor)
     // activations (hidden layers only), all [max_batch_pad, N_phys] unless noted
@@ -258,6 +260,8 @@ struct WdModel {
     cudaStream_t sstream[2] = {nullptr, nullptr};
     cudaStream_t stream_up = nullptr;        // host->device refills of batch slots (wd_batch_prefetch_slot), overlapping the running step
     cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr, ev_wide_fwd = nullptr, ev_wgrad_rest = nullptr;
+    bool crelu = false;                          // dnn_activation_function crelu: relu on mirrored kernels (mlp.cu crelu_fold / crelu_mirror)
+    bool list_apply_fused[2] = {false, false};   // this step's rows of the list were updated by its gradient-sum / combine launches (sparse.cu)
     bool record_wgrad_rest = false;           // mlp_backward: record ev_wgrad_rest before the first layer's weight gradient
     int dense_split_tensor = -1, dense_part = 0;   // dense_apply: see mlp.cu (single-GPU step, split dense optimizer)
     cudaEvent_t ev_grouped[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -414,6 +418,10 @@ int metrics_finish(WdModel* m, double* out10);
 
 int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n);   // sort.cu
 int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out);   // sort.cu (in place, n known on host)
+int seg_heads(WdModel* m, const int32_t* d_n, const uint32_t* keys, uint32_t invalid, int32_t* pos, int64_t cap, int32_t* ustart, uint32_t* urow,
+              int32_t* d_nuniq);                                                    // sort.cu: unique rows of sorted keys (2 launches)
+int chunk_offsets(WdModel* m, const int32_t* d_nuniq, const int32_t* ustart, uint32_t* urow, int32_t* choff, int64_t cap, int chunk,
+                  int32_t* d_nchunks);                                              // sort.cu: hot-row chunk layout (2 launches)
 
 template <typename T>
 int dev_alloc(WdModel* m, T** p, int64_t count, bool zero = true) {

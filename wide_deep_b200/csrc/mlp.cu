@@ -1174,9 +1174,57 @@ int mlp_backward(WdModel* m) {
     return WD_OK;
 }
 
+// ---- crelu layers (reference python/lib/utils/model_util.py:45-50, tf.nn.crelu): built as relu layers of twice the width whose
+// kernel / bias columns n + u hold minus columns n.  The backward leaves gradients for both halves; the variable's gradient is their
+// difference (d/dW of [xW | -xW]).  crelu_fold puts it into the first half of every live partial and zeroes the second half, so the
+// reduction, the exchange and the optimizer kernels see a plain tensor; crelu_mirror re-derives the tied half (parameter negated,
+// optimizer slots copied) and refreshes the GEMM operand copies after the optimizer.
+__global__ void crelu_fold_kernel(float* __restrict__ gp, int parts, int64_t gstride, int rows, int cols, int u) {
+    const int64_t total = (int64_t)parts * rows * u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % u);
+        const int64_t pr = i / u;
+        float* q = gp + (pr / rows) * gstride + (pr % rows) * cols + n;
+        q[0] -= q[u];
+        q[u] = 0.f;
+    }
+}
+__global__ void crelu_mirror_kernel(float* __restrict__ P, float* __restrict__ S1, float* __restrict__ S2, int rows, int cols, int u) {
+    const int64_t total = (int64_t)rows * u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = (i / u) * cols + i % u;
+        P[e + u] = -P[e];
+        S1[e + u] = S1[e];
+        S2[e + u] = S2[e];
+    }
+}
+static int crelu_fold(WdModel* m) {
+    const int rts = (m->dbatch.B + 127) / 128;
+    for (const DenseTensor& t : m->dense) {
+        if (!t.mirror_u) continue;
+        const int parts = t.g_rowtiles ? rts : t.gparts;
+        crelu_fold_kernel<<<grid_for((int64_t)parts * t.rows * t.mirror_u, 256), 256, 0, m->stream>>>(m->d_gpart + t.gpart_off, parts, t.gstride, t.rows, t.cols,
+                                                                                                    t.mirror_u);
+        m->launches++;
+    }
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+static int crelu_mirror(WdModel* m) {
+    for (const DenseTensor& t : m->dense) {
+        if (!t.mirror_u) continue;
+        crelu_mirror_kernel<<<grid_for((int64_t)t.rows * t.mirror_u, 256), 256, 0, m->stream>>>(m->d_P + t.off, m->d_S1 + t.off, m->d_S2 + t.off, t.rows, t.cols,
+                                                                                              t.mirror_u);
+        m->launches++;
+    }
+    WD_CUDA(cudaGetLastError());
+    return dense_refresh_transposes(m);
+}
+
 int dense_reduce_grads(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
     const int rts = (m->dbatch.B + 127) / 128;
+    if (m->crelu) { int rc = crelu_fold(m); if (rc) return rc; }
     if (m->gemm_engine == WD_GEMM_BF16X3) {
         if (m->fuse_dense) return WD_OK;                              // single-GPU step: reduced inside dense_apply's kernel
         OptParamsD z{};
@@ -1193,7 +1241,7 @@ int dense_reduce_grads(WdModel* m) {
     return WD_OK;
 }
 
-int dense_apply(WdModel* m) {
+static int dense_apply_plain(WdModel* m) {
     if (m->dense_count == 0) return WD_OK;
     OptParamsD d = make_opt_d(m->dnn_opt, m->d_bpow + 2);
     OptParamsD l = make_opt_d(m->lin_opt, m->d_bpow);
@@ -1223,6 +1271,13 @@ int dense_apply(WdModel* m) {
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
+}
+
+// optimizer of the dense arena (+ the tied halves of crelu layers)
+int dense_apply(WdModel* m) {
+    int rc = dense_apply_plain(m);
+    if (!rc && m->crelu && m->dense_count > 0) rc = crelu_mirror(m);
+    return rc;
 }
 
 }  // namespace wd

@@ -111,12 +111,124 @@ int exclusive_scan_i32(WdModel* m, int32_t* data, int64_t n, int32_t* total_out)
     return WD_OK;
 }
 
+// ------------------------------------------------------------------------- fused scans of the grouping stage
+// The two scans of the grouping stage take their input from a formula instead of an array, and the first one's add pass is also
+// the compaction: 4 launches where (flag kernel, scan, scan-add, compact kernel, chunk-count kernel, scan, scan-add) were 7.
+//   GEN 0: value(i) = 1 where the sorted key i starts a new valid segment (segment heads -> unique rows)
+//   GEN 1: value(u) = chunks of unique row u if it is a multi-chunk (hot) row, else 0; also pads urow[u >= nuniq] with kInvalidRow
+struct ScanGen { const int32_t* d_n; const uint32_t* keys; uint32_t invalid; const int32_t* ustart; uint32_t* urow; int chunk; };
+template <int GEN>
+__device__ __forceinline__ int scan_gen_value(const ScanGen& g, int64_t i, int n) {
+    if (GEN == 0) {
+        if (i >= n) return 0;
+        const uint32_t k = g.keys[i];
+        return (k != g.invalid && (i == 0 || g.keys[i - 1] != k)) ? 1 : 0;
+    }
+    if (i < n) {
+        const int len = g.ustart[i + 1] - g.ustart[i];
+        return len > g.chunk ? (len + g.chunk - 1) / g.chunk : 0;
+    }
+    g.urow[i] = kInvalidRow;
+    return 0;
+}
+template <int GEN>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_gen_chunks_kernel(ScanGen g, int32_t* data, int64_t cap, int32_t* chunk_sums, int32_t* counter) {
+    __shared__ int sm[33];
+    __shared__ bool is_last;
+    const int n = *g.d_n;
+    int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < cap) ? scan_gen_value<GEN>(g, base + i, n) : 0;
+        s += v[i];
+    }
+    int tot;
+    int ex = block_excl_scan(s, sm, &tot);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < cap) data[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) {
+        chunk_sums[blockIdx.x] = tot;
+        __threadfence();
+        int t = atomicAdd(counter, 1);
+        is_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    int carry = 0;
+    for (int off = 0; off < (int)gridDim.x; off += SCAN_THREADS) {
+        int i = off + threadIdx.x;
+        int x = i < (int)gridDim.x ? ((volatile int32_t*)chunk_sums)[i] : 0;
+        int t2;
+        int e = block_excl_scan(x, sm, &t2);
+        if (i < (int)gridDim.x) chunk_sums[i] = e + carry;
+        carry += t2;
+    }
+    if (threadIdx.x == 0) {
+        chunk_sums[gridDim.x] = carry;
+        *counter = 0;
+    }
+}
+// add pass of the segment-head scan + compaction: head i goes to slot pos(i) of (ustart, urow); the end of the last valid segment
+// closes the list; *d_nuniq = number of heads
+__global__ void __launch_bounds__(SCAN_THREADS) seg_add_compact_kernel(ScanGen g, const int32_t* __restrict__ pos, const int32_t* __restrict__ chunk_sums,
+                                                                       int nchunks, int32_t* __restrict__ ustart, uint32_t* __restrict__ urow,
+                                                                       int32_t* __restrict__ d_nuniq) {
+    const int n = *g.d_n;
+    const int add = chunk_sums[blockIdx.x], total = chunk_sums[nchunks];
+    int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int64_t i = base + j;
+        if (i >= n) continue;
+        const uint32_t k = g.keys[i];
+        if (k == g.invalid) continue;
+        if (i == 0 || g.keys[i - 1] != k) {
+            const int p = pos[i] + add;
+            ustart[p] = (int32_t)i;
+            urow[p] = k;
+        }
+        if (i == n - 1 || g.keys[i + 1] == g.invalid) ustart[total] = (int32_t)i + 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nuniq = total;
+}
+
+// unique rows of the sorted keys: (ustart, urow, *d_nuniq); `pos` = scratch of `cap` ints
+int seg_heads(WdModel* m, const int32_t* d_n, const uint32_t* keys, uint32_t invalid, int32_t* pos, int64_t cap, int32_t* ustart, uint32_t* urow,
+              int32_t* d_nuniq) {
+    int nchunks = (int)((cap + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (nchunks < 1) nchunks = 1;
+    int32_t* sums = (int32_t*)m->d_scan_tmp_s[m->scratch_sel];
+    const ScanGen g{d_n, keys, invalid, nullptr, nullptr, 0};
+    scan_gen_chunks_kernel<0><<<nchunks, SCAN_THREADS, 0, m->stream>>>(g, pos, cap, sums, m->d_sort_counter_s[m->scratch_sel]);
+    seg_add_compact_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(g, pos, sums, nchunks, ustart, urow, d_nuniq);
+    m->launches += 2;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+// hot-row chunk layout: choff = exclusive scan of the chunk counts of the unique rows (0 for rows summed directly), choff[cap] and
+// *d_nchunks = total; pads urow beyond the unique rows with kInvalidRow
+int chunk_offsets(WdModel* m, const int32_t* d_nuniq, const int32_t* ustart, uint32_t* urow, int32_t* choff, int64_t cap, int chunk, int32_t* d_nchunks) {
+    int nchunks = (int)((cap + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (nchunks < 1) nchunks = 1;
+    int32_t* sums = (int32_t*)m->d_scan_tmp_s[m->scratch_sel];
+    const ScanGen g{d_nuniq, nullptr, 0u, ustart, urow, chunk};
+    scan_gen_chunks_kernel<1><<<nchunks, SCAN_THREADS, 0, m->stream>>>(g, choff, cap, sums, m->d_sort_counter_s[m->scratch_sel]);
+    scan_add_kernel<<<nchunks, SCAN_THREADS, 0, m->stream>>>(choff, cap, sums, nchunks, d_nchunks);
+    m->launches += 2;
+    WD_CUDA(cudaGetLastError());
+    return WD_OK;
+}
+
 // ------------------------------------------------------------------------------------------ radix sort
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS_PER_WARP = kSortTile / RS_WARPS;  // 4 rounds of 32
 constexpr int RS_TILE = kSortTile;                       // 1024 keys per tile: short blocks, enough of them to fill the SMs
-constexpr int RS_MAX_BINS = 1024;
 
 // Per-tile digit histogram -> hist[tile * bins + bin] (tile-major, coalesced) and global per-bin totals gtot[bin].
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,

@@ -421,83 +421,50 @@ __global__ void sort_keys_kernel(const int32_t* __restrict__ d_nnz, const uint32
     }
 }
 
-// flags[i] = 1 if sorted key i starts a new valid segment; counts valid entries
-__global__ void seg_flag_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ keys, uint32_t invalid,
-                                int32_t* flags, int64_t cap) {
-    int n = *d_nnz;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
-        int f = 0;
-        if (i < n) {
-            uint32_t k = keys[i];
-            f = (k != invalid && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
-        }
-        flags[i] = f;
-    }
-}
 
-// after the exclusive scan of flags (pos = flags): scatter segment starts and unique rows; segment end sentinel
-__global__ void seg_compact_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ keys, uint32_t invalid,
-                                   const int32_t* __restrict__ pos, int32_t* ustart, uint32_t* urow,
-                                   const int32_t* __restrict__ d_nuniq) {
-    int n = *d_nnz;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t k = keys[i];
-        bool head = (k != invalid && (i == 0 || keys[i - 1] != k));
-        if (head) {
-            ustart[pos[i]] = i;
-            urow[pos[i]] = k;
-        }
-        // the first invalid entry (or n) terminates the last valid segment
-        bool last_valid = (k != invalid) && (i == n - 1 || keys[i + 1] == invalid);
-        if (last_valid) ustart[*d_nuniq] = i + 1;
-    }
-}
 
 // ---- per unique row: g = ordered sum of its occurrences' gradients.
 // Rows touched at most kChunk times are summed by one lane group directly.  Hotter rows (small tables,
 // skewed ids) are split into chunks of kChunk occurrences that are summed in parallel and then combined in
 // chunk order, so the result stays deterministic and no single group walks thousands of occurrences.
 
-// mch[u] = number of chunks of a multi-chunk row, 0 for rows summed directly (and for u >= nuniq)
-// (also pads the unique-row list with kInvalidRow up to its capacity, so fixed-size exchanges need no host-side count)
-__global__ void chunk_count_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ ustart, int32_t* mch, uint32_t* urow, int64_t cap) {
-    const int nu = *d_nuniq;
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += (int64_t)gridDim.x * blockDim.x) {
-        int v = 0;
-        if (u < nu) {
-            int len = ustart[u + 1] - ustart[u];
-            if (len > kChunk) v = (len + kChunk - 1) / kChunk;
-        } else {
-            urow[u] = kInvalidRow;
-        }
-        mch[u] = v;
-    }
-}
 
 
 // embedding rows: contribution of occurrence j = dX0[b, x0_off : x0_off + dim] / bag_size(b, column)
-// 8 lanes per work item, each lane covers float4 chunks lig, lig+8, ... of the row
-template <bool CHUNKED>
-__global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nitems, const int32_t* __restrict__ d_nuniq,
+// 8 lanes per work item, each lane covers float4 chunks lig, lig+8, ... of the row.  One launch covers both kinds of work item:
+// items [0, nu) are the unique rows (summed directly into ugrad unless they are hot), items [nu, nu + nchunks) are the chunks of
+// the hot rows (summed into cpart, combined afterwards by chunk_combine_kernel).
+// APPLY (single-GPU step, row-local optimizer): the optimizer update of a directly summed row follows its sum in the same thread —
+// the summed gradient never reaches memory; the hot rows are updated by chunk_combine_kernel<1>.
+struct RowApply { const uint32_t* urow; float* const* tab_data; const int32_t* tab_stride; const int64_t* tab_row_base; OptParams o; };
+template <bool APPLY>
+__global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ d_nchunks,
                                                            const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
                                                            const uint32_t* __restrict__ svals,
                                                            const int32_t* __restrict__ e_bc, const int32_t* __restrict__ offs,
                                                            int C, const int32_t* __restrict__ col_table,
                                                            const int32_t* __restrict__ tab_dim, const int32_t* __restrict__ tab_x0,
-                                                           const float* __restrict__ dX0, int ld, float* __restrict__ out, int width) {
+                                                           const float* __restrict__ dX0, int ld, float* __restrict__ ugrad,
+                                                           float* __restrict__ cpart, int width, RowApply ra) {
     const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
-    const int nitems = *d_nitems, nu = *d_nuniq;
+    const int nu = *d_nuniq;
+    const int64_t nitems = (int64_t)nu + *d_nchunks;
     const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
     const int64_t gstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 4;
     for (int64_t it = g0; it < nitems; it += gstep) {
         int s, e;
-        if (!CHUNKED) {
+        float* out;
+        const bool direct = it < nu;
+        if (direct) {
             s = ustart[it]; e = ustart[it + 1];
-            if (e - s > kChunk) continue;                     // summed by the chunked pass
+            if (e - s > kChunk) continue;                     // hot row: summed chunk by chunk below
+            out = ugrad + it * width;
         } else {
-            int u = chunk_owner(choff, nu, (int)it);
-            s = ustart[u] + ((int)it - choff[u]) * kChunk;
+            const int c = (int)(it - nu);
+            const int u = chunk_owner(choff, nu, c);
+            s = ustart[u] + (c - choff[u]) * kChunk;
             e = min(ustart[u + 1], s + kChunk);
+            out = cpart + (int64_t)c * width;
         }
         int bc0 = e_bc[svals[s]];
         int t = col_table[bc0 % C];
@@ -525,7 +492,25 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
                     acc.x += v.x * inv; acc.y += v.y * inv; acc.z += v.z * inv; acc.w += v.w * inv;
                 }
             }
-            *reinterpret_cast<float4*>(out + (int64_t)it * width + q * 4) = acc;
+            if (APPLY && direct) {
+                if (q * 4 < dim) {
+                    const int stride = ra.tab_stride[t];
+                    float* rec = ra.tab_data[t] + ((int64_t)ra.urow[it] - ra.tab_row_base[t]) * stride;
+                    const int nslots = stride / dim - 1;
+                    float4 w = *reinterpret_cast<float4*>(rec + q * 4);
+                    float4 s1 = nslots >= 1 ? *reinterpret_cast<float4*>(rec + dim + q * 4) : make_float4(0, 0, 0, 0);
+                    float4 s2 = nslots >= 2 ? *reinterpret_cast<float4*>(rec + 2 * dim + q * 4) : make_float4(0, 0, 0, 0);
+                    opt_update(ra.o, acc.x, w.x, s1.x, s2.x);
+                    opt_update(ra.o, acc.y, w.y, s1.y, s2.y);
+                    opt_update(ra.o, acc.z, w.z, s1.z, s2.z);
+                    opt_update(ra.o, acc.w, w.w, s1.w, s2.w);
+                    *reinterpret_cast<float4*>(rec + q * 4) = w;
+                    if (nslots >= 1) *reinterpret_cast<float4*>(rec + dim + q * 4) = s1;
+                    if (nslots >= 2) *reinterpret_cast<float4*>(rec + 2 * dim + q * 4) = s2;
+                }
+            } else {
+                *reinterpret_cast<float4*>(out + q * 4) = acc;
+            }
         }
     }
 }
@@ -535,8 +520,17 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
 // tree adds the group sums, so the result does not depend on scheduling.  Hot rows are neighbours in row order (they are the
 // rows of the small tables), so a warp takes every NW-th group of rows (lane l of warp w checks row (it * 32 + l) * NW + w):
 // neighbouring hot rows land in different warps and their long chunk lists are walked concurrently, not one after the other.
+// KIND 0: the sum goes to ugrad.  KIND 1 / 2 (single-GPU step, row-local optimizer): the hot row's optimizer update follows its
+// sum here (1: embedding record, width a power of two in [4, 128]; 2: wide record, width 1) — together with the APPLY variants of
+// the gradient-sum kernels this leaves no separate optimizer launch for the list.
+struct HotApply {
+    const uint32_t* urow; int ntab; const int64_t* tab_row_base; float* const* tab_data; const int32_t* tab_dim; const int32_t* tab_stride;   // KIND 1 (tables in row order)
+    float4* wide;                                                                                                                          // KIND 2
+    OptParams o;
+};
+template <int KIND>
 __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ choff,
-                                                            const float* __restrict__ cpart, float* __restrict__ ugrad, int width) {
+                                                            const float* __restrict__ cpart, float* __restrict__ ugrad, int width, HotApply ha) {
     const int nu = *d_nuniq;
     const int lane = threadIdx.x & 31;
     const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -549,7 +543,7 @@ __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __res
             const int src = __ffs(multi) - 1;
             multi &= multi - 1;
             const int b0 = __shfl_sync(0xffffffffu, c0, src), b1 = __shfl_sync(0xffffffffu, c1, src);
-            const int64_t urow = (it * 32 + src) * nw + w0;
+            const int64_t uu = (it * 32 + src) * nw + w0;          // the unique row being combined
             const int G = width >> 2;
             if (width >= 4 && (G & (G - 1)) == 0 && G <= 32) {
                 // G lanes cover one chunk's row (float4 each), 32/G chunks in flight per step, 4 steps unrolled;
@@ -575,40 +569,80 @@ __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __res
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
                     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
                 }
-                if (cg == 0) *reinterpret_cast<float4*>(ugrad + urow * width + lq * 4) = acc;
+                if (KIND == 1) {
+                    if (cg == 0) {
+                        const int64_t row = ha.urow[uu];
+                        int lo = 0, hi = ha.ntab - 1;               // table of this global row (tables are few: binary search)
+                        while (lo < hi) {
+                            int mid = (lo + hi + 1) >> 1;
+                            if (ha.tab_row_base[mid] <= row) lo = mid; else hi = mid - 1;
+                        }
+                        const int dim = ha.tab_dim[lo], stride = ha.tab_stride[lo];
+                        if (lq * 4 < dim) {
+                            float* rec = ha.tab_data[lo] + (row - ha.tab_row_base[lo]) * stride;
+                            const int nslots = stride / dim - 1;
+                            float4 w = *reinterpret_cast<float4*>(rec + lq * 4);
+                            float4 s1 = nslots >= 1 ? *reinterpret_cast<float4*>(rec + dim + lq * 4) : make_float4(0, 0, 0, 0);
+                            float4 s2 = nslots >= 2 ? *reinterpret_cast<float4*>(rec + 2 * dim + lq * 4) : make_float4(0, 0, 0, 0);
+                            opt_update(ha.o, acc.x, w.x, s1.x, s2.x);
+                            opt_update(ha.o, acc.y, w.y, s1.y, s2.y);
+                            opt_update(ha.o, acc.z, w.z, s1.z, s2.z);
+                            opt_update(ha.o, acc.w, w.w, s1.w, s2.w);
+                            *reinterpret_cast<float4*>(rec + lq * 4) = w;
+                            if (nslots >= 1) *reinterpret_cast<float4*>(rec + dim + lq * 4) = s1;
+                            if (nslots >= 2) *reinterpret_cast<float4*>(rec + 2 * dim + lq * 4) = s2;
+                        }
+                    }
+                } else if (cg == 0) *reinterpret_cast<float4*>(ugrad + uu * width + lq * 4) = acc;
             } else {
                 for (int q = 0; q < width; ++q) {
                     float acc = 0.f;
                     for (int c = b0 + lane; c < b1; c += 32) acc += cpart[(int64_t)c * width + q];
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                    if (lane == 0) ugrad[urow * width + q] = acc;
+                    if (lane == 0) {
+                        if (KIND == 2) {                            // width == 1
+                            float4 r = ha.wide[ha.urow[uu]];
+                            opt_update(ha.o, acc, r.x, r.y, r.z);
+                            ha.wide[ha.urow[uu]] = r;
+                        } else ugrad[uu * width + q] = acc;
+                    }
                 }
             }
         }
     }
 }
 
-// wide rows: contribution of occurrence j = dlogit[b]; one thread per work item
-template <bool CHUNKED>
-__global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nitems, const int32_t* __restrict__ d_nuniq,
+// wide rows: contribution of occurrence j = dlogit[b]; one thread per work item.  Items [0, nu) = unique rows (hot ones skipped),
+// items [nu, nu + nchunks) = chunks of the hot rows, as in emb_grad_sum_kernel; APPLY: record {w, s1, s2, -} updated in place.
+template <bool APPLY>
+__global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ d_nchunks,
                                      const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
                                      const uint32_t* __restrict__ svals, const int32_t* __restrict__ e_bc, int C,
-                                     const float* __restrict__ dlogit, float* __restrict__ out) {
-    const int nitems = *d_nitems, nu = *d_nuniq;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+                                     const float* __restrict__ dlogit, float* __restrict__ ugrad, float* __restrict__ cpart,
+                                     const uint32_t* __restrict__ urow, float4* __restrict__ wide, OptParams o) {
+    const int nu = *d_nuniq;
+    const int64_t nitems = (int64_t)nu + *d_nchunks;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += (int64_t)gridDim.x * blockDim.x) {
         int s, e;
-        if (!CHUNKED) {
+        const bool direct = it < nu;
+        if (direct) {
             s = ustart[it]; e = ustart[it + 1];
             if (e - s > kChunk) continue;
         } else {
-            int u = chunk_owner(choff, nu, it);
-            s = ustart[u] + (it - choff[u]) * kChunk;
+            const int c = (int)(it - nu);
+            const int u = chunk_owner(choff, nu, c);
+            s = ustart[u] + (c - choff[u]) * kChunk;
             e = min(ustart[u + 1], s + kChunk);
         }
         float acc = 0.f;
         for (int j = s; j < e; ++j) acc += dlogit[e_bc[svals[j]] / C];
-        out[it] = acc;
+        if (!direct) cpart[it - nu] = acc;
+        else if (APPLY) {
+            float4 r = wide[urow[it]];
+            opt_update(o, acc, r.x, r.y, r.z);
+            wide[urow[it]] = r;
+        } else ugrad[it] = acc;
     }
 }
 
@@ -676,16 +710,8 @@ static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t*
 // unique rows + segment starts of the sorted (row, occurrence) pairs in d_sk / d_sv
 static int group_tail(WdModel* m, int which, const int32_t* d_n) {
     const uint32_t invalid = 1u << m->sort_bits[which];
-    int g = grid_for(m->max_nnz, 256);
-    int rc;
-    int32_t* flags = (int32_t*)m->d_sk2[which];               // ping-pong buffer is free after the sort
-    seg_flag_kernel<<<g, 256, 0, m->stream>>>(d_n, m->d_sk[which], invalid, flags, m->max_nnz);
-    m->launches++;
-    rc = exclusive_scan_i32(m, flags, m->max_nnz, m->d_nuniq[which]);
-    if (rc) return rc;
-    seg_compact_kernel<<<g, 256, 0, m->stream>>>(d_n, m->d_sk[which], invalid, flags, m->d_ustart[which], m->d_urow[which], m->d_nuniq[which]);
-    m->launches++;
-    return WD_OK;
+    int32_t* pos = (int32_t*)m->d_sk2[which];                 // ping-pong buffer is free after the sort
+    return seg_heads(m, d_n, m->d_sk[which], invalid, pos, m->max_nnz, m->d_ustart[which], m->d_urow[which], m->d_nuniq[which]);
 }
 
 // out[u] = sum over the segment of in[sv[j]] (rows of `width` floats); one thread per (unique row, float4 chunk)
@@ -776,9 +802,7 @@ int sparse_group_which(WdModel* m, int which) {
     const bool present = which == 0 ? (m->use_deep && !m->tables.empty()) : m->use_wide;
     if (present) {
         if ((rc = group_rows(m, which, m->d_nnz, which == 0 ? m->d_e_emb : m->d_e_wide))) return rc;
-        chunk_count_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_choff[which], m->d_urow[which], m->max_nnz);
-        m->launches++;
-        if ((rc = exclusive_scan_i32(m, m->d_choff[which], m->max_nnz, m->d_nchunks[which]))) return rc;
+        if ((rc = chunk_offsets(m, m->d_nuniq[which], m->d_ustart[which], m->d_urow[which], m->d_choff[which], m->max_nnz, kChunk, m->d_nchunks[which]))) return rc;
         mark(m, which == 0 ? "emb_group" : "wide_group");
     }
     WD_CUDA(cudaGetLastError());
@@ -789,17 +813,34 @@ int sparse_group(WdModel* m) {
     return rc ? rc : sparse_group_which(m, 1);
 }
 
-// Stage 2: per-row gradient sums; leaves (urow, ugrad, nuniq) ready for exchange / apply
+// Stage 2: per-row gradient sums; leaves (urow, ugrad, nuniq) ready for exchange / apply.
+// Single-GPU step (train_eager: nothing exchanges the sums between backward and optimizer) with a row-local optimizer (everything
+// but Adam, whose moments decay over whole tables): the rows are updated inside these two launches and sparse_apply_which has
+// nothing left to launch for the list (m->list_apply_fused).
+static bool fuse_row_apply(const WdModel* m, const WdOptimizer& o) {
+    static const bool no_fuse = getenv("WD_NO_FUSED_ROW_APPLY") != nullptr;              // A/B switch (bench only)
+    return m->fuse_dense && o.kind != WD_OPT_ADAM && m->gs_count == 0 && !no_fuse;
+}
 int sparse_reduce_emb(WdModel* m) {
     const int g = grid_for(m->max_nnz, 256);
     if (m->use_deep && !m->tables.empty()) {
-        int ge = grid_for(m->max_nnz * 8, 256);
-        emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
-            m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->emb_max_dim);
-        emb_grad_sum_kernel<true><<<grid_for(m->cpart_cap * 8, 256), 256, 0, m->stream>>>(m->d_nchunks[0], m->d_nuniq[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
-            m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_cpart[0], m->emb_max_dim);
-        chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], m->emb_max_dim);
-        m->launches += 3;
+        const int width = m->emb_max_dim, G4 = width >> 2;
+        const int ge = grid_for((m->max_nnz + m->cpart_cap) * 8, 256);
+        // the hot rows' update lives in the lane-group branch of chunk_combine_kernel: widths 4, 8, ..., 128
+        const bool fused = fuse_row_apply(m, m->dnn_opt) && width >= 4 && (G4 & (G4 - 1)) == 0 && G4 <= 32;
+        const RowApply ra{m->d_urow[0], m->d_tab_data, m->d_tab_stride, m->d_tab_row_base, make_opt(m->dnn_opt)};
+        const HotApply ha{m->d_urow[0], m->n_rtab, m->d_rtab_row_base, m->d_rtab_data, m->d_rtab_dim, m->d_rtab_stride, nullptr, make_opt(m->dnn_opt)};
+        if (fused) {
+            emb_grad_sum_kernel<true><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->d_cpart[0], width, ra);
+            chunk_combine_kernel<1><<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], width, ha);
+        } else {
+            emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+                m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->d_cpart[0], width, ra);
+            chunk_combine_kernel<0><<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], width, ha);
+        }
+        m->list_apply_fused[0] = fused;
+        m->launches += 2;
         mark(m, "emb_grad_sum");
         m->sparse_overridden[0] = false;
     }
@@ -810,12 +851,20 @@ int sparse_reduce_emb(WdModel* m) {
 int sparse_reduce_wide(WdModel* m) {
     const int g = grid_for(m->max_nnz, 256);
     if (m->use_wide) {
-        wide_grad_sum_kernel<false><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
-                                                              m->n_columns, m->d_dlogit, m->d_ugrad[1]);
-        wide_grad_sum_kernel<true><<<grid_for(m->cpart_cap, 256), 256, 0, m->stream>>>(m->d_nchunks[1], m->d_nuniq[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
-                                                                                      m->n_columns, m->d_dlogit, m->d_cpart[1]);
-        chunk_combine_kernel<<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1);
-        m->launches += 3;
+        const bool fused = fuse_row_apply(m, m->lin_opt);
+        const HotApply ha{m->d_urow[1], 0, nullptr, nullptr, nullptr, nullptr, m->d_wide, make_opt(m->lin_opt)};
+        const int gw = grid_for(m->max_nnz + m->cpart_cap, 256);
+        if (fused) {
+            wide_grad_sum_kernel<true><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                                 m->n_columns, m->d_dlogit, m->d_ugrad[1], m->d_cpart[1], m->d_urow[1], m->d_wide, ha.o);
+            chunk_combine_kernel<2><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1, ha);
+        } else {
+            wide_grad_sum_kernel<false><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+                                                                  m->n_columns, m->d_dlogit, m->d_ugrad[1], m->d_cpart[1], m->d_urow[1], m->d_wide, ha.o);
+            chunk_combine_kernel<0><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1, ha);
+        }
+        m->list_apply_fused[1] = fused;
+        m->launches += 2;
         mark(m, "wide_grad_sum");
         m->sparse_overridden[1] = false;
     }
@@ -981,6 +1030,10 @@ static int adam_dense_pass(WdModel* m, int which, bool step) {
 
 int sparse_apply_which(WdModel* m, int which) {
     int rc;
+    // rows already updated by the gradient-sum / combine launches of this step (single-GPU step), unless a caller replaced the list since
+    const bool done = m->list_apply_fused[which] && !m->sparse_overridden[which];
+    m->list_apply_fused[which] = false;
+    if (done) return WD_OK;
     if (which == 0 && m->use_deep && !m->tables.empty()) {
         const bool adam = m->dnn_opt.kind == WD_OPT_ADAM;
         if (adam && (rc = adam_dense_pass(m, 0, false))) return rc;
@@ -1011,14 +1064,12 @@ int list_sort_by_key(WdModel* m, int which, const int32_t* d_n, const uint32_t* 
 int list_group(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row) {
     int rc = group_rows(m, which, d_n, e_row);
     if (rc) return rc;
-    chunk_count_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_ustart[which], m->d_choff[which], m->d_urow[which], m->max_nnz);
-    m->launches++;
-    if ((rc = exclusive_scan_i32(m, m->d_choff[which], m->max_nnz, m->d_nchunks[which]))) return rc;
+    if ((rc = chunk_offsets(m, m->d_nuniq[which], m->d_ustart[which], m->d_urow[which], m->d_choff[which], m->max_nnz, kChunk, m->d_nchunks[which]))) return rc;
     WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
 int list_chunk_combine(WdModel* m, int which, int width) {
-    chunk_combine_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_choff[which], m->d_cpart[which], m->d_ugrad[which], width);
+    chunk_combine_kernel<0><<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(m->d_nuniq[which], m->d_choff[which], m->d_cpart[which], m->d_ugrad[which], width, HotApply{});
     m->launches++;
     WD_CUDA(cudaGetLastError());
     return WD_OK;

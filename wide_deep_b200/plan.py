@@ -31,7 +31,7 @@ COL_HASH, COL_VOCAB, COL_IDENTITY, COL_BUCKET, COL_CROSS = range(5)
 NORM = {None: 0, "min_max": 1, "standard": 2, "log": 3}
 KEY_FIELD, KEY_COLUMN = 0, 1
 OPT = {"sgd": 0, "adagrad": 1, "ftrl": 2, "adam": 3, "rmsprop": 4}
-ACTS = ["relu", "relu6", "sigmoid", "tanh", "leaky_relu", "elu", "selu", "softplus", "softsign"]
+ACTS = ["relu", "relu6", "sigmoid", "tanh", "leaky_relu", "elu", "selu", "softplus", "softsign", "crelu"]      # WD_ACT_*
 MODES = ["simple", "first_dense", "last_dense", "dense", "resnet"]
 T_WIDE_COL, T_EMB_TABLE, T_DENSE, T_WIDE_BIAS = range(4)
 D_KERNEL, D_BIAS, D_GAMMA, D_BETA = range(4)
@@ -353,8 +353,8 @@ class Plan(object):
                 T[scope + "/kernel"] = (T_DENSE, did, D_KERNEL, (i, o))
                 T[scope + "/bias"] = (T_DENSE, did, D_BIAS, (o,))
                 if self.batch_norm and l < len(dims) - 1:
-                    T[scope + "/batch_normalization/gamma"] = (T_DENSE, did, D_GAMMA, (o,))
-                    T[scope + "/batch_normalization/beta"] = (T_DENSE, did, D_BETA, (o,))
+                    T[scope + "/batch_normalization/gamma"] = (T_DENSE, did, D_GAMMA, (self.out_width(o),))
+                    T[scope + "/batch_normalization/beta"] = (T_DENSE, did, D_BETA, (self.out_width(o),))
 
     # ------------------------------------------------------------------ helpers
     def is_sharded_tensor(self, name):
@@ -410,8 +410,12 @@ class Plan(object):
     def layer_dims(self, tower):
         hu, mode = self.towers[tower]["hidden"], self.towers[tower]["mode"]
         srcs = self.layer_sources(mode, len(hu))
-        w = lambda s: self.d0 if s == "x" else hu[s]
+        w = lambda s: self.d0 if s == "x" else self.out_width(hu[s])
         return [(sum(w(s) for s in srcs[l]), hu[l] if l < len(hu) else 1) for l in range(len(hu) + 1)]
+
+    def out_width(self, units):
+        """Features a hidden layer of `units` units hands on (tf.nn.crelu doubles them, reference model_util.py:45-50)."""
+        return 2 * units if self.activation == "crelu" else units
 
     def exchange_rows(self, rows_per_column):
         """Upper bounds (K_emb, K_wide) on the touched rows per step that stay in the (row, gradient) lists, given the maximum
