@@ -182,8 +182,18 @@ __global__ void ids_fill_kernel(DevPlan p, DevBatch bt, const int32_t* __restric
             }
             if (ind >= 0 && xrow) xrow[ind + id] += 1.f;       // indicator_column: multi-hot counts (A.7)
         };
-        if (p.col_kind[c] != WD_COL_CROSS) {
-            for (int k = 0; k < cnt; ++k) emit(base + k, simple_kth(p, bt, b, c, k));
+        const int kind = p.col_kind[c];
+        if (kind == WD_COL_BUCKET) {
+            if (cnt > 0) emit(base, simple_kth(p, bt, b, c, 0));
+            continue;
+        }
+        if (kind != WD_COL_CROSS) {
+            // one pass over the field's keys (a long multihot bag would otherwise be rescanned from its start for every id)
+            int s, e, k = 0;
+            field_range(bt, p.n_cat_fields, b, p.col_field[c], s, e);
+            int64_t id;
+            for (int j = s; j < e && k < cnt; ++j)
+                if (simple_id(p, c, kind, bt.cat_keys[j], &id)) emit(base + k++, id);
             continue;
         }
         if (cnt == 0) continue;

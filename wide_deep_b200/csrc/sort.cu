@@ -227,10 +227,13 @@ int chunk_offsets(WdModel* m, const int32_t* d_nuniq, const int32_t* ustart, uin
 // ------------------------------------------------------------------------------------------ radix sort
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS_PER_WARP = kSortTile / RS_WARPS;  // 4 rounds of 32
-constexpr int RS_TILE = kSortTile;                       // 1024 keys per tile: short blocks, enough of them to fill the SMs
+// Keys per tile (template parameter TILE of the three kernels): kSortTile = 1024 for the lists of a few 100 K keys (short blocks,
+// enough of them to fill the SMs); RS_BIG_TILE for lists of millions of keys, where the per-tile overhead (clearing and scanning
+// RS_WARPS x bins counters, the bin-base scan: ~10 shared-memory operations per key at 1024 keys) is what a pass costs.
+constexpr int RS_BIG_TILE = 4096;
 
 // Per-tile digit histogram -> hist[tile * bins + bin] (tile-major, coalesced) and global per-bin totals gtot[bin].
+template <int RS_TILE>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,
                                                              int shift, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot) {
     extern __shared__ int sh[];           // bins
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __r
 
 // Column scan: one warp per bin turns the per-tile counts hist[tile][bin] into exclusive prefixes over tiles
 // (32 tiles per shuffle scan); the last lane leaves the bin total in gtot[bin].
+template <int RS_TILE>
 __global__ void __launch_bounds__(256) rs_colscan_kernel(const int32_t* __restrict__ d_n, int bins, int32_t* __restrict__ hist, int32_t* __restrict__ gtot) {
     const int n = *d_n;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(256) rs_colscan_kernel(const int32_t* __restri
 
 // Stable scatter of one tile.  Output base of (tile, bin) = exclusive scan over bins of the bin totals + the tile's
 // prefix inside the bin (both precomputed by rs_colscan_kernel).
+template <int RS_TILE>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -288,6 +293,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
                                                                 const int32_t* __restrict__ hist, const int32_t* __restrict__ gtot) {
     extern __shared__ int wh[];           // [RS_WARPS][bins] then tilebase[bins]
     __shared__ int sm[33];
+    constexpr int RS_ITEMS_PER_WARP = RS_TILE / RS_WARPS;
     const int n = *d_n;
     const int ntiles = (n + RS_TILE - 1) / RS_TILE;
     const int tile = blockIdx.x;
@@ -352,11 +358,15 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
 // On return the sorted pairs are in d_sk/d_sv (buffers are swapped as needed).
 int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     if (bits < 1) bits = 1;
+    // (8-bit digits for the big lists — 16-byte runs instead of one 4-byte write per sector — were measured no faster: the 43 MB
+    // of a pass's output sit in L2, the scattered writes combine there; gpurun_out/r2_b33_wide.json)
+    const bool big = m->max_nnz >= (int64_t)2 << 20;                    // lists of millions of keys: larger tiles
     int passes = (bits + 9) / 10;
     int per = (bits + passes - 1) / passes;
     if (per < 8) per = 8;                                   // bins >= 256 so every thread owns at least one bin
     int bins = 1 << per;
-    int ntiles_cap = (int)((m->max_nnz + RS_TILE - 1) / RS_TILE);
+    const int tile = big ? RS_BIG_TILE : kSortTile;
+    int ntiles_cap = (int)((m->max_nnz + tile - 1) / tile);
     if ((int64_t)bins * ntiles_cap + 4 * 1024 > m->sort_hist_cap) {
         set_error("radix sort histogram capacity too small");
         return WD_ESTATE;
@@ -365,10 +375,19 @@ int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     int32_t* gtot = hist + (int64_t)bins * ntiles_cap;                  // [passes][bins]
     for (int p = 0; p < passes; ++p) {
         int shift = p * per;
-        rs_hist_kernel<<<ntiles_cap, RS_THREADS, bins * sizeof(int), m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
-        rs_colscan_kernel<<<(bins * 32 + 255) / 256, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
-        rs_scatter_kernel<<<ntiles_cap, RS_THREADS, (RS_WARPS + 1) * bins * sizeof(int), m->stream>>>(
-            m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
+        const size_t sh_h = bins * sizeof(int), sh_s = (RS_WARPS + 1) * bins * sizeof(int);
+        const int gcs = (bins * 32 + 255) / 256;
+        if (big) {
+            rs_hist_kernel<RS_BIG_TILE><<<ntiles_cap, RS_THREADS, sh_h, m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
+            rs_colscan_kernel<RS_BIG_TILE><<<gcs, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
+            rs_scatter_kernel<RS_BIG_TILE><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
+                m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
+        } else {
+            rs_hist_kernel<kSortTile><<<ntiles_cap, RS_THREADS, sh_h, m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
+            rs_colscan_kernel<kSortTile><<<gcs, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
+            rs_scatter_kernel<kSortTile><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
+                m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
+        }
         m->launches += 3;
         std::swap(m->d_sk[which], m->d_sk2[which]);
         std::swap(m->d_sv[which], m->d_sv2[which]);
