@@ -495,11 +495,15 @@ def test_long_multihot_bags_resdnn():
     assert np.max(np.abs(got - exp)) <= 0.03 * 0.05
 
 
-@pytest.mark.parametrize("nnz_cap", [2048 * 32, 2 << 20])
-def test_wide_only_hashed_crosses_ftrl(nnz_cap):
+@pytest.mark.parametrize("nnz_cap,digit_bits", [(2048 * 32, None), (2 << 20, None), (2 << 20, 10), (2048 * 32, 10)])
+def test_wide_only_hashed_crosses_ftrl(nnz_cap, digit_bits, monkeypatch):
     """BASELINE.json configs[4] in miniature: model_type 'wide', many hashed crosses into large bucket spaces, FTRL.
     The pure sparse-linear path: cross ids bit-exact, FTRL state (w, n, z) after three steps.  An id capacity of 2 M and more
-    selects the radix sort's 8-bit digits (sort.cu radix_sort_pairs: what the 5.4 M-key lists of the wide-only benchmark use)."""
+    selects the radix sort's big-list kernels (4096-key tiles reordered in shared memory, sort.cu radix_sort_pairs: what the
+    5.4 M-key lists of the wide-only benchmark use); WD_SORT_DIGIT_BITS=10 runs them with the 1024 bins the benchmark's 125 M
+    buckets need, which these small tables would not reach."""
+    if digit_bits:
+        monkeypatch.setenv("WD_SORT_DIGIT_BITS", str(digit_bits))
     fc = OrderedDict()
     for i in range(6):
         fc["k%d" % i] = dict(type="category", transform="hash_bucket", parameter=1000 + 17 * i)

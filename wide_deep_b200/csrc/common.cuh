@@ -260,6 +260,7 @@ struct WdModel {
     cudaStream_t sstream[2] = {nullptr, nullptr};
     cudaStream_t stream_up = nullptr;        // host->device refills of batch slots (wd_batch_prefetch_slot), overlapping the running step
     cudaEvent_t ev_ids = nullptr, ev_head = nullptr, ev_dx0 = nullptr, ev_bwd_done = nullptr, ev_wide_fwd = nullptr, ev_wgrad_rest = nullptr;
+    bool sort_smem_opt_in = false;               // rs_scatter_kernel<RS_BIG_TILE, true> was granted its dynamic shared memory on this device
     bool crelu = false;                          // dnn_activation_function crelu: relu on mirrored kernels (mlp.cu crelu_fold / crelu_mirror)
     bool list_apply_fused[2] = {false, false};   // this step's rows of the list were updated by its gradient-sum / combine launches (sparse.cu)
     bool record_wgrad_rest = false;           // mlp_backward: record ev_wgrad_rest before the first layer's weight gradient

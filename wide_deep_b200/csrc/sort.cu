@@ -4,6 +4,8 @@
 // The sort groups the step's (row id -> occurrence) pairs so that every touched table row gets exactly
 // one optimizer update from the ordered sum of its gradients — TensorFlow's "sum duplicates, apply once"
 // semantics for IndexedSlices — without float atomics (bit-reproducible run to run).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wd {
@@ -285,13 +287,18 @@ __global__ void __launch_bounds__(256) rs_colscan_kernel(const int32_t* __restri
 
 // Stable scatter of one tile.  Output base of (tile, bin) = exclusive scan over bins of the bin totals + the tile's
 // prefix inside the bin (both precomputed by rs_colscan_kernel).
-template <int RS_TILE>
+// LOCAL (the big-list instance): a key's 4-byte store into its bin's run is one store transaction per key whatever L2 does with
+// the sector afterwards, and at ~0.4 such transactions per clock and SM that rate is what a pass of a 5 M-key list costs (94 us
+// measured).  So the tile is first reordered in shared memory (position = the bin's tile-local base + the key's offset inside the
+// tile's run) and then written out in that order: consecutive threads hold consecutive addresses of a run, a warp's store covers
+// whole runs (4096 / bins keys each) instead of 32 unrelated sectors.
+template <int RS_TILE, bool LOCAL>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                 const int32_t* __restrict__ d_n, int shift, int bins,
                                                                 const int32_t* __restrict__ hist, const int32_t* __restrict__ gtot) {
-    extern __shared__ int wh[];           // [RS_WARPS][bins] then tilebase[bins]
+    extern __shared__ int wh[];           // [RS_WARPS][bins], tilebase[bins]; LOCAL: + lbase[bins], skey[RS_TILE], sval[RS_TILE]
     __shared__ int sm[33];
     constexpr int RS_ITEMS_PER_WARP = RS_TILE / RS_WARPS;
     const int n = *d_n;
@@ -299,10 +306,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
     const int tile = blockIdx.x;
     if (tile >= ntiles) return;
     int* tilebase = wh + RS_WARPS * bins;
+    int* lbase = tilebase + bins;
+    uint32_t* skey = reinterpret_cast<uint32_t*>(lbase + bins);
+    uint32_t* sval = skey + RS_TILE;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = bins / RS_THREADS > 0 ? bins / RS_THREADS : 1;           // bins is a power of two >= 256
+    const int b0 = threadIdx.x * per;
     {
-        const int per = bins / RS_THREADS > 0 ? bins / RS_THREADS : 1;       // bins is a power of two >= 256
-        const int b0 = threadIdx.x * per;
         int tot[4] = {0, 0, 0, 0};
         int s = 0;
         if (b0 < bins)
@@ -316,10 +326,21 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
     __syncthreads();
     const int wbase = tile * RS_TILE + w * RS_ITEMS_PER_WARP;
     int* my = wh + w * bins;
+    // the warp's keys and values, all loads in flight at once: the rounds below are ordered (a round's ranks depend on the counters
+    // the previous round left), so loading inside them would put one global-memory round trip on every round of both phases
+    constexpr int RS_ROUNDS = RS_ITEMS_PER_WARP / 32;
+    uint32_t kreg[RS_ROUNDS], vreg[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int j = wbase + r * 32 + lane;
+        kreg[r] = j < n ? keys_in[j] : 0u;
+        vreg[r] = j < n ? vals_in[j] : 0u;
+    }
     // phase A: per-warp histogram
-    for (int r = 0; r < RS_ITEMS_PER_WARP; r += 32) {
-        int j = wbase + r + lane;
-        if (j < n) atomicAdd(&my[(keys_in[j] >> shift) & (bins - 1)], 1);
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int j = wbase + r * 32 + lane;
+        if (j < n) atomicAdd(&my[(kreg[r] >> shift) & (bins - 1)], 1);
     }
     __syncthreads();
     // phase B: warp bases = tile base + counts of earlier warps
@@ -331,16 +352,36 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
             wh[ww * bins + b] = run;
             run += c;
         }
+        if (LOCAL) lbase[b] = run - tilebase[b];                              // keys of this tile in bin b
     }
     __syncthreads();
+    if (LOCAL) {                                                              // lbase = exclusive scan over bins of the tile's counts
+        int tot[4] = {0, 0, 0, 0};
+        int s = 0;
+        if (b0 < bins)
+            for (int k = 0; k < per; ++k) { tot[k] = lbase[b0 + k]; s += tot[k]; }
+        int blocktot;
+        int run = block_excl_scan(s, sm, &blocktot);
+        if (b0 < bins)
+            for (int k = 0; k < per; ++k) { lbase[b0 + k] = run; run += tot[k]; }
+        __syncthreads();
+    }
     // phase C: ordered rounds; rank inside a round by match_any
-    for (int r = 0; r < RS_ITEMS_PER_WARP; r += 32) {
-        int j = wbase + r + lane;
-        bool valid = j < n;
-        uint32_t k = valid ? keys_in[j] : 0u;
-        uint32_t v = valid ? vals_in[j] : 0u;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int j = wbase + r * 32 + lane;
+        const bool valid = j < n;
+        const uint32_t k = kreg[r], v = vreg[r];
         int d = valid ? (int)((k >> shift) & (bins - 1)) : bins;    // invalid lanes get a digit nobody shares
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit: one ballot per digit bit (match.any.sync costs ~5 issue cycles per key and SM here, which
+        // was what a pass of a long list took; ten votes and twenty logic operations are several times cheaper)
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int bit = 0; bit < 10; ++bit) {                        // bins <= 1024; bits above the digit are 0 in every valid lane
+            const bool one = (d >> bit) & 1;
+            const unsigned mask = __ballot_sync(0xffffffffu, one);
+            peers &= one ? mask : ~mask;
+        }
         int rank = __popc(peers & ((1u << lane) - 1u));
         int pos = 0;
         if (valid) pos = my[d] + rank;
@@ -348,8 +389,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
         if (valid && rank == 0) my[d] += __popc(peers);
         __syncwarp();
         if (valid) {
-            keys_out[pos] = k;
-            vals_out[pos] = v;
+            if (LOCAL) {
+                const int lp = lbase[d] + (pos - tilebase[d]);
+                skey[lp] = k;
+                sval[lp] = v;
+            } else {
+                keys_out[pos] = k;
+                vals_out[pos] = v;
+            }
+        }
+    }
+    if (LOCAL) {
+        __syncthreads();
+        const int nt = min(RS_TILE, n - tile * RS_TILE);
+        for (int i = threadIdx.x; i < nt; i += RS_THREADS) {
+            const uint32_t k = skey[i];
+            const int d = (int)((k >> shift) & (bins - 1));
+            const int o = tilebase[d] + (i - lbase[d]);
+            keys_out[o] = k;
+            vals_out[o] = sval[i];
         }
     }
 }
@@ -358,12 +416,18 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
 // On return the sorted pairs are in d_sk/d_sv (buffers are swapped as needed).
 int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     if (bits < 1) bits = 1;
-    // (8-bit digits for the big lists — 16-byte runs instead of one 4-byte write per sector — were measured no faster: the 43 MB
-    // of a pass's output sit in L2, the scattered writes combine there; gpurun_out/r2_b33_wide.json)
-    const bool big = m->max_nnz >= (int64_t)2 << 20;                    // lists of millions of keys: larger tiles
+    // Lists of millions of keys (the wide-only workload: 5.4 M keys per step): 4096-key tiles reordered in shared memory before
+    // they are written (rs_scatter_kernel<.., true>).  (8-bit digits WITHOUT that reorder were measured no faster than 10-bit
+    // ones, gpurun_out/r2_b33_wide.json: every key stayed one store transaction.)  WD_SORT_DIGIT_BITS=8|9|10 fixes the digit width
+    // (A/B runs, and the tests use it to reach the 1024-bin kernels with small tables).
+    const bool big = m->max_nnz >= (int64_t)2 << 20;
     int passes = (bits + 9) / 10;
     int per = (bits + passes - 1) / passes;
     if (per < 8) per = 8;                                   // bins >= 256 so every thread owns at least one bin
+    if (const char* e = getenv("WD_SORT_DIGIT_BITS")) {
+        const int v = atoi(e);
+        if (v >= 8 && v <= 10) { per = v; passes = (bits + per - 1) / per; }
+    }
     int bins = 1 << per;
     const int tile = big ? RS_BIG_TILE : kSortTile;
     int ntiles_cap = (int)((m->max_nnz + tile - 1) / tile);
@@ -376,16 +440,26 @@ int radix_sort_pairs(WdModel* m, int which, int bits, const int32_t* d_n) {
     for (int p = 0; p < passes; ++p) {
         int shift = p * per;
         const size_t sh_h = bins * sizeof(int), sh_s = (RS_WARPS + 1) * bins * sizeof(int);
+        const size_t sh_l = (RS_WARPS + 2) * bins * sizeof(int) + 2 * RS_BIG_TILE * sizeof(uint32_t);    // + lbase, skey, sval
         const int gcs = (bins * 32 + 255) / 256;
         if (big) {
+            if (!m->sort_smem_opt_in) {                                 // 72 KB of dynamic shared memory at 1024 bins (per device: once per handle)
+                WD_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<RS_BIG_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                m->sort_smem_opt_in = true;
+            }
             rs_hist_kernel<RS_BIG_TILE><<<ntiles_cap, RS_THREADS, sh_h, m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
             rs_colscan_kernel<RS_BIG_TILE><<<gcs, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
-            rs_scatter_kernel<RS_BIG_TILE><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
-                m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
+            static const bool no_local = getenv("WD_SORT_NO_LOCAL") != nullptr;       // A/B switch
+            if (no_local)
+                rs_scatter_kernel<RS_BIG_TILE, false><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
+                    m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
+            else
+                rs_scatter_kernel<RS_BIG_TILE, true><<<ntiles_cap, RS_THREADS, sh_l, m->stream>>>(
+                    m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
         } else {
             rs_hist_kernel<kSortTile><<<ntiles_cap, RS_THREADS, sh_h, m->stream>>>(m->d_sk[which], d_n, shift, bins, hist, gtot + p * bins);
             rs_colscan_kernel<kSortTile><<<gcs, 256, 0, m->stream>>>(d_n, bins, hist, gtot + p * bins);
-            rs_scatter_kernel<kSortTile><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
+            rs_scatter_kernel<kSortTile, false><<<ntiles_cap, RS_THREADS, sh_s, m->stream>>>(
                 m->d_sk[which], m->d_sv[which], m->d_sk2[which], m->d_sv2[which], d_n, shift, bins, hist, gtot + p * bins);
         }
         m->launches += 3;

@@ -411,13 +411,16 @@ int sparse_forward_emb(WdModel* m) {
 // ------------------------------------------------------------------------------------ backward: grouping
 // keys/values for the two sorts: which = 0 embedding rows, 1 wide rows.  Non-participating entries get the
 // key `invalid` (= 1 << bits) so they sort behind every real row.
+// (key, value) pairs for the sort: key = row (invalid rows sort last), value = val_src[i], or the entry's index i without val_src.
+// The batch's own lists carry the entry's cell index bc = b * C + c (e_bc) as the value: that is all the gradient sums need to
+// find an occurrence's gradient, so they read it straight from the sorted list instead of chasing e_bc[index] per occurrence.
 __global__ void sort_keys_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ e_row, uint32_t invalid,
-                                 uint32_t* keys, uint32_t* vals) {
+                                 uint32_t* keys, uint32_t* vals, const int32_t* __restrict__ val_src) {
     int n = *d_nnz;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t r = e_row[i];
         keys[i] = r == kInvalidRow ? invalid : r;
-        vals[i] = (uint32_t)i;
+        vals[i] = val_src ? (uint32_t)val_src[i] : (uint32_t)i;
     }
 }
 
@@ -440,8 +443,8 @@ struct RowApply { const uint32_t* urow; float* const* tab_data; const int32_t* t
 template <bool APPLY>
 __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ d_nchunks,
                                                            const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
-                                                           const uint32_t* __restrict__ svals,
-                                                           const int32_t* __restrict__ e_bc, const int32_t* __restrict__ offs,
+                                                           const uint32_t* __restrict__ sbc /* sorted cell indices bc = b * C + c */,
+                                                           const int32_t* __restrict__ offs,
                                                            int C, const int32_t* __restrict__ col_table,
                                                            const int32_t* __restrict__ tab_dim, const int32_t* __restrict__ tab_x0,
                                                            const float* __restrict__ dX0, int ld, float* __restrict__ ugrad,
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
             e = min(ustart[u + 1], s + kChunk);
             out = cpart + (int64_t)c * width;
         }
-        int bc0 = e_bc[svals[s]];
+        int bc0 = (int)sbc[s];
         int t = col_table[bc0 % C];
         int dim = tab_dim[t], x0 = tab_x0[t];
         for (int q = lig; q * 4 < width; q += 8) {
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
                 for (; j + 4 <= e; j += 4) {                  // 4 gradient rows in flight
                     int bcs[4]; float4 v[4]; float inv[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) bcs[r] = e_bc[svals[j + r]];
+                    for (int r = 0; r < 4; ++r) bcs[r] = (int)sbc[j + r];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         v[r] = *reinterpret_cast<const float4*>(dX0 + (int64_t)(bcs[r] / C) * ld + x0 + q * 4);
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(256) emb_grad_sum_kernel(const int32_t* __rest
                     for (int r = 0; r < 4; ++r) { acc.x += v[r].x * inv[r]; acc.y += v[r].y * inv[r]; acc.z += v[r].z * inv[r]; acc.w += v[r].w * inv[r]; }
                 }
                 for (; j < e; ++j) {
-                    int bc = e_bc[svals[j]];
+                    int bc = (int)sbc[j];
                     float4 v = *reinterpret_cast<const float4*>(dX0 + (int64_t)(bc / C) * ld + x0 + q * 4);
                     float inv = 1.f / (float)(offs[bc + 1] - offs[bc]);
                     acc.x += v.x * inv; acc.y += v.y * inv; acc.z += v.z * inv; acc.w += v.w * inv;
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(256) chunk_combine_kernel(const int32_t* __res
 template <bool APPLY>
 __global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const int32_t* __restrict__ d_nchunks,
                                      const int32_t* __restrict__ ustart, const int32_t* __restrict__ choff,
-                                     const uint32_t* __restrict__ svals, const int32_t* __restrict__ e_bc, int C,
+                                     const uint32_t* __restrict__ sbc /* sorted cell indices bc = b * C + c */, int C,
                                      const float* __restrict__ dlogit, float* __restrict__ ugrad, float* __restrict__ cpart,
                                      const uint32_t* __restrict__ urow, float4* __restrict__ wide, OptParams o) {
     const int nu = *d_nuniq;
@@ -636,7 +639,7 @@ __global__ void wide_grad_sum_kernel(const int32_t* __restrict__ d_nuniq, const 
             e = min(ustart[u + 1], s + kChunk);
         }
         float acc = 0.f;
-        for (int j = s; j < e; ++j) acc += dlogit[e_bc[svals[j]] / C];
+        for (int j = s; j < e; ++j) acc += dlogit[sbc[j] / (uint32_t)C];
         if (!direct) cpart[it - nu] = acc;
         else if (APPLY) {
             float4 r = wide[urow[it]];
@@ -698,10 +701,10 @@ __global__ void wide_apply_kernel(const int32_t* __restrict__ d_nuniq, const uin
 
 // sort (row, occurrence) pairs by row and find the unique rows; e_row: per-occurrence row ids (kInvalidRow = skip)
 static int group_tail(WdModel* m, int which, const int32_t* d_n);
-static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row) {
+static int group_rows(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_row, const int32_t* val_src = nullptr) {
     const uint32_t invalid = 1u << m->sort_bits[which];
     int g = grid_for(m->max_nnz, 256);
-    sort_keys_kernel<<<g, 256, 0, m->stream>>>(d_n, e_row, invalid, m->d_sk[which], m->d_sv[which]);
+    sort_keys_kernel<<<g, 256, 0, m->stream>>>(d_n, e_row, invalid, m->d_sk[which], m->d_sv[which], val_src);
     m->launches++;
     int rc = radix_sort_pairs(m, which, m->sort_bits[which] + 1, d_n);
     if (rc) return rc;
@@ -801,7 +804,7 @@ int sparse_group_which(WdModel* m, int which) {
     const int g = grid_for(m->max_nnz, 256);
     const bool present = which == 0 ? (m->use_deep && !m->tables.empty()) : m->use_wide;
     if (present) {
-        if ((rc = group_rows(m, which, m->d_nnz, which == 0 ? m->d_e_emb : m->d_e_wide))) return rc;
+        if ((rc = group_rows(m, which, m->d_nnz, which == 0 ? m->d_e_emb : m->d_e_wide, m->d_e_bc))) return rc;     // values = cell indices
         if ((rc = chunk_offsets(m, m->d_nuniq[which], m->d_ustart[which], m->d_urow[which], m->d_choff[which], m->max_nnz, kChunk, m->d_nchunks[which]))) return rc;
         mark(m, which == 0 ? "emb_group" : "wide_group");
     }
@@ -831,11 +834,11 @@ int sparse_reduce_emb(WdModel* m) {
         const RowApply ra{m->d_urow[0], m->d_tab_data, m->d_tab_stride, m->d_tab_row_base, make_opt(m->dnn_opt)};
         const HotApply ha{m->d_urow[0], m->n_rtab, m->d_rtab_row_base, m->d_rtab_data, m->d_rtab_dim, m->d_rtab_stride, nullptr, make_opt(m->dnn_opt)};
         if (fused) {
-            emb_grad_sum_kernel<true><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+            emb_grad_sum_kernel<true><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0],
                 m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->d_cpart[0], width, ra);
             chunk_combine_kernel<1><<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], width, ha);
         } else {
-            emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0], m->d_e_bc,
+            emb_grad_sum_kernel<false><<<ge, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_nchunks[0], m->d_ustart[0], m->d_choff[0], m->d_sv[0],
                 m->d_col_offs, m->n_columns, m->dplan.col_emb_table, m->d_tab_dim, m->d_tab_x0, m->d_dX0, m->d0_phys, m->d_ugrad[0], m->d_cpart[0], width, ra);
             chunk_combine_kernel<0><<<g, 256, 0, m->stream>>>(m->d_nuniq[0], m->d_choff[0], m->d_cpart[0], m->d_ugrad[0], width, ha);
         }
@@ -855,11 +858,11 @@ int sparse_reduce_wide(WdModel* m) {
         const HotApply ha{m->d_urow[1], 0, nullptr, nullptr, nullptr, nullptr, m->d_wide, make_opt(m->lin_opt)};
         const int gw = grid_for(m->max_nnz + m->cpart_cap, 256);
         if (fused) {
-            wide_grad_sum_kernel<true><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+            wide_grad_sum_kernel<true><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1],
                                                                  m->n_columns, m->d_dlogit, m->d_ugrad[1], m->d_cpart[1], m->d_urow[1], m->d_wide, ha.o);
             chunk_combine_kernel<2><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1, ha);
         } else {
-            wide_grad_sum_kernel<false><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1], m->d_e_bc,
+            wide_grad_sum_kernel<false><<<gw, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_nchunks[1], m->d_ustart[1], m->d_choff[1], m->d_sv[1],
                                                                   m->n_columns, m->d_dlogit, m->d_ugrad[1], m->d_cpart[1], m->d_urow[1], m->d_wide, ha.o);
             chunk_combine_kernel<0><<<g, 256, 0, m->stream>>>(m->d_nuniq[1], m->d_choff[1], m->d_cpart[1], m->d_ugrad[1], 1, ha);
         }
@@ -1057,7 +1060,7 @@ int sparse_apply_which(WdModel* m, int which) {
 // ---- wrappers used by shard.cu (rows this rank owns in a row-sharded table space)
 // stable sort of (e_key[i], i) pairs, i < *d_n, by key; keys equal to kInvalidRow sort last; result in d_sk / d_sv of list `which`
 int list_sort_by_key(WdModel* m, int which, const int32_t* d_n, const uint32_t* e_key) {
-    sort_keys_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(d_n, e_key, 1u << m->sort_bits[which], m->d_sk[which], m->d_sv[which]);
+    sort_keys_kernel<<<grid_for(m->max_nnz, 256), 256, 0, m->stream>>>(d_n, e_key, 1u << m->sort_bits[which], m->d_sk[which], m->d_sv[which], nullptr);
     m->launches++;
     return radix_sort_pairs(m, which, m->sort_bits[which] + 1, d_n);
 }
