@@ -1,3 +1,5 @@
+# One GPU call that re-validates a round: full GPU suite, the three bench workloads, a step timeline and the ncu launch list.
+#   tools/gpurun_retry.sh gpurun_out/check.log --timeout 1000 -- "bash tools/gpu_round_check.sh"
 set -x
 mkdir -p gpurun_out
 timeout 420 python -m pytest tests -m gpu -q > gpurun_out/r2_t38_full.log 2>&1; echo "pytest rc=$?"
