@@ -292,11 +292,22 @@ typedef struct WdTsvSpec {
     int32_t use_weight;
     int32_t has_label;
 } WdTsvSpec;
-/* Returns nnz, or negative error.  keys_cap == 0 (or keys_out NULL): only counts (offsets filled) — call again with a buffer of nnz
- * keys; or call once with keys_cap >= an upper bound (without tf_compat_pad: n_lines * n_cat_fields + number of ',' in the text). */
+/* Returns nnz, or negative error.  keys_cap == 0 (or keys_out NULL), or nnz > keys_cap: only counts (offsets, dense, label and
+ * weight are filled, no key is copied) — call again with a buffer of nnz keys and the same arguments otherwise: the follow-up call
+ * copies the keys of the parse the first call did (one parse per batch).  Without tf_compat_pad
+ * n_lines * n_cat_fields + number of ',' in the text is an upper bound of nnz. */
 int64_t wd_tsv_parse(const WdTsvSpec *spec, const char *text, int64_t text_len, int32_t n_lines,
                      int32_t *offsets_out, uint64_t *keys_out, int64_t keys_cap,
                      float *dense_out, float *label_out, float *weight_out, int32_t n_threads);
+/* Line index of a file image, for shuffled / sharded passes without splitting or joining text (reference python/lib/dataset.py:
+ * 167-184: TextLineDataset -> shard -> shuffle -> batch): start offsets and lengths of the non-empty lines ('\r' before the
+ * newline excluded).  Returns the number of lines (the arrays receive the first `cap` of them; pass NULL / 0 to count). */
+int64_t wd_tsv_index_lines(const char *text, int64_t text_len, int64_t *starts_out, int32_t *lens_out, int64_t cap);
+/* wd_tsv_parse over lines picked through that index: line i of the batch is text[starts[idx[i]] .. + lens[idx[i]]) (idx NULL:
+ * line i).  Same outputs and return value as wd_tsv_parse. */
+int64_t wd_tsv_parse_lines(const WdTsvSpec *spec, const char *text, const int64_t *starts, const int32_t *lens, const int64_t *idx,
+                           int32_t n_lines, int32_t *offsets_out, uint64_t *keys_out, int64_t keys_cap,
+                           float *dense_out, float *label_out, float *weight_out, int32_t n_threads);
 
 /* Page-locked host buffers for the input pipeline (the `dataset.prefetch` buffers of the reference's input_fn, python/lib/
  * dataset.py:181-184): parse into these, hand them to wd_batch_prefetch_slot.  WD_ENODEVICE without a CUDA device. */

@@ -204,6 +204,188 @@ def test_pinned_ring_and_prefetch_thread_yield_the_same_batches(native_lib, tf_c
     assert counts[0] == counts[1] == counts[2] == -(-(5000 // 3) // 64)
 
 
+@pytest.mark.parametrize("tf_compat_pad", [False, True])
+@pytest.mark.parametrize("mode,rank,world", [("eval", 0, 1), ("train", 0, 1), ("train", 1, 3)])
+def test_input_fn_over_the_line_index_equals_the_line_list_path(native_lib, tmp_path, tf_compat_pad, mode, rank, world):
+    """input_fn indexes the file image once (wd_tsv_index_lines) and parses each batch's lines in place (wd_tsv_parse_lines); what
+    it yields must be, batch by batch, what the straightforward procedure gives: split the files into lines, drop empty ones,
+    take every world-th line from `rank`, shuffle with Philox(seed) in train mode, join and parse batch_size lines at a time
+    (reference dataset.py:167-184: TextLineDataset -> shard -> shuffle -> batch).  Two files, CRLF line ends, blank lines and a
+    missing final newline included."""
+    from wide_deep_b200.dataset import TsvReader, input_fn
+    from wide_deep_b200.plan import compile_plan
+    cfg = Config()
+    plan = compile_plan(cfg, "wide_deep", 100, tf_compat_pad=tf_compat_pad)
+    src = open(os.path.join(ROOT, "data", "test", "test1"), "rb").read().split(b"\n")
+    src = [l for l in src if l][:700]
+    d = tmp_path / "data"
+    d.mkdir()
+    (d / "part-0").write_bytes(b"\n".join(src[:300]) + b"\n\n\n")                 # blank lines at the end
+    (d / "part-1").write_bytes(b"\r\n".join(src[300:]))                            # CRLF, no final newline
+    (d / ".hidden").write_bytes(b"not data\n")
+    lines = src[:300] + [l + b"\r" for l in src[300:-1]] + [src[-1]]
+    if world > 1:
+        lines = lines[rank::world][:len(lines) // world]
+    if mode == "train":
+        perm = np.random.Generator(np.random.Philox(123)).permutation(len(lines))
+        lines = [lines[i] for i in perm]
+    reader = TsvReader(cfg, plan)
+    want = [reader.parse(lines[i:i + 100]) for i in range(0, len(lines), 100)]
+    for pinned in (False, True):
+        got = 0
+        for a, b in zip(want, input_fn(str(d), None, mode, 100, config=cfg, plan=plan, rank=rank, world=world, pinned=pinned)):
+            assert b.batch_size == a.batch_size
+            np.testing.assert_array_equal(b.keys, a.keys)
+            np.testing.assert_array_equal(b.offsets, a.offsets)
+            np.testing.assert_array_equal(b.dense, a.dense)
+            np.testing.assert_array_equal(b.label, a.label)
+            got += 1
+        assert got == len(want) == -(-len(lines) // 100)
+
+
+def test_tsv_two_call_protocol_parses_once_and_never_mixes_batches(native_lib):
+    """wd_tsv_parse with no key buffer (or one that is too small) only counts and keeps its parse; the follow-up call with the same
+    arguments copies the keys out.  A follow-up call for DIFFERENT text (same sizes, same output arrays) must parse afresh."""
+    from wide_deep_b200.dataset import TsvReader
+    from wide_deep_b200.plan import compile_plan
+    cfg = Config()
+    plan = compile_plan(cfg, "wide_deep", 64, tf_compat_pad=True)
+    reader = TsvReader(cfg, plan)
+    src = [l for l in open(os.path.join(ROOT, "data", "test", "test1"), "rb").read().split(b"\n") if l]
+    a_lines, b_lines = src[:64], src[64:128]
+    want_a, want_b = reader.parse(a_lines), reader.parse(b_lines)
+    lib, spec = reader._lib, reader._spec
+    F, Nd = len(plan.cat_fields), len(plan.dense_fields)
+    offs = np.zeros(64 * F + 1, dtype=np.int32); dense = np.zeros((64, Nd), dtype=np.float32)
+    label = np.zeros(64, dtype=np.float32); weight = np.ones(64, dtype=np.float32)
+    ta, tb = b"\n".join(a_lines), b"\n".join(b_lines)
+
+    def call(text, keys):
+        import ctypes
+        return lib.wd_tsv_parse(ctypes.byref(spec), text, len(text), 64, offs.ctypes.data, keys.ctypes.data if keys is not None else None,
+                                keys.size if keys is not None else 0, dense.ctypes.data, label.ctypes.data, weight.ctypes.data, 2)
+    small = np.empty(8, dtype=np.uint64)
+    nnz = call(ta, small)                                             # too small: counts only
+    assert nnz == len(want_a.keys) > 8
+    keys = np.empty(nnz, dtype=np.uint64)
+    assert call(ta, keys) == nnz                                      # follow-up: the kept parse
+    np.testing.assert_array_equal(keys, want_a.keys)
+    np.testing.assert_array_equal(offs, want_a.offsets)
+    assert call(ta, None) == nnz                                      # counting call for A ...
+    nb = call(tb, np.empty(len(want_b.keys), dtype=np.uint64))        # ... followed by a call for B: parsed afresh
+    kb = np.empty(nb, dtype=np.uint64)
+    assert call(tb, kb) == nb == len(want_b.keys)
+    np.testing.assert_array_equal(kb, want_b.keys)
+    np.testing.assert_array_equal(offs, want_b.offsets)
+    np.testing.assert_array_equal(dense, want_b.dense)
+
+
+def test_tsv_fast_number_fields_equal_strtof_and_strtoll(native_lib):
+    """The loader decodes plain [-]digits[.digits] fields itself and leaves every other shape to strtof / strtoll; its floats must
+    be the correctly rounded float of the decimal — what libc's strtof returns — including decimals that sit on or next to the
+    midpoint between two floats (where rounding through double would go wrong), and its ints what strtoll returns."""
+    import ctypes
+    import ctypes.util
+    from wide_deep_b200._native import TsvSpecC
+    libc = ctypes.CDLL(ctypes.util.find_library("c"))
+    libc.strtof.restype, libc.strtof.argtypes = ctypes.c_float, [ctypes.c_char_p, ctypes.c_void_p]
+    libc.strtoll.restype, libc.strtoll.argtypes = ctypes.c_longlong, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(17)
+    floats = ["0", "-0", "-0.0", "1.", ".5", "-.5", "00012.50", "31.0", "1e5", "-2.5E-3", "16777217", "16777219", "33554434", "8388608.5",
+              "8388609.5", "0.1", "0.30000000000000004", "123456789012345", "1234567890123456", "3.4028235e38", "1e-45", "7.006492321624085e-46",
+              "4294967296.000001", "0.000000059604644775390625", "1.00000005960464477539", "9007199254740993"]
+    for _ in range(20000):
+        kind = int(rng.integers(0, 5))
+        if kind == 0:                                                 # plain decimals, 1-15 significant digits
+            digs = "".join(str(int(x)) for x in rng.integers(0, 10, size=int(rng.integers(1, 16))))
+            k = int(rng.integers(0, len(digs) + 1))
+            t = digs[:k] + "." + digs[k:] if rng.random() < 0.8 else digs
+        elif kind == 1:                                               # integers around 2^24 .. 2^40: exact float midpoints are common
+            t = str(int(rng.integers(1 << 24, 1 << 40)))
+        elif kind == 2:                                               # midpoints between neighbouring floats, printed exactly when short
+            f = np.float32(rng.uniform(0.001, 4096.0))
+            mid = (float(f) + float(np.nextafter(f, np.float32(np.inf)))) / 2
+            t = repr(mid) if rng.random() < 0.5 else "%.15g" % mid
+        elif kind == 3:                                               # what %g / repr print for random floats
+            t = repr(float(np.float32(rng.standard_normal() * 10 ** int(rng.integers(-6, 7)))))
+        else:
+            t = "%.*f" % (int(rng.integers(0, 12)), rng.uniform(-1e6, 1e6))
+        floats.append(("-" if rng.random() < 0.2 and not t.startswith("-") else "") + t)
+    ints = ["0", "-0", "7", "-7", "+7", "007", "999999999999999999", "-999999999999999999", "9223372036854775807", "-9223372036854775808",
+            "1234567890123456789"] + [str(int(x)) for x in rng.integers(-2 ** 62, 2 ** 62, size=2000)]
+    floats = [t for t in floats if t not in ("", "-")]               # (empty and '-' are the NA tokens)
+    n = max(len(floats), len(ints))
+    floats += ["1"] * (n - len(floats))
+    ints += ["1"] * (n - len(ints))
+    text = "\n".join("%s\t%s" % (a, b) for a, b in zip(floats, ints)).encode()
+    role, target = np.asarray([3, 2], dtype=np.int32), np.asarray([0, 0], dtype=np.int32)
+    spec = TsvSpecC()
+    spec.n_columns, spec.col_role, spec.col_target = 2, role.ctypes.data, target.ctypes.data
+    spec.n_cat_fields, spec.n_dense_fields, spec.multivalue, spec.tf_compat_pad = 1, 1, 0, 0
+    spec.pos_weight, spec.neg_weight, spec.use_weight, spec.has_label = 1.0, 1.0, 0, 0
+    offs, keys = np.zeros(n + 1, dtype=np.int32), np.zeros(n, dtype=np.uint64)
+    dense, weight = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    got = native_lib.wd_tsv_parse(ctypes.byref(spec), text, len(text), n, offs.ctypes.data, keys.ctypes.data, n, dense.ctypes.data, None,
+                                  weight.ctypes.data, 3)
+    assert got == n, native_lib.wd_last_error()
+    want_f = np.asarray([libc.strtof(t.encode(), None) for t in floats], dtype=np.float32)
+    want_i = np.asarray([libc.strtoll(t.encode(), None, 10) for t in ints], dtype=np.int64)
+    bad = np.flatnonzero(dense.view(np.uint32) != want_f.view(np.uint32))
+    assert bad.size == 0, [(floats[i], float(dense[i]), float(want_f[i])) for i in bad[:5]]
+    np.testing.assert_array_equal(keys.view(np.int64), want_i)
+
+
+def test_tsv_worker_pool_concurrent_callers_and_fork(native_lib):
+    """The loader's persistent worker threads: several Python threads parsing at once with changing thread counts get the same
+    batches as a single-threaded parse, and a forked child (whose copy of the pool has no threads) parses too."""
+    import threading
+    from wide_deep_b200.dataset import TsvReader
+    from wide_deep_b200.plan import compile_plan
+    cfg = Config()
+    plan = compile_plan(cfg, "wide_deep", 4096, tf_compat_pad=True)
+    src = [l for l in open(os.path.join(ROOT, "data", "test", "test1"), "rb").read().split(b"\n") if l]
+    want = {}
+    for o, n in [(0, 1), (3, 255), (100, 900), (500, 2500), (7, 4000)]:
+        b = TsvReader(cfg, plan, n_threads=1).parse(src[o:o + n])
+        want[(o, n)] = (b.keys.copy(), b.offsets.copy(), b.dense.copy())
+    errors = []
+
+    def job(tid):
+        rng = np.random.default_rng(tid)
+        try:
+            for _ in range(40):
+                (o, n), nt = list(want)[int(rng.integers(0, len(want)))], int(rng.integers(1, 17))
+                b = TsvReader(cfg, plan, n_threads=nt).parse(src[o:o + n])
+                k, f, d = want[(o, n)]
+                assert np.array_equal(b.keys, k) and np.array_equal(b.offsets, f) and np.array_equal(b.dense, d), (o, n, nt)
+        except Exception as e:                                          # surfaced on the main thread
+            errors.append(e)
+    ths = [threading.Thread(target=job, args=(i,)) for i in range(3)]
+    [t.start() for t in ths]
+    [t.join(120) for t in ths]
+    assert not errors and not any(t.is_alive() for t in ths), errors
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            b = TsvReader(cfg, plan, n_threads=8).parse(src[500:3000])
+            ok = 0 if np.array_equal(b.keys, want[(500, 2500)][0]) else 2
+        finally:
+            os._exit(ok)
+    for _ in range(600):                                                # a hung child must fail the test, not hang it
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        import time
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        os.waitpid(pid, 0)
+        raise AssertionError("forked child hung in the TSV loader")
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert np.array_equal(TsvReader(cfg, plan, n_threads=8).parse(src[500:3000]).keys, want[(500, 2500)][0])
+
+
 def test_sharded_plan_marks_large_tables_only(native_lib):
     from wide_deep_b200 import synthetic
     from wide_deep_b200.plan import Plan

@@ -92,6 +92,8 @@ SYMBOLS = {
     "wd_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "wd_host_free": (ctypes.c_int, [_vp]),
     "wd_tsv_parse": (_i64, [_vp, ctypes.c_char_p, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32]),
+    "wd_tsv_index_lines": (_i64, [_vp, _i64, _vp, _vp, _i64]),
+    "wd_tsv_parse_lines": (_i64, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32]),
 }
 
 

@@ -125,6 +125,7 @@ class TsvReader(object):
         self.is_pred = is_pred
         self.n_threads = n_threads or min(os.cpu_count() or 1, 16)
         self._lib = _native.lib()
+        self._key_guess = 0                                           # keys of the largest batch seen (+25 %): first-call capacity
 
     def parse(self, lines, ring=None):
         """list of text lines (str or bytes, no trailing newline needed) -> Batch.  ``ring``: a PinnedRing whose next buffer set
@@ -159,22 +160,26 @@ class TsvReader(object):
                      weight if (self.use_weight and not self.is_pred) else None)
 
 
-def _parse_into_ring(self, text, n, ring):
+def _parse_into_ring(self, text, n, ring, index=None):
+    """``index`` = (starts, lens, idx): the batch's lines are picked out of the file image ``text`` (wd_tsv_parse_lines)."""
     F, Nd = len(self.plan.cat_fields), len(self.plan.dense_fields)
     if n > ring.n_rows:
         raise ValueError("batch of %d lines, pinned ring sized for %d" % (n, ring.n_rows))
-    need = n * max(F, 1) + text.count(b",") + 1                      # every field holds at most (commas + 1) tokens
     s = ring.next()                                                  # the oldest set: nothing in flight reads it any more
-    if self.plan.tf_compat_pad:
-        # padded string fields (quirk Q2) can exceed the token count: ask for the size first (keys_cap = 0)
-        need = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, s["offsets"].ctypes.data, None, 0,
-                                      s["dense"].ctypes.data, s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
-        if need < 0:
-            raise ValueError(self._lib.wd_last_error().decode())
-    if need > ring.key_cap:
-        ring.grow_keys(max(need, 2 * ring.key_cap))                  # (old key buffers stay allocated: in-flight batches alias them)
-    nnz = self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, s["offsets"].ctypes.data, s["keys"].ctypes.data,
-                                 ring.key_cap, s["dense"].ctypes.data, s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
+
+    def call():
+        if index is None:
+            return self._lib.wd_tsv_parse(ctypes.byref(self._spec), text, len(text), n, s["offsets"].ctypes.data, s["keys"].ctypes.data,
+                                          ring.key_cap, s["dense"].ctypes.data, s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
+        starts, lens, idx = index
+        return self._lib.wd_tsv_parse_lines(ctypes.byref(self._spec), text, starts.ctypes.data, lens.ctypes.data, idx.ctypes.data, n,
+                                            s["offsets"].ctypes.data, s["keys"].ctypes.data, ring.key_cap, s["dense"].ctypes.data,
+                                            s["label"].ctypes.data, s["weight"].ctypes.data, self.n_threads)
+
+    nnz = call()
+    if nnz > ring.key_cap:                                           # nothing was copied; the library keeps the parse for the next call
+        ring.grow_keys(max(nnz, 2 * ring.key_cap))                   # (old key buffers stay allocated: in-flight batches alias them)
+        nnz = call()
     if nnz < 0:
         raise ValueError(self._lib.wd_last_error().decode())
     b = Batch.__new__(Batch)                                         # views of the pinned set: no copies (Batch() would copy)
@@ -186,7 +191,35 @@ def _parse_into_ring(self, text, n, ring):
     return b
 
 
+def _parse_indexed(self, text, starts, lens, idx, ring=None):
+    """Batch of the lines ``idx`` of the file image ``text`` (``starts`` / ``lens`` from wd_tsv_index_lines): no line is split off,
+    copied or joined on the way to the parser."""
+    n = len(idx)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    if ring is not None:
+        return self._parse_into_ring(text, n, ring, index=(starts, lens, idx))
+    F, Nd = len(self.plan.cat_fields), len(self.plan.dense_fields)
+    offsets = np.zeros(n * F + 1, dtype=np.int32)
+    dense = np.zeros((n, max(Nd, 1)), dtype=np.float32)
+    label = np.zeros(n, dtype=np.float32)
+    weight = np.ones(n, dtype=np.float32)
+    keys = np.empty(max(self._key_guess, n * max(F, 1)), dtype=np.uint64)
+    for _ in range(2):                                               # second round only if the guess was too small (parse is reused)
+        nnz = self._lib.wd_tsv_parse_lines(ctypes.byref(self._spec), text, starts.ctypes.data, lens.ctypes.data, idx.ctypes.data, n,
+                                           offsets.ctypes.data, keys.ctypes.data, keys.size, dense.ctypes.data, label.ctypes.data,
+                                           weight.ctypes.data, self.n_threads)
+        if nnz < 0:
+            raise ValueError(self._lib.wd_last_error().decode())
+        if nnz <= keys.size:
+            break
+        keys = np.empty(nnz, dtype=np.uint64)
+    self._key_guess = max(self._key_guess, int(nnz * 1.25) + 16)
+    return Batch(n, keys[:nnz], offsets, dense[:, :Nd] if Nd else None, None if self.is_pred else label,
+                 weight if (self.use_weight and not self.is_pred) else None)
+
+
 TsvReader._parse_into_ring = _parse_into_ring
+TsvReader.parse_indexed = _parse_indexed
 
 
 class Prefetcher(object):
@@ -233,18 +266,30 @@ def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=N
     if img_data_file:
         raise ValueError("image inputs are not supported by the B200 path (cnn_use_flag: 0)")
     reader = TsvReader(config, plan, is_pred=(mode == "pred"))
-    lines = []
+    lib = _native.lib()
+    # one image of all files + an index of its non-empty lines (wd_tsv_index_lines): sharding and shuffling permute INDICES, the
+    # parser reads each batch's lines in place (wd_tsv_parse_lines) — no per-line Python objects, no per-batch join
+    parts = []
     for f in list_files(csv_data_file):
         with open(f, "rb") as fh:
-            lines.extend(l for l in fh.read().split(b"\n") if l != b"")
+            parts.append(fh.read())
+    text = parts[0] if len(parts) == 1 else b"\n".join(parts)
+    del parts
+    n_all = lib.wd_tsv_index_lines(text, len(text), None, None, 0)
+    if n_all < 0:
+        raise ValueError(lib.wd_last_error().decode())
+    starts, lens = np.empty(max(n_all, 1), dtype=np.int64), np.empty(max(n_all, 1), dtype=np.int32)
+    lib.wd_tsv_index_lines(text, len(text), starts.ctypes.data, lens.ctypes.data, n_all)
+    order = np.arange(n_all, dtype=np.int64)
     if world > 1:
         # dataset.shard(num_workers, worker_index) (reference dataset.py:173-174): every world-th line.  Synchronous training
         # needs the same number of batches on every rank, so the few lines beyond a multiple of `world` are dropped.
-        per = len(lines) // world
-        lines = lines[rank::world][:per]
+        per = n_all // world
+        order = order[rank::world][:per]
     if mode == "train":
-        perm = np.random.Generator(np.random.Philox(seed)).permutation(len(lines))
-        lines = [lines[i] for i in perm]
+        perm = np.random.Generator(np.random.Philox(seed)).permutation(len(order))
+        order = order[perm]
+    order = np.ascontiguousarray(order)
     # pinned=True (estimator.train, which consumes batch by batch): parse into a ring of page-locked buffers so the host->device
     # refill of a batch slot is truly asynchronous; a yielded Batch stays valid for the next `depth - 1` batches
     ring = None
@@ -253,7 +298,7 @@ def input_fn(csv_data_file, img_data_file, mode, batch_size, config=None, plan=N
         ring = PinnedRing(batch_size, F, Nd, key_cap=batch_size * max(F, 1) * 4, depth=6)
 
     def batches():
-        for i in range(0, len(lines), batch_size):
-            yield reader.parse(lines[i:i + batch_size], ring=ring)
+        for i in range(0, len(order), batch_size):
+            yield reader.parse_indexed(text, starts, lens, order[i:i + batch_size], ring=ring)
 
     return batches()
