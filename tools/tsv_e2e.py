@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from wide_deep_b200.config import Config  # noqa: E402
-from wide_deep_b200.dataset import TsvReader, input_fn, list_files  # noqa: E402
+from wide_deep_b200.dataset import input_fn, list_files  # noqa: E402
 from wide_deep_b200.estimator import build_custom_estimator  # noqa: E402
 
 
@@ -39,8 +39,7 @@ def main():
         n_lines = src.count(b"\n") * args.repeat
         nbytes = len(src) * args.repeat
         est = build_custom_estimator(os.path.join(tmp, "model"), args.model_type, config=cfg, max_batch=args.batch)
-        # parser alone (same reader, same batch size, pageable buffers)
-        reader = TsvReader(cfg, est.plan)
+        # host pipeline alone (same input_fn, same batch size, pageable buffers): read + index + shuffle + parse / hash
         t0 = time.time()
         for _ in input_fn(path, None, "train", args.batch, config=cfg, plan=est.plan):      # file image -> line index -> shuffled batches
             pass
@@ -67,7 +66,7 @@ def main():
     print({"lines": n_lines, "mbytes": round(nbytes / 1e6, 1), "batch": args.batch,
            "host_pipeline_lines_per_s": round(n_lines / t_parse), "host_pipeline_MB_per_s": round(nbytes / 1e6 / t_parse, 1),
            "e2e_tsv_lines_per_s": round(n_lines / t_e2e), "step_only_lines_per_s": round(args.batch / t_step),
-           "note": "e2e = read file + split + shuffle (Python) + parse/hash (C++ threads, pinned ring, prefetch thread) + H2D + train step + "
+           "note": "e2e = read file + line index + shuffle + parse/hash (C++ worker pool, pinned ring, prefetch thread) + H2D + train step + "
                    "loss readback every step; no checkpoint inside the timed pass"})
 
 
