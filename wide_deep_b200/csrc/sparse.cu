@@ -409,9 +409,8 @@ int sparse_forward_emb(WdModel* m) {
 }
 
 // ------------------------------------------------------------------------------------ backward: grouping
-// keys/values for the two sorts: which = 0 embedding rows, 1 wide rows.  Non-participating entries get the
-// key `invalid` (= 1 << bits) so they sort behind every real row.
-// (key, value) pairs for the sort: key = row (invalid rows sort last), value = val_src[i], or the entry's index i without val_src.
+// (key, value) pairs for the two sorts (which = 0 embedding rows, 1 wide rows): key = row — non-participating entries get the key
+// `invalid` (= 1 << bits), so they sort behind every real row —, value = val_src[i], or the entry's index i without val_src.
 // The batch's own lists carry the entry's cell index bc = b * C + c (e_bc) as the value: that is all the gradient sums need to
 // find an occurrence's gradient, so they read it straight from the sorted list instead of chasing e_bc[index] per occurrence.
 __global__ void sort_keys_kernel(const int32_t* __restrict__ d_nnz, const uint32_t* __restrict__ e_row, uint32_t invalid,
@@ -425,13 +424,10 @@ __global__ void sort_keys_kernel(const int32_t* __restrict__ d_nnz, const uint32
 }
 
 
-
 // ---- per unique row: g = ordered sum of its occurrences' gradients.
 // Rows touched at most kChunk times are summed by one lane group directly.  Hotter rows (small tables,
 // skewed ids) are split into chunks of kChunk occurrences that are summed in parallel and then combined in
 // chunk order, so the result stays deterministic and no single group walks thousands of occurrences.
-
-
 
 // embedding rows: contribution of occurrence j = dX0[b, x0_off : x0_off + dim] / bag_size(b, column)
 // 8 lanes per work item, each lane covers float4 chunks lig, lig+8, ... of the row.  One launch covers both kinds of work item:
