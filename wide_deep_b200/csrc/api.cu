@@ -1062,7 +1062,7 @@ static bool same_view(const DevBatch& a, const DevBatch& b) {
     return a.B == b.B && a.cat_offsets == b.cat_offsets && a.cat_keys == b.cat_keys && a.dense == b.dense && a.label == b.label && a.weight == b.weight;
 }
 
-// One whole train step on the current slot.  After two eager steps the step (both streams, ~65 kernels, no host sync)
+// One whole train step on the current slot.  After two eager steps the step (three streams, ~55 kernels, no host sync)
 // is captured once into a CUDA graph per batch slot and replayed: launch gaps between the many small kernels
 // disappear and the host cost of a step becomes one cudaGraphLaunch.
 static int train_current(WdModel* m, float* loss_out) {
