@@ -94,6 +94,11 @@ def test_crelu_shapes_match_oracle_and_all_ten_activation_names_parse():
         assert shapes == {k: v.shape for k, v in om.params.items() if k.startswith("dnn/dnn_1/")}, mode
         assert shapes["dnn/dnn_1/hiddenlayer_0/kernel"] == (p.d0, hidden[0])
         assert shapes["dnn/dnn_1/hiddenlayer_0/batch_normalization/gamma"] == (2 * hidden[0],)
+        desc, keep = p.to_c()                                        # the library receives the conf's units and WD_ACT_CRELU (= 9)
+        assert desc.activation == 9 and ACTS[desc.activation] == "crelu"
+        import ctypes
+        hu = ctypes.cast(desc.hidden_units, ctypes.POINTER(ctypes.c_int32))
+        assert [hu[i] for i in range(len(hidden))] == list(hidden)
     with pytest.raises(ValueError):
         small = small_conf(act="swish")
         Plan(small[0], small[1], small[2], "wide_deep", max_batch=8)
